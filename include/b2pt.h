@@ -1,0 +1,323 @@
+/*
+ * b2pt.h -- C ABI of the B200-native wavefront path tracer.
+ *
+ * This is the drop-in boundary for ONE hot path of nkkk98/MyGPURaytracer: the
+ * per-iteration wavefront loop behind
+ *
+ *     void pathtraceInit(Scene*);                          apps/src/pathtrace.h:7
+ *     void pathtraceFree();                                apps/src/pathtrace.h:8
+ *     void pathtrace(uchar4* pbo, int frame, int iter);    apps/src/pathtrace.h:9
+ *     PerformanceTimer& timer();                           apps/src/pathtrace.h:6
+ *     void sendToGPU(uchar4* pbo, int iter);               apps/src/pathtrace.h:10
+ *
+ * Everything here is plain C: PODs, pointers and sizes.  No C++ types, no
+ * torch types, no glm.  Functions return 0 (B2PT_OK) or a negative error code
+ * and never call exit() (the reference's checkCUDAError does,
+ * apps/src/pathtrace.cu:46-64).  b2pt_last_error() returns the text of the
+ * last failure on the calling thread.
+ *
+ * Layout conventions
+ *   - matrices are 16 floats, column-major (m[col*4+row]), the layout of
+ *     glm::mat4 in the reference's Geom (apps/src/sceneStructs.h:50-70);
+ *   - vectors are tightly packed floats;
+ *   - images are W*H*3 floats, index = x + y*W (apps/src/pathtrace.cu:255).
+ */
+#ifndef B2PT_H_
+#define B2PT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2PT_ABI_VERSION 1
+
+/* ---- error codes ------------------------------------------------------ */
+enum {
+  B2PT_OK = 0,
+  B2PT_ERR_INVALID = -1,  /* bad argument / inconsistent scene           */
+  B2PT_ERR_CUDA = -2,     /* a CUDA runtime call failed                  */
+  B2PT_ERR_NOMEM = -3,    /* host or device allocation failed            */
+  B2PT_ERR_IO = -4,       /* scene / OBJ / texture file problem          */
+  B2PT_ERR_STATE = -5,    /* call made in the wrong state                */
+  B2PT_ERR_RANGE = -6     /* index / capacity out of range               */
+};
+
+/* ---- scene PODs -------------------------------------------------------- */
+
+/* enum GeomType, apps/src/sceneStructs.h:10-15 (same numeric values). */
+enum { B2PT_SPHERE = 0, B2PT_CUBE = 1, B2PT_TRIANGLE = 2, B2PT_OBJ = 3 };
+
+/* struct Material, apps/src/sceneStructs.h:72-82 (same 44-byte layout). */
+typedef struct B2ptMaterial {
+  float color[3];
+  float specular_exponent;
+  float specular_color[3];
+  float has_reflective;
+  float has_refractive;
+  float index_of_refraction;
+  float emittance;
+} B2ptMaterial;
+
+/* struct Texture, apps/src/sceneStructs.h:36-48.  Raw 8-bit interleaved
+ * texels, row 0 first (the reference flips images at load,
+ * apps/src/scene.cpp:133; the bytes here are post-flip). */
+typedef struct B2ptTexture {
+  int32_t width;
+  int32_t height;
+  int32_t channels; /* 0 = "no texture" (Texture() ctor) */
+  int32_t reserved;
+  const uint8_t* texels; /* width*height*channels bytes, host memory */
+} B2ptTexture;
+
+/* struct Geom, apps/src/sceneStructs.h:50-70, minus the fields the hot path
+ * never reads (translation/rotation/scale/minPos/maxPos).  Faces and
+ * textures are referenced by index instead of by device pointer. */
+typedef struct B2ptGeom {
+  int32_t type;        /* B2PT_SPHERE / B2PT_CUBE / B2PT_TRIANGLE / B2PT_OBJ */
+  int32_t material_id; /* Geom::materialid */
+  float transform[16];
+  float inverse_transform[16];
+  float inv_transpose[16];
+  int32_t face_begin; /* first face of this geom in the scene face arrays */
+  int32_t face_count; /* Geom::faceSize */
+  int32_t tex_kd;     /* index into B2ptScene::textures or -1 */
+  int32_t tex_ks;
+  int32_t tex_bump;
+  int32_t tex_ke;
+} B2ptGeom;
+
+/* struct Camera, apps/src/sceneStructs.h:84-93 (same 84-byte layout).
+ * These are the values pathtrace() actually reads, i.e. AFTER the orbit
+ * recompute of apps/src/main.cpp:222-240; `right` is NOT normalised there. */
+typedef struct B2ptCamera {
+  int32_t resolution[2];
+  float position[3];
+  float look_at[3];
+  float view[3];
+  float up[3];
+  float right[3];
+  float fov[2];
+  float pixel_length[2];
+} B2ptCamera;
+
+/* A whole scene.  Faces of all OBJ geoms live in two flat arrays:
+ *   face_pos: 9 floats per face  (Face::v0/v1/v2 .position)
+ *   face_uv : 6 floats per face  (Face::v0/v1/v2 .texcoord)
+ * which is the only part of the reference's 156-byte Face the path reads
+ * (apps/src/intersections.h:216-249). */
+typedef struct B2ptScene {
+  int32_t n_geoms;
+  int32_t n_materials;
+  int32_t n_textures;
+  int32_t n_faces;
+  const B2ptGeom* geoms;
+  const B2ptMaterial* materials;
+  const B2ptTexture* textures;
+  const float* face_pos;
+  const float* face_uv;
+  B2ptCamera camera;
+  int32_t trace_depth; /* RenderState::traceDepth */
+  int32_t iterations;  /* RenderState::iterations (informational) */
+} B2ptScene;
+
+/* ---- options ------------------------------------------------------------ */
+
+/* Trigonometry used by the cosine-hemisphere / lens sampling
+ * (apps/src/interactions.h:42-43, apps/src/pathtrace.cu:238):
+ *   NATIVE   - CUDA libdevice sinf/cosf/pow: what the reference's kernels call;
+ *   PORTABLE - a fixed +,* only polynomial shared bit-for-bit with the CPU
+ *              oracle (<= 2 ulp from NATIVE); used by the parity tests. */
+enum { B2PT_TRIG_NATIVE = 0, B2PT_TRIG_PORTABLE = 1 };
+
+/* RNG keying.  SLOT reproduces the reference: the shader seeds with the
+ * array slot after sort+compaction (apps/src/pathtrace.cu:467).  PIXEL keys
+ * a counter on (pixel, iteration, depth) and cannot match the reference
+ * per iteration (only the converged image). */
+enum { B2PT_RNG_SLOT = 0, B2PT_RNG_PIXEL = 1 };
+
+typedef struct B2ptOptions {
+  uint32_t struct_size;       /* sizeof(B2ptOptions), for ABI growth       */
+  int32_t device;             /* CUDA device ordinal                        */
+  int32_t antialiasing;       /* ANTIALIASING, pathtrace.cu:39   (def 1)    */
+  int32_t depth_of_field;     /* DEPTH_OF_FIELD, pathtrace.cu:36 (def 0)    */
+  float lens_radius;          /* pathtrace.cu:279 (def 0.8)                 */
+  float focal_distance;       /* pathtrace.cu:280 (def 11)                  */
+  int32_t sort_by_material;   /* SORT_BY_MATERIAL, pathtrace.cu:38 (def 1)  */
+  int32_t cache_first_bounce; /* intended semantics of pathtrace.cu:586-610;
+                                 only honoured when AA and DOF are off (def 0) */
+  int32_t trig_mode;          /* B2PT_TRIG_*  (def NATIVE)                  */
+  int32_t rng_mode;           /* B2PT_RNG_*   (def SLOT)                    */
+  int32_t use_bvh;            /* 1 = LBVH traversal, 0 = brute force (def 1)*/
+  int32_t record_stages;      /* 1 = keep per-depth stage dumps of the next
+                                 b2pt_render call readable (def 0)          */
+  int32_t use_graph;          /* 1 = replay the iteration as a CUDA graph   */
+  int32_t reserved[8];
+} B2ptOptions;
+
+/* Fills `opt` with the defaults above (the reference's compile-time macros). */
+void b2pt_default_options(B2ptOptions* opt);
+
+/* ---- context ------------------------------------------------------------- */
+typedef struct B2ptCtx B2ptCtx;
+
+/* pathtraceInit (apps/src/pathtrace.cu:130-194): uploads the scene as SoA
+ * buffers, builds the LBVH of every OBJ geom on the GPU, allocates the path
+ * state, hit records and the zeroed accumulation / albedo images. */
+int b2pt_create(const B2ptScene* scene, const B2ptOptions* opt, B2ptCtx** out);
+
+/* pathtraceFree (apps/src/pathtrace.cu:196-223).  NULL is accepted. */
+void b2pt_destroy(B2ptCtx* ctx);
+
+/* Replace the camera (the reference re-runs pathtraceInit when the camera
+ * moves, apps/src/main.cpp:222-248) and zero the accumulators. */
+int b2pt_set_camera(B2ptCtx* ctx, const B2ptCamera* cam);
+
+/* Zero the accumulation and albedo images (what Free+Init does to them). */
+int b2pt_reset_accum(B2ptCtx* ctx);
+
+/* Render iterations iter_first, iter_first+iter_stride, ... (iter_count of
+ * them) and add each into the device accumulation image:
+ *     image[pixel] += color * PI          (apps/src/pathtrace.cu:501-510)
+ * One call with (iter, 1, 1) is the device part of one reference pathtrace()
+ * call.  iter_stride > 1 is the samples-per-pixel sharding used across GPUs:
+ * rank r of R renders (r+1, count, R).  Asynchronous on the context's stream. */
+int b2pt_render(B2ptCtx* ctx, int32_t iter_first, int32_t iter_count, int32_t iter_stride);
+
+/* Wait for everything queued on the context's stream. */
+int b2pt_sync(B2ptCtx* ctx);
+
+/* The D2H half of pathtrace() (apps/src/pathtrace.cu:663-668): copy the
+ * un-normalised running sum and the iteration-1 albedo to host memory
+ * (W*H*3 floats each; either may be NULL).  Synchronous. */
+int b2pt_read_accum(B2ptCtx* ctx, float* image_host, float* albedo_host);
+
+/* Exactly one reference pathtrace(pbo, frame, iter) call: render `iter`, then
+ * copy image and albedo to the host buffers (scene->state.image / .albedo). */
+int b2pt_pathtrace(B2ptCtx* ctx, int32_t iter, float* image_host, float* albedo_host);
+
+/* Device pointers of the accumulators (W*H*3 floats), for zero-copy hand-off
+ * to a collective or a device-side denoiser. */
+float* b2pt_device_image(B2ptCtx* ctx);
+float* b2pt_device_albedo(B2ptCtx* ctx);
+
+/* Accumulate into caller-owned device memory (e.g. an NCCL-registered
+ * buffer) instead of the context's own image.  NULL restores the default. */
+int b2pt_set_device_image(B2ptCtx* ctx, float* image_dev);
+
+/* The CUDA stream (cudaStream_t) all work of this context is queued on. */
+void* b2pt_stream(B2ptCtx* ctx);
+
+/* Mirror of timer().getGpuElapsedTimeForPreviousOperation()
+ * (apps/src/main.cpp:263): milliseconds of the depth loop of the last
+ * rendered iteration (the window of apps/src/pathtrace.cu:583-653). */
+float b2pt_last_loop_ms(B2ptCtx* ctx);
+
+/* sendImageToPBO / sendDenosiedImageToPBO (apps/src/pathtrace.cu:73-116):
+ * rgba8_dev[i] = clamp(int(pix / iter * 255.0)), w = 0.  `src_dev` NULL means
+ * the accumulation image; iter <= 0 means "already normalised" (the denoised
+ * variant).  rgba8_dev is device memory, W*H*4 bytes. */
+int b2pt_tonemap_rgba8(B2ptCtx* ctx, const float* src_dev, int32_t iter, uint8_t* rgba8_dev);
+
+/* ---- statistics and stage dumps (parity / measurement) --------------------- */
+
+/* Live path counts of the last rendered iteration: n_live[d] = number of
+ * paths entering depth d (n_live[0] = W*H).  Returns the number of depths
+ * written (<= cap).  Synchronises. */
+int b2pt_live_counts(B2ptCtx* ctx, int32_t* n_live, int32_t cap);
+
+/* Kernel launches issued by this context since creation. */
+int64_t b2pt_launch_count(B2ptCtx* ctx);
+
+/* Stage ids for b2pt_stage_read; all arrays are in slot order. */
+enum {
+  B2PT_STAGE_RAY_ORIGIN = 0, /* float[n*3]  rays entering depth d (pre-sort)  */
+  B2PT_STAGE_RAY_DIR = 1,    /* float[n*3]                                    */
+  B2PT_STAGE_RAY_PIXEL = 2,  /* int32[n]    pixelIndex, pre-sort order        */
+  B2PT_STAGE_HIT_T = 3,      /* float[n]    -1 on a miss, pre-sort order      */
+  B2PT_STAGE_HIT_NORMAL = 4, /* float[n*3]                                    */
+  B2PT_STAGE_HIT_UV = 5,     /* float[n*2]  valid for OBJ hits only           */
+  B2PT_STAGE_HIT_GEOM = 6,   /* int32[n]    -1 on a miss                      */
+  B2PT_STAGE_HIT_FACE = 7,   /* int32[n]    face within the geom, -1 if none  */
+  B2PT_STAGE_HIT_MATERIAL = 8, /* int32[n]  0 on a miss (the memset value)    */
+  B2PT_STAGE_SORT_PERM = 9,  /* int32[n]    sorted slot j <- pre-sort slot    */
+  B2PT_STAGE_SHADED_COLOR = 10, /* float[n*3] after shade, sorted order       */
+  B2PT_STAGE_SHADED_BOUNCES = 11, /* int32[n] remainingBounces after shade    */
+  B2PT_STAGE_SHADED_ORIGIN = 12,  /* float[n*3]                               */
+  B2PT_STAGE_SHADED_DIR = 13,     /* float[n*3]                               */
+  B2PT_STAGE_PARTITION_PIXEL = 14 /* int32[n] pixelIndex after the stable
+                                     partition: live prefix then dead tail   */
+};
+
+/* Copy one stage array of depth `depth` of the last iteration rendered with
+ * record_stages=1 into host memory.  `bytes` is the capacity of `dst`.
+ * Returns the number of bytes written or a negative error. */
+int64_t b2pt_stage_read(B2ptCtx* ctx, int32_t depth, int32_t stage, void* dst, int64_t bytes);
+
+/* ---- BVH introspection ------------------------------------------------------ */
+typedef struct B2ptBvhInfo {
+  int32_t n_faces;
+  int32_t n_nodes;
+  int32_t max_depth;
+  float build_ms; /* Morton + radix sort + hierarchy + refit, device time */
+} B2ptBvhInfo;
+int b2pt_bvh_info(B2ptCtx* ctx, int32_t geom, B2ptBvhInfo* info);
+
+/* ---- standalone device primitives -------------------------------------------
+ * The scan / compaction / sort kernels of the wavefront loop, callable on
+ * host arrays.  They serve the surface of the reference's side library
+ * StreamCompaction::{Efficient,Naive,Thrust}::scan / compact
+ * (apps/stream_compaction/efficient.h:8-11) and make the kernels unit-testable.
+ */
+
+/* Exclusive prefix sum of n ints (decoupled look-back single pass). */
+int b2pt_scan_exclusive_i32(int32_t n, int32_t* out_host, const int32_t* in_host);
+
+/* Stable compaction of the non-zero elements; returns the count or <0. */
+int b2pt_compact_nonzero_i32(int32_t n, int32_t* out_host, const int32_t* in_host);
+
+/* Stable partition permutation on a predicate array: perm_host[k] is the
+ * source index of output slot k (flag!=0 first, both halves stable), the
+ * permutation thrust::stable_partition applies at pathtrace.cu:649.
+ * Returns the number of kept elements or <0. */
+int b2pt_partition_perm(int32_t n, const uint8_t* flags_host, int32_t* perm_host);
+
+/* Stable sort permutation by DESCENDING key (pathtrace.cu:512-516,612):
+ * perm_host[k] = source index of sorted slot k.  keys must be in [0, 65535]. */
+int b2pt_sort_desc_perm(int32_t n, const int32_t* keys_host, int32_t* perm_host);
+
+/* Stable LSD radix sort of 32-bit keys with 32-bit values (onesweep, 4 passes
+ * of 8 bits); the sort behind the LBVH Morton ordering. */
+int b2pt_radix_sort_pairs_u32(int32_t n, uint32_t* keys_host, uint32_t* vals_host);
+
+/* ---- scene loader -------------------------------------------------------------
+ * The scenes/<name>.txt format of apps/src/scene.cpp (MATERIAL / CAMERA / OBJECT
+ * blocks), OBJ+MTL meshes and 8-bit textures.  The camera returned is the one
+ * the renderer uses, i.e. after the orbit recompute of main.cpp:67-81,222-240.
+ */
+typedef struct B2ptLoadedScene B2ptLoadedScene;
+
+typedef struct B2ptLoadOverrides {
+  int32_t width;      /* >0 overrides RES x (pixelLength is recomputed)      */
+  int32_t height;     /* >0 overrides RES y                                  */
+  int32_t iterations; /* >0 overrides ITERATIONS                             */
+  int32_t depth;      /* >0 overrides DEPTH                                  */
+} B2ptLoadOverrides;
+
+int b2pt_scene_load(const char* path, const B2ptLoadOverrides* ov, B2ptLoadedScene** out);
+const B2ptScene* b2pt_scene_view(const B2ptLoadedScene* s);
+const char* b2pt_scene_image_name(const B2ptLoadedScene* s); /* FILE line */
+void b2pt_scene_free(B2ptLoadedScene* s);
+
+/* ---- misc ------------------------------------------------------------------------- */
+const char* b2pt_last_error(void);
+int b2pt_abi_version(void);
+/* Number of visible CUDA devices, or a negative error. */
+int b2pt_device_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2PT_H_ */
