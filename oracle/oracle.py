@@ -71,6 +71,7 @@ def lib() -> C.CDLL:
         L.oracle_render.argtypes = [C.POINTER(abi.Scene), C.POINTER(abi.Options), i32, i32, i32, vp, vp, vp, vp]
         L.oracle_num_threads.restype = C.c_int
         L.oracle_set_num_threads.argtypes = [C.c_int]
+        L.oracle_set_dof_arg_order.argtypes = [C.c_int]
         _lib = L
     return _lib
 
@@ -288,6 +289,10 @@ def render(scene: PodScene, opt: abi.Options, iter_first: int = 1, count: int = 
     if rc != 0:
         raise RuntimeError(f"oracle_render failed: {rc}")
     return image, albedo, n_live, int(seg.value)
+
+
+def set_dof_arg_order(right_to_left: bool) -> None:
+    lib().oracle_set_dof_arg_order(1 if right_to_left else 0)
 
 
 def num_threads() -> int:

@@ -365,6 +365,9 @@ void oracle_hemisphere(const float n[3], uint32_t* rng, int32_t trig_mode, float
 /* stages                                                                     */
 /* ------------------------------------------------------------------------- */
 
+static int g_dof_args_right_to_left = 0;
+void oracle_set_dof_arg_order(int right_to_left) { g_dof_args_right_to_left = right_to_left; }
+
 /* ConcentricSampleDisk, apps/src/pathtrace.cu:225-239. */
 static void concentric_disk(float px, float py, int32_t trig_mode, float* ox, float* oy) {
   float ux = 2.f * px - 1.0f, uy = 2.f * py - 1.0f;
@@ -407,11 +410,19 @@ int oracle_generate(const B2ptCamera* cam, const B2ptOptions* opt, int32_t iter,
       v3 d = normalize3(sub(sub(view, muls(muls(right, cam->pixel_length[0]), antia_x - (float)W * 0.5f)),
                             muls(muls(up, cam->pixel_length[1]), antia_y - (float)H * 0.5f)));
       if (opt->depth_of_field && opt->lens_radius > 0) {
-        /* glm::vec2(uDOF(rng), uDOF(rng)): argument evaluation order is
-         * unspecified in C++; nvcc's device and host passes both evaluate
-         * left to right here (checked against oracle/_ref). */
-        float u0 = oracle_uniform(&rng, 0.0f, 1.0f);
-        float u1 = oracle_uniform(&rng, 0.0f, 1.0f);
+        /* glm::vec2(uDOF(rng), uDOF(rng)): the evaluation order of the two
+         * arguments is unspecified in C++.  g++ (the reference's host pass,
+         * oracle/_ref/ref_cpu) draws the SECOND argument first; nvcc's device
+         * front end draws left to right (oracle/_ref/ref_gpu_dof).  The
+         * oracle follows the device unless told otherwise. */
+        float u0, u1;
+        if (g_dof_args_right_to_left) {
+          u1 = oracle_uniform(&rng, 0.0f, 1.0f);
+          u0 = oracle_uniform(&rng, 0.0f, 1.0f);
+        } else {
+          u0 = oracle_uniform(&rng, 0.0f, 1.0f);
+          u1 = oracle_uniform(&rng, 0.0f, 1.0f);
+        }
         float lx, ly;
         concentric_disk(u0, u1, opt->trig_mode, &lx, &ly);
         lx = opt->lens_radius * lx;

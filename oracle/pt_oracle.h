@@ -94,6 +94,11 @@ int oracle_gather(int32_t n, float* image, const float* color, const int32_t* pi
 int oracle_render(const B2ptScene* s, const B2ptOptions* opt, int32_t iter_first, int32_t count,
                   int32_t stride, float* image, float* albedo, int32_t* n_live, int64_t* segments);
 
+/* Order in which the two lens draws of glm::vec2(uDOF(rng), uDOF(rng))
+ * (apps/src/pathtrace.cu:285) are taken: 0 = left to right (nvcc device
+ * code), 1 = right to left (g++ host build of the same line). */
+void oracle_set_dof_arg_order(int right_to_left);
+
 /* Number of OpenMP threads the stage loops will use. */
 int oracle_num_threads(void);
 void oracle_set_num_threads(int n);
