@@ -1,0 +1,345 @@
+"""Host-side mirror of the reference's render API over the C ABI.
+
+The reference exposes five free functions with file-static state
+(apps/src/pathtrace.h:6-10) and a ``Scene`` class with public vectors
+(apps/src/scene.h:12-32).  This module keeps those names and their meaning:
+
+========================  =====================================================
+reference                 here
+========================  =====================================================
+``new Scene(path)``       :class:`Scene` (``scene.geoms``, ``.materials``,
+                          ``.state.image``, ``.state.albedo``, ...)
+``pathtraceInit(scene)``  :func:`pathtraceInit`
+``pathtrace(pbo, f, it)`` :func:`pathtrace` -- renders iteration ``it`` and
+                          copies the running sum and the albedo AOV into
+                          ``scene.state.image`` / ``.albedo`` exactly as
+                          apps/src/pathtrace.cu:663-668 does
+``pathtraceFree()``       :func:`pathtraceFree` (safe before the first Init,
+                          apps/src/main.cpp:245-248)
+``timer()``               :func:`timer` -> object with
+                          ``getGpuElapsedTimeForPreviousOperation()``
+``sendToGPU(pbo, iter)``  :func:`sendToGPU` (tone-map into an RGBA8 buffer)
+========================  =====================================================
+
+:class:`Renderer` is the explicit-context form of the same calls (several
+contexts, one per GPU, can coexist; it also exposes the batched
+``render(iter_first, count, stride)`` used for samples-per-pixel sharding).
+
+Everything computes on the GPU through ``libb2pt.so``.  There is no CPU
+fallback: if the library has not been built, or no CUDA device is present,
+the calls raise :class:`B2ptError`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Dict, List, Optional
+
+import numpy as np
+
+from . import abi
+from .podscene import PodScene
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb2pt.so")
+_lib: Optional[C.CDLL] = None
+
+
+class B2ptError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"b2pt error {code} ({abi.ERR_NAMES.get(code, '?')}): {message}")
+        self.code = code
+
+
+def load_library() -> C.CDLL:
+    """dlopen ``libb2pt.so`` and check every symbol of ``include/b2pt.h``."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B2ptError(abi.B2PT_OK - 5, f"{LIB_PATH} is missing: run `python -m mygpuraytracer_b200.build` "
+                                             "(there is no CPU fallback)")
+        _lib = abi.declare(C.CDLL(LIB_PATH))
+    return _lib
+
+
+def _check(rc: int) -> int:
+    if rc < 0:
+        raise B2ptError(rc, load_library().b2pt_last_error().decode("utf-8", "replace"))
+    return rc
+
+
+def device_count() -> int:
+    return _check(load_library().b2pt_device_count())
+
+
+# ---------------------------------------------------------------------------------------
+# Scene
+# ---------------------------------------------------------------------------------------
+class RenderState:
+    """RenderState, apps/src/sceneStructs.h:95-103."""
+
+    def __init__(self, pod: PodScene, image_name: str):
+        self.camera = pod.camera
+        self.iterations = pod.iterations
+        self.traceDepth = pod.trace_depth
+        self.imageName = image_name
+        n = pod.n_pixels
+        self.image = np.zeros((n, 3), np.float32)
+        self.albedo = np.zeros((n, 3), np.float32)
+        self.output = np.zeros((n, 3), np.float32)
+
+
+class Scene:
+    """``Scene(filename)``, apps/src/scene.cpp:10-36, via ``b2pt_scene_load``.
+
+    ``width``/``height``/``iterations``/``depth`` override the RES /
+    ITERATIONS / DEPTH lines (every shipped scene says 800x800, 5000, 8).
+    A :class:`Scene` can also wrap an existing :class:`PodScene`.
+    """
+
+    def __init__(self, filename: Optional[str] = None, *, width: int = 0, height: int = 0, iterations: int = 0,
+                 depth: int = 0, pod: Optional[PodScene] = None):
+        if pod is None:
+            if filename is None:
+                raise ValueError("Scene needs a file name or a PodScene")
+            lib = load_library()
+            ov = abi.LoadOverrides(width, height, iterations, depth)
+            h = C.c_void_p()
+            _check(lib.b2pt_scene_load(os.fsencode(filename), C.byref(ov), C.byref(h)))
+            try:
+                pod = PodScene.from_ctypes(lib.b2pt_scene_view(h).contents)
+                name = lib.b2pt_scene_image_name(h).decode()
+            finally:
+                lib.b2pt_scene_free(h)
+        else:
+            name = "pod"
+        self.pod = pod
+        self.state = RenderState(pod, name)
+
+    # the reference's public vectors
+    @property
+    def geoms(self):
+        return self.pod.geoms
+
+    @property
+    def materials(self):
+        return self.pod.materials
+
+    @property
+    def allFaces(self):
+        return [self.pod.face_pos[g["face_begin"]: g["face_begin"] + g["face_count"]] for g in self.pod.geoms]
+
+
+# ---------------------------------------------------------------------------------------
+# Renderer: one context
+# ---------------------------------------------------------------------------------------
+class Renderer:
+    def __init__(self, scene, options: Optional[abi.Options] = None, **opt_kw):
+        self.lib = load_library()
+        self.pod: PodScene = scene.pod if isinstance(scene, Scene) else scene
+        self.options = options if options is not None else abi.default_options(**opt_kw)
+        self._cscene = self.pod.as_ctypes()
+        self._h = C.c_void_p()
+        _check(self.lib.b2pt_create(C.byref(self._cscene), C.byref(self.options), C.byref(self._h)))
+        self.n_pixels = self.pod.n_pixels
+
+    # -- lifetime ------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.b2pt_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # pragma: no cover - interpreter shutdown
+            pass
+
+    # -- rendering -----------------------------------------------------------------------
+    def render(self, iter_first: int = 1, count: int = 1, stride: int = 1) -> None:
+        _check(self.lib.b2pt_render(self._h, iter_first, count, stride))
+
+    def sync(self) -> None:
+        _check(self.lib.b2pt_sync(self._h))
+
+    def read(self, image: Optional[np.ndarray] = None, albedo: Optional[np.ndarray] = None, want_albedo: bool = True):
+        if image is None:
+            image = np.empty((self.n_pixels, 3), np.float32)
+        if albedo is None and want_albedo:
+            albedo = np.empty((self.n_pixels, 3), np.float32)
+        _check(self.lib.b2pt_read_accum(self._h, image.ctypes.data, albedo.ctypes.data if albedo is not None else None))
+        return image, albedo
+
+    def pathtrace(self, iteration: int, image: np.ndarray, albedo: Optional[np.ndarray]) -> None:
+        _check(self.lib.b2pt_pathtrace(self._h, iteration, image.ctypes.data,
+                                       albedo.ctypes.data if albedo is not None else None))
+
+    def reset(self) -> None:
+        _check(self.lib.b2pt_reset_accum(self._h))
+
+    def set_camera(self, camera: np.ndarray) -> None:
+        cam = abi.Camera()
+        C.memmove(C.byref(cam), np.ascontiguousarray(camera).ctypes.data, C.sizeof(abi.Camera))
+        _check(self.lib.b2pt_set_camera(self._h, C.byref(cam)))
+
+    def last_loop_ms(self) -> float:
+        return float(self.lib.b2pt_last_loop_ms(self._h))
+
+    def live_counts(self) -> np.ndarray:
+        buf = np.zeros(64, np.int32)
+        k = _check(self.lib.b2pt_live_counts(self._h, buf.ctypes.data_as(C.POINTER(C.c_int32)), 64))
+        return buf[:k].copy()
+
+    def launch_count(self) -> int:
+        return int(self.lib.b2pt_launch_count(self._h))
+
+    # -- zero-copy hand-off ----------------------------------------------------------------
+    def device_image_ptr(self) -> int:
+        return int(self.lib.b2pt_device_image(self._h) or 0)
+
+    def device_albedo_ptr(self) -> int:
+        return int(self.lib.b2pt_device_albedo(self._h) or 0)
+
+    def set_device_image_ptr(self, ptr: int) -> None:
+        _check(self.lib.b2pt_set_device_image(self._h, C.c_void_p(ptr)))
+
+    def stream_ptr(self) -> int:
+        return int(self.lib.b2pt_stream(self._h) or 0)
+
+    def tonemap_rgba8(self, dst_ptr: int, iteration: int, src_ptr: int = 0) -> None:
+        _check(self.lib.b2pt_tonemap_rgba8(self._h, C.c_void_p(src_ptr) if src_ptr else None, iteration,
+                                           C.c_void_p(dst_ptr)))
+
+    # -- parity / introspection --------------------------------------------------------------
+    def stage(self, depth: int, name: str) -> np.ndarray:
+        sid, dt, cols = abi.STAGES[name]
+        cap = self.n_pixels * cols
+        buf = np.empty(cap, dt)
+        got = self.lib.b2pt_stage_read(self._h, depth, sid, buf.ctypes.data, buf.nbytes)
+        if got < 0:
+            _check(int(got))
+        n = got // 4 // cols
+        out = buf[: n * cols].copy()
+        return out.reshape(n, cols) if cols > 1 else out
+
+    def stages(self) -> List[Dict[str, np.ndarray]]:
+        """All recorded stage arrays of the last iteration (needs record_stages=1)."""
+        res = []
+        for d in range(max(self.pod.trace_depth, 1)):
+            try:
+                n = len(self.stage(d, "ray_pixel"))
+            except B2ptError:
+                break
+            if n == 0:
+                break
+            res.append({name: self.stage(d, name) for name in abi.STAGES})
+        return res
+
+    def bvh_info(self, geom: int) -> abi.BvhInfo:
+        info = abi.BvhInfo()
+        _check(self.lib.b2pt_bvh_info(self._h, geom, C.byref(info)))
+        return info
+
+
+# ---------------------------------------------------------------------------------------
+# standalone primitives (apps/stream_compaction surface)
+# ---------------------------------------------------------------------------------------
+def scan_exclusive(a: np.ndarray) -> np.ndarray:
+    a = np.ascontiguousarray(a, np.int32)
+    out = np.empty_like(a)
+    _check(load_library().b2pt_scan_exclusive_i32(len(a), out.ctypes.data, a.ctypes.data))
+    return out
+
+
+def compact_nonzero(a: np.ndarray) -> np.ndarray:
+    a = np.ascontiguousarray(a, np.int32)
+    out = np.empty_like(a)
+    k = _check(load_library().b2pt_compact_nonzero_i32(len(a), out.ctypes.data, a.ctypes.data))
+    return out[:k].copy()
+
+
+def partition_perm(flags: np.ndarray):
+    f = np.ascontiguousarray(flags, np.uint8)
+    perm = np.empty(len(f), np.int32)
+    k = _check(load_library().b2pt_partition_perm(len(f), f.ctypes.data, perm.ctypes.data))
+    return perm, k
+
+
+def sort_desc_perm(keys: np.ndarray) -> np.ndarray:
+    k = np.ascontiguousarray(keys, np.int32)
+    perm = np.empty(len(k), np.int32)
+    _check(load_library().b2pt_sort_desc_perm(len(k), k.ctypes.data, perm.ctypes.data))
+    return perm
+
+
+def radix_sort_pairs(keys: np.ndarray, vals: np.ndarray):
+    k = np.ascontiguousarray(keys, np.uint32).copy()
+    v = np.ascontiguousarray(vals, np.uint32).copy()
+    _check(load_library().b2pt_radix_sort_pairs_u32(len(k), k.ctypes.data, v.ctypes.data))
+    return k, v
+
+
+# ---------------------------------------------------------------------------------------
+# the reference's five free functions (global state, like apps/src/pathtrace.cu:118-128)
+# ---------------------------------------------------------------------------------------
+_hst_scene: Optional[Scene] = None
+_renderer: Optional[Renderer] = None
+_options_for_next_init: Optional[abi.Options] = None
+
+
+class _Timer:
+    """``timer()``: only the GPU stopwatch of the depth loop is reproduced."""
+
+    def getGpuElapsedTimeForPreviousOperation(self) -> float:
+        return _renderer.last_loop_ms() if _renderer is not None else 0.0
+
+
+_timer = _Timer()
+
+
+def timer() -> _Timer:
+    return _timer
+
+
+def set_options(options: Optional[abi.Options]) -> None:
+    """Options the next :func:`pathtraceInit` uses (the reference's macros are compile time)."""
+    global _options_for_next_init
+    _options_for_next_init = options
+
+
+def pathtraceInit(scene: Scene) -> None:
+    global _hst_scene, _renderer
+    if _renderer is not None:
+        _renderer.close()
+    _hst_scene = scene
+    _renderer = Renderer(scene, _options_for_next_init)
+
+
+def pathtraceFree() -> None:
+    global _renderer, _hst_scene
+    if _renderer is not None:
+        _renderer.close()
+    _renderer = None
+    _hst_scene = None
+
+
+def pathtrace(pbo, frame: int, iteration: int) -> None:
+    """One reference ``pathtrace(pbo, frame, iter)`` call: render, then D2H of
+    ``image`` and ``albedo`` into the scene's RenderState.  ``pbo`` and
+    ``frame`` are accepted and ignored, as in the reference's AI_DENOISE build."""
+    if _renderer is None or _hst_scene is None:
+        raise B2ptError(-5, "pathtrace() before pathtraceInit()")
+    _renderer.pathtrace(iteration, _hst_scene.state.image, _hst_scene.state.albedo)
+
+
+def sendToGPU(pbo_ptr: int, iteration: int) -> None:
+    """``sendToGPU``: tone-map the accumulated image into a device RGBA8 buffer."""
+    if _renderer is None:
+        raise B2ptError(-5, "sendToGPU() before pathtraceInit()")
+    _renderer.tonemap_rgba8(pbo_ptr, iteration)

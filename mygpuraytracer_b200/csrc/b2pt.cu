@@ -1,0 +1,991 @@
+// b2pt.cu -- context, wavefront loop and the C ABI of include/b2pt.h.
+//
+// Host side of the hot path: what pathtraceInit / pathtrace / pathtraceFree do
+// in the reference (apps/src/pathtrace.cu:130-223, 527-671), re-designed so
+// that one iteration is a fixed sequence of kernels with no host round trip:
+//
+//   k_iter_begin                       (iteration number and counters live on the device)
+//   k_generate                         generateRayFromCamera
+//   for d in 0 .. depth-1:
+//     k_intersect<d>                   memset + computeIntersections + sort-key extraction + histogram
+//     k_onesweep_pass<MaterialSort,d>  thrust::sort_by_key  -> 4-byte permutation only
+//     k_shade_compact<d>               shadeFakeMaterial + stable_partition + finalGather
+//
+// Every kernel reads its element count from device memory, so the sequence is
+// identical for every iteration and is captured once into a CUDA graph.
+// Compiled with -fmad=false (see pt_math.cuh).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b2pt.h"
+#include "k_generate.cuh"
+#include "k_intersect.cuh"
+#include "k_lbvh.cuh"
+#include "k_prims.cuh"
+#include "k_shade.cuh"
+#include "k_sort.cuh"
+#include "pt_device.cuh"
+
+using namespace b2pt;
+
+// ---------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) {                                                                             \
+      char b_[512];                                                                                      \
+      snprintf(b_, sizeof b_, "CUDA error (%s:%d): %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+      return fail(B2PT_ERR_CUDA, b_);                                                                    \
+    }                                                                                                    \
+  } while (0)
+
+extern "C" const char* b2pt_last_error(void) { return g_last_error.c_str(); }
+// used by host/scene_loader.cpp (same shared object) to report through the same channel
+extern "C" void b2pt_set_last_error_(const char* msg) { g_last_error = msg ? msg : ""; }
+extern "C" int b2pt_abi_version(void) { return B2PT_ABI_VERSION; }
+extern "C" int b2pt_device_count(void) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) return fail(B2PT_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+  return n;
+}
+
+extern "C" void b2pt_default_options(B2ptOptions* o) {
+  if (!o) return;
+  memset(o, 0, sizeof *o);
+  o->struct_size = sizeof(B2ptOptions);
+  o->device = 0;
+  o->antialiasing = 1;       // ANTIALIASING 1, pathtrace.cu:39
+  o->depth_of_field = 0;     // DEPTH_OF_FIELD 0, pathtrace.cu:36
+  o->lens_radius = 0.8f;     // pathtrace.cu:279
+  o->focal_distance = 11.0f; // pathtrace.cu:280
+  o->sort_by_material = 1;   // SORT_BY_MATERIAL 1, pathtrace.cu:38
+  o->cache_first_bounce = 0;
+  o->trig_mode = B2PT_TRIG_NATIVE;
+  o->rng_mode = B2PT_RNG_SLOT;
+  o->use_bvh = 1;
+  o->record_stages = 0;
+  o->use_graph = 1;
+}
+
+// ---------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------
+struct MeshBuild {
+  float4* nodes = nullptr;
+  float4* tris = nullptr;
+  float* face_pos = nullptr;
+  float* face_uv = nullptr;
+  B2ptBvhInfo info{};
+};
+
+struct StageRecord {
+  int n = 0;
+  std::vector<float4> in_s0, in_s1, in_s2, h0, h1, sh_s0, sh_s1, sh_s2;
+  std::vector<int> perm, live, dead;
+  int n_live_out = 0;
+};
+
+struct B2ptCtx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  B2ptOptions opt{};
+  int W = 0, H = 0, P = 0, depth = 0, loop_depth = 0;
+  int n_geoms = 0, n_materials = 0;
+  int sm_count = 0;
+
+  std::vector<void*> allocs;  // every cudaMalloc, freed in b2pt_destroy
+  std::vector<MeshBuild> meshes;
+  std::vector<int> geom_mesh;
+  DevScene dscene{};
+  GenParams gen{};
+
+  PathBuf buf[2]{};
+  HitBuf hits{};
+  uint8_t* key = nullptr;
+  int* perm = nullptr;
+  Counters* ctr = nullptr;
+  int* iter_state = nullptr;
+  unsigned long long* sort_status = nullptr;
+  unsigned long long* shade_status = nullptr;
+  float* image = nullptr;
+  float* albedo = nullptr;
+  float* image_target = nullptr;  // where the gather accumulates (own image or caller's buffer)
+
+  // stage recording
+  float4 *rec_s0 = nullptr, *rec_s1 = nullptr, *rec_s2 = nullptr;
+  int *rec_live = nullptr, *rec_dead = nullptr;
+  std::vector<StageRecord> records;
+
+  int isect_grid = 0, sort_grid = 0, shade_grid = 0, gen_grid = 0;
+  cudaEvent_t ev_loop_a = nullptr, ev_loop_b = nullptr;
+  bool loop_timed = false;
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  int graph_kernels = 0;
+  int64_t launches = 0;
+
+  template <typename T>
+  int dalloc(T** p, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
+    if (e != cudaSuccess) return fail(B2PT_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    allocs.push_back(q);
+    *p = (T*)q;
+    return 0;
+  }
+};
+
+static Mat34 rows_of(const float* m) {
+  Mat34 r;
+  r.r0 = make_float4(m[0], m[4], m[8], m[12]);
+  r.r1 = make_float4(m[1], m[5], m[9], m[13]);
+  r.r2 = make_float4(m[2], m[6], m[10], m[14]);
+  return r;
+}
+
+// 1 if the upper 3x3 of the transform is orthonormal (object-space distances
+// equal world-space distances).
+static int is_rigid(const float* m) {
+  for (int a = 0; a < 3; ++a)
+    for (int b = a; b < 3; ++b) {
+      double d = 0;
+      for (int k = 0; k < 3; ++k) d += (double)m[a * 4 + k] * (double)m[b * 4 + k];
+      if (std::fabs(d - (a == b ? 1.0 : 0.0)) > 1e-5) return 0;
+    }
+  return 1;
+}
+
+static DevCamera to_dev_camera(const B2ptCamera& c) {
+  DevCamera d;
+  d.res_x = c.resolution[0];
+  d.res_y = c.resolution[1];
+  d.position = {c.position[0], c.position[1], c.position[2]};
+  d.view = {c.view[0], c.view[1], c.view[2]};
+  d.up = {c.up[0], c.up[1], c.up[2]};
+  d.right = {c.right[0], c.right[1], c.right[2]};
+  d.plx = c.pixel_length[0];
+  d.ply = c.pixel_length[1];
+  return d;
+}
+
+// ---------------------------------------------------------------------------------
+// radix sort of pairs (device arrays), used by the LBVH build and exported
+// ---------------------------------------------------------------------------------
+struct RadixTemps {
+  unsigned int* hist = nullptr;     // [4][256]
+  unsigned int* tickets = nullptr;  // [4]
+  unsigned long long* status = nullptr;
+  uint32_t* key_alt = nullptr;
+  uint32_t* val_alt = nullptr;
+};
+
+static unsigned int g_radix_epoch = 1;
+
+// Sorts n pairs in place (result ends in key/val after four passes).
+static int radix_sort_pairs_dev(uint32_t* key, uint32_t* val, int n, cudaStream_t s, int64_t* launches) {
+  if (n <= 1) return 0;
+  RadixTemps t;
+  const int tiles = (n + kSortTile - 1) / kSortTile;
+  CK(cudaMalloc(&t.hist, 4 * 256 * sizeof(unsigned int)));
+  CK(cudaMalloc(&t.tickets, 4 * sizeof(unsigned int)));
+  CK(cudaMalloc(&t.status, (size_t)tiles * 256 * sizeof(unsigned long long)));
+  CK(cudaMalloc(&t.key_alt, (size_t)n * 4));
+  CK(cudaMalloc(&t.val_alt, (size_t)n * 4));
+  CK(cudaMemsetAsync(t.hist, 0, 4 * 256 * sizeof(unsigned int), s));
+  CK(cudaMemsetAsync(t.tickets, 0, 4 * sizeof(unsigned int), s));
+  CK(cudaMemsetAsync(t.status, 0, (size_t)tiles * 256 * sizeof(unsigned long long), s));
+  k_radix_hist<<<std::min(tiles * 4, 1184), 256, 0, s>>>(key, n, t.hist);
+  uint32_t *ki = key, *vi = val, *ko = t.key_alt, *vo = t.val_alt;
+  for (int pass = 0; pass < 4; ++pass) {
+    RadixPassPolicy pol;
+    pol.key_in = ki;
+    pol.val_in = vi;
+    pol.key_out = ko;
+    pol.val_out = vo;
+    pol.hist = t.hist + pass * 256;
+    pol.ticket_ = t.tickets + pass;
+    pol.status_ = t.status;
+    pol.epoch_ = g_radix_epoch++;
+    pol.n_ = n;
+    pol.shift = pass * 8;
+    k_onesweep_pass<RadixPassPolicy><<<tiles, kSortThreads, 0, s>>>(pol);
+    std::swap(ki, ko);
+    std::swap(vi, vo);
+  }
+  if (launches) *launches += 5;
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(s));
+  cudaFree(t.hist);
+  cudaFree(t.tickets);
+  cudaFree(t.status);
+  cudaFree(t.key_alt);
+  cudaFree(t.val_alt);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// LBVH build for one mesh
+// ---------------------------------------------------------------------------------
+static int build_mesh(B2ptCtx* c, const float* pos_host, const float* uv_host, int n, MeshBuild* out) {
+  cudaStream_t s = c->stream;
+  int rc;
+  if ((rc = c->dalloc(&out->face_pos, (size_t)n * 9))) return rc;
+  if ((rc = c->dalloc(&out->face_uv, (size_t)n * 6))) return rc;
+  CK(cudaMemcpyAsync(out->face_pos, pos_host, (size_t)n * 36, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(out->face_uv, uv_host, (size_t)n * 24, cudaMemcpyHostToDevice, s));
+  if ((rc = c->dalloc(&out->tris, (size_t)n * 3))) return rc;
+  if ((rc = c->dalloc(&out->nodes, (size_t)std::max(n - 1, 1) * 4))) return rc;
+  out->info.n_faces = n;
+  out->info.n_nodes = std::max(n - 1, 0);
+
+  // pad: a few 1e-6 of the mesh extent (host pass over the positions)
+  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (size_t i = 0; i < (size_t)n * 3; ++i)
+    for (int k = 0; k < 3; ++k) {
+      lo[k] = std::min(lo[k], pos_host[i * 3 + k]);
+      hi[k] = std::max(hi[k], pos_host[i * 3 + k]);
+    }
+  float ext = 0.0f;
+  for (int k = 0; k < 3; ++k) ext = std::max(ext, std::max(std::fabs(lo[k]), std::fabs(hi[k])));
+  const float pad = 4e-6f * std::max(ext, 1.0f);
+
+  TriBounds* bounds = nullptr;
+  uint32_t *code = nullptr, *val = nullptr;
+  float4 *leaf_box = nullptr, *node_box = nullptr;
+  int2* children = nullptr;
+  int *parent = nullptr, *visit = nullptr;
+  CK(cudaMalloc(&bounds, sizeof(TriBounds)));
+  CK(cudaMalloc(&code, (size_t)n * 4));
+  CK(cudaMalloc(&val, (size_t)n * 4));
+  CK(cudaMalloc(&leaf_box, (size_t)n * 2 * sizeof(float4)));
+  CK(cudaMalloc(&node_box, (size_t)std::max(n - 1, 1) * 2 * sizeof(float4)));
+  CK(cudaMalloc(&children, (size_t)std::max(n - 1, 1) * sizeof(int2)));
+  CK(cudaMalloc(&parent, (size_t)(2 * n) * sizeof(int)));
+  CK(cudaMalloc(&visit, (size_t)std::max(n - 1, 1) * sizeof(int)));
+
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, s));
+  const int blocks = (n + 255) / 256;
+  k_bounds_init<<<1, 32, 0, s>>>(bounds);
+  k_centroid_bounds<<<std::min(blocks, 1184), 256, 0, s>>>(out->face_pos, n, bounds);
+  k_morton<<<blocks, 256, 0, s>>>(out->face_pos, n, bounds, code, val);
+  c->launches += 3;
+  if ((rc = radix_sort_pairs_dev(code, val, n, s, &c->launches))) return rc;
+  k_leaves<<<blocks, 256, 0, s>>>(out->face_pos, val, n, pad, out->tris, leaf_box);
+  c->launches += 1;
+  if (n >= 2) {
+    CK(cudaMemsetAsync(visit, 0, (size_t)(n - 1) * sizeof(int), s));
+    const int iblocks = (n - 1 + 255) / 256;
+    k_karras<<<iblocks, 256, 0, s>>>(code, n, children, parent);
+    k_refit<<<blocks, 256, 0, s>>>(n, children, parent, leaf_box, node_box, visit, bounds);
+    k_tree_depth<<<blocks, 256, 0, s>>>(n, parent, bounds);
+    k_emit_nodes<<<iblocks, 256, 0, s>>>(n, children, leaf_box, node_box, out->nodes);
+    c->launches += 4;
+  }
+  CK(cudaEventRecord(e1, s));
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(s));
+  CK(cudaEventElapsedTime(&out->info.build_ms, e0, e1));
+  TriBounds hb;
+  CK(cudaMemcpy(&hb, bounds, sizeof hb, cudaMemcpyDeviceToHost));
+  out->info.max_depth = n >= 2 ? hb.max_depth : 1;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(bounds);
+  cudaFree(code);
+  cudaFree(val);
+  cudaFree(leaf_box);
+  cudaFree(node_box);
+  cudaFree(children);
+  cudaFree(parent);
+  cudaFree(visit);
+  if (out->info.max_depth > kShortStack + kLocalStack)
+    return fail(B2PT_ERR_RANGE, "LBVH deeper than the traversal stack");
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// create / destroy
+// ---------------------------------------------------------------------------------
+static int upload_texture(B2ptCtx* c, const B2ptScene* sc, int idx, DevTexture* out) {
+  out->texels = nullptr;
+  out->w = out->h = out->channels = 0;
+  if (idx < 0) return 0;
+  if (idx >= sc->n_textures) return fail(B2PT_ERR_INVALID, "texture index out of range");
+  const B2ptTexture& t = sc->textures[idx];
+  if (t.channels == 0 || t.texels == nullptr) return 0;
+  if (t.channels < 3 || t.width <= 0 || t.height <= 0)
+    return fail(B2PT_ERR_INVALID, "textures need >= 3 channels and positive dimensions");
+  uint8_t* d = nullptr;
+  const size_t bytes = (size_t)t.width * t.height * t.channels;
+  int rc = c->dalloc(&d, bytes);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(d, t.texels, bytes, cudaMemcpyHostToDevice, c->stream));
+  out->texels = d;
+  out->w = t.width;
+  out->h = t.height;
+  out->channels = t.channels;
+  return 0;
+}
+
+static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* c) {
+  B2ptOptions opt;
+  b2pt_default_options(&opt);
+  if (opt_in) {
+    if (opt_in->struct_size == 0 || opt_in->struct_size > sizeof(B2ptOptions))
+      return fail(B2PT_ERR_INVALID, "B2ptOptions.struct_size is not set");
+    memcpy(&opt, opt_in, opt_in->struct_size);
+    opt.struct_size = sizeof(B2ptOptions);
+  }
+  c->opt = opt;
+  const int W = sc->camera.resolution[0], H = sc->camera.resolution[1];
+  if (W <= 0 || H <= 0 || (long long)W * H >= (1ll << 30)) return fail(B2PT_ERR_INVALID, "bad resolution");
+  if (sc->n_geoms < 0 || sc->n_geoms > kMaxGeoms) return fail(B2PT_ERR_RANGE, "at most 64 geoms are supported");
+  if (sc->n_materials <= 0 || sc->n_materials > kMaxMaterials)
+    return fail(B2PT_ERR_RANGE, "between 1 and 256 materials are supported");
+  if (sc->trace_depth < 0 || sc->trace_depth > kMaxDepth) return fail(B2PT_ERR_RANGE, "trace depth must be in [0, 62]");
+  if (sc->n_geoms > 0 && !sc->geoms) return fail(B2PT_ERR_INVALID, "geoms is NULL");
+  if (!sc->materials) return fail(B2PT_ERR_INVALID, "materials is NULL");
+  c->W = W;
+  c->H = H;
+  c->P = W * H;
+  c->depth = sc->trace_depth;
+  c->loop_depth = std::max(sc->trace_depth, 1);  // the reference's while loop always runs once
+  c->n_geoms = sc->n_geoms;
+  c->n_materials = sc->n_materials;
+
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (opt.device < 0 || opt.device >= ndev) return fail(B2PT_ERR_INVALID, "no such CUDA device");
+  c->device = opt.device;
+  CK(cudaSetDevice(c->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, c->device));
+  c->sm_count = prop.multiProcessorCount;
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&c->ev_loop_a));
+  CK(cudaEventCreate(&c->ev_loop_b));
+
+  int rc;
+  // ---- geoms, meshes, textures -----------------------------------------------------
+  std::vector<DevGeom> hg(sc->n_geoms);
+  std::vector<DevMesh> hm;
+  c->geom_mesh.assign(sc->n_geoms, -1);
+  for (int g = 0; g < sc->n_geoms; ++g) {
+    const B2ptGeom& G = sc->geoms[g];
+    DevGeom& D = hg[g];
+    D.inv = rows_of(G.inverse_transform);
+    D.fwd = rows_of(G.transform);
+    D.invT = rows_of(G.inv_transpose);
+    D.type = G.type;
+    D.material = G.material_id;
+    D.mesh = -1;
+    D.rigid = is_rigid(G.transform);
+    if (G.material_id < 0 || G.material_id >= sc->n_materials)
+      return fail(B2PT_ERR_INVALID, "geom material id out of range");
+    if (G.type == B2PT_OBJ && G.face_count > 0) {
+      if (G.face_begin < 0 || (long long)G.face_begin + G.face_count > sc->n_faces || !sc->face_pos || !sc->face_uv)
+        return fail(B2PT_ERR_INVALID, "geom face range out of bounds");
+      MeshBuild mb;
+      if ((rc = build_mesh(c, sc->face_pos + (size_t)G.face_begin * 9, sc->face_uv + (size_t)G.face_begin * 6,
+                           G.face_count, &mb)))
+        return rc;
+      DevMesh M{};
+      M.nodes = mb.nodes;
+      M.tris = mb.tris;
+      M.face_pos = mb.face_pos;
+      M.face_uv = mb.face_uv;
+      M.n_faces = G.face_count;
+      M.root = G.face_count >= 2 ? 0 : ~0;
+      if ((rc = upload_texture(c, sc, G.tex_kd, &M.kd))) return rc;
+      if ((rc = upload_texture(c, sc, G.tex_ks, &M.ks))) return rc;
+      if ((rc = upload_texture(c, sc, G.tex_bump, &M.bump))) return rc;
+      if ((rc = upload_texture(c, sc, G.tex_ke, &M.ke))) return rc;
+      D.mesh = (int)hm.size();
+      c->geom_mesh[g] = D.mesh;
+      hm.push_back(M);
+      c->meshes.push_back(mb);
+    }
+  }
+  DevGeom* dg = nullptr;
+  DevMesh* dm = nullptr;
+  DevMaterial* dmat = nullptr;
+  if ((rc = c->dalloc(&dg, hg.size()))) return rc;
+  if ((rc = c->dalloc(&dm, hm.size()))) return rc;
+  if ((rc = c->dalloc(&dmat, (size_t)sc->n_materials))) return rc;
+  if (!hg.empty()) CK(cudaMemcpyAsync(dg, hg.data(), hg.size() * sizeof(DevGeom), cudaMemcpyHostToDevice, c->stream));
+  if (!hm.empty()) CK(cudaMemcpyAsync(dm, hm.data(), hm.size() * sizeof(DevMesh), cudaMemcpyHostToDevice, c->stream));
+  static_assert(sizeof(DevMaterial) == sizeof(B2ptMaterial), "material layout");
+  CK(cudaMemcpyAsync(dmat, sc->materials, (size_t)sc->n_materials * sizeof(DevMaterial), cudaMemcpyHostToDevice, c->stream));
+  c->dscene.geoms = dg;
+  c->dscene.meshes = dm;
+  c->dscene.materials = dmat;
+  c->dscene.n_geoms = sc->n_geoms;
+  c->dscene.n_meshes = (int)hm.size();
+  c->dscene.n_materials = sc->n_materials;
+
+  // ---- wavefront buffers -------------------------------------------------------------
+  const size_t P = (size_t)c->P;
+  for (int b = 0; b < 2; ++b) {
+    if ((rc = c->dalloc(&c->buf[b].s0, P))) return rc;
+    if ((rc = c->dalloc(&c->buf[b].s1, P))) return rc;
+    if ((rc = c->dalloc(&c->buf[b].s2, P))) return rc;
+  }
+  if ((rc = c->dalloc(&c->hits.h0, P))) return rc;
+  if ((rc = c->dalloc(&c->hits.h1, P))) return rc;
+  if ((rc = c->dalloc(&c->key, P))) return rc;
+  if ((rc = c->dalloc(&c->perm, P))) return rc;
+  if ((rc = c->dalloc(&c->ctr, 1))) return rc;
+  if ((rc = c->dalloc(&c->iter_state, 4))) return rc;
+  c->sort_grid = (int)((P + kSortTile - 1) / kSortTile);
+  c->shade_grid = (int)((P + kShadeThreads - 1) / kShadeThreads);
+  c->gen_grid = (int)std::min<size_t>((P + 255) / 256, (size_t)c->sm_count * 8);
+  if ((rc = c->dalloc(&c->sort_status, (size_t)c->sort_grid * 256))) return rc;
+  if ((rc = c->dalloc(&c->shade_status, (size_t)c->shade_grid))) return rc;
+  if ((rc = c->dalloc(&c->image, P * 3))) return rc;
+  if ((rc = c->dalloc(&c->albedo, P * 3))) return rc;
+  c->image_target = c->image;
+  CK(cudaMemsetAsync(c->ctr, 0, sizeof(Counters), c->stream));
+  CK(cudaMemsetAsync(c->iter_state, 0, 4 * sizeof(int), c->stream));
+  CK(cudaMemsetAsync(c->sort_status, 0, (size_t)c->sort_grid * 256 * 8, c->stream));
+  CK(cudaMemsetAsync(c->shade_status, 0, (size_t)c->shade_grid * 8, c->stream));
+  CK(cudaMemsetAsync(c->image, 0, P * 12, c->stream));
+  CK(cudaMemsetAsync(c->albedo, 0, P * 12, c->stream));
+  if (opt.record_stages) {
+    if ((rc = c->dalloc(&c->rec_s0, P))) return rc;
+    if ((rc = c->dalloc(&c->rec_s1, P))) return rc;
+    if ((rc = c->dalloc(&c->rec_s2, P))) return rc;
+    if ((rc = c->dalloc(&c->rec_live, P))) return rc;
+    if ((rc = c->dalloc(&c->rec_dead, P))) return rc;
+  }
+
+  // persistent grid of the intersect kernel: SMs x resident CTAs
+  int occ = 0;
+  if (opt.use_bvh)
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_intersect<true>, kIsectThreads, 0));
+  else
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_intersect<false>, kIsectThreads, 0));
+  c->isect_grid = c->sm_count * std::max(occ, 1);
+
+  c->gen.cam = to_dev_camera(sc->camera);
+  c->gen.trace_depth = sc->trace_depth;
+  c->gen.antialiasing = opt.antialiasing;
+  c->gen.depth_of_field = opt.depth_of_field;
+  c->gen.lens_radius = opt.lens_radius;
+  c->gen.focal_distance = opt.focal_distance;
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" void b2pt_destroy(B2ptCtx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+  if (c->graph) cudaGraphDestroy(c->graph);
+  for (void* p : c->allocs) cudaFree(p);
+  if (c->ev_loop_a) cudaEventDestroy(c->ev_loop_a);
+  if (c->ev_loop_b) cudaEventDestroy(c->ev_loop_b);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+extern "C" int b2pt_create(const B2ptScene* scene, const B2ptOptions* opt, B2ptCtx** out) {
+  if (!scene || !out) return fail(B2PT_ERR_INVALID, "scene and out must not be NULL");
+  *out = nullptr;
+  B2ptCtx* c = new (std::nothrow) B2ptCtx();
+  if (!c) return fail(B2PT_ERR_NOMEM, "out of host memory");
+  int rc = create_impl(scene, opt, c);
+  if (rc != 0) {
+    std::string keep = g_last_error;
+    b2pt_destroy(c);
+    g_last_error = keep;
+    return rc;
+  }
+  *out = c;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// one iteration
+// ---------------------------------------------------------------------------------
+__global__ void k_set_iter(int* iter_state, int first, int stride) {
+  iter_state[1] = first;
+  iter_state[2] = stride;
+}
+
+template <int TRIG>
+static void launch_generate(B2ptCtx* c) {
+  k_generate<TRIG><<<c->gen_grid, 256, 0, c->stream>>>(c->gen, c->iter_state, c->buf[0]);
+}
+
+template <int TRIG, bool RECORD>
+static void launch_shade(B2ptCtx* c, const ShadeParams& sp) {
+  k_shade_compact<TRIG, RECORD><<<c->shade_grid, kShadeThreads, 0, c->stream>>>(sp);
+}
+
+static void unpack3(const std::vector<float4>& v, int n, float* dst) {
+  for (int i = 0; i < n; ++i) {
+    dst[3 * i] = v[i].x;
+    dst[3 * i + 1] = v[i].y;
+    dst[3 * i + 2] = v[i].z;
+  }
+}
+
+// Queue the kernels of one iteration (also the body that gets graph-captured).
+static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool capturing = false) {
+  cudaStream_t s = c->stream;
+  const int slots = c->loop_depth + 1;
+  k_iter_begin<<<8, 256, 0, s>>>(c->ctr, c->iter_state, c->P, slots);
+  if (c->opt.trig_mode == B2PT_TRIG_PORTABLE) launch_generate<1>(c); else launch_generate<0>(c);
+  c->launches += 2;
+  if (time_loop) CK(cudaEventRecordWithFlags(c->ev_loop_a, s, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
+  if (record) c->records.assign(c->loop_depth, StageRecord());
+  for (int d = 0; d < c->loop_depth; ++d) {
+    PathBuf in = c->buf[d & 1], out = c->buf[(d + 1) & 1];
+    StageRecord* R = record ? &c->records[d] : nullptr;
+    int n = 0;
+    if (record) {
+      CK(cudaStreamSynchronize(s));
+      CK(cudaMemcpy(&n, &c->ctr->n_live[d], sizeof(int), cudaMemcpyDeviceToHost));
+      R->n = n;
+      R->in_s0.resize(n); R->in_s1.resize(n); R->in_s2.resize(n);
+      CK(cudaMemcpy(R->in_s0.data(), in.s0, (size_t)n * 16, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(R->in_s1.data(), in.s1, (size_t)n * 16, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(R->in_s2.data(), in.s2, (size_t)n * 16, cudaMemcpyDeviceToHost));
+    }
+    IsectParams ip;
+    ip.scene = c->dscene;
+    ip.in = in;
+    ip.out = c->hits;
+    ip.key = c->key;
+    ip.ctr = c->ctr;
+    ip.depth = d;
+    if (c->opt.use_bvh)
+      k_intersect<true><<<c->isect_grid, kIsectThreads, 0, s>>>(ip);
+    else
+      k_intersect<false><<<c->isect_grid, kIsectThreads, 0, s>>>(ip);
+    c->launches += 1;
+    if (c->opt.sort_by_material) {
+      MaterialSortPolicy mp;
+      mp.key = c->key;
+      mp.perm = c->perm;
+      mp.ctr = c->ctr;
+      mp.status_ = c->sort_status;
+      mp.depth = d;
+      k_onesweep_pass<MaterialSortPolicy><<<c->sort_grid, kSortThreads, 0, s>>>(mp);
+      c->launches += 1;
+    }
+    if (record) {
+      CK(cudaStreamSynchronize(s));
+      R->h0.resize(n); R->h1.resize(n); R->perm.resize(n);
+      CK(cudaMemcpy(R->h0.data(), c->hits.h0, (size_t)n * 16, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(R->h1.data(), c->hits.h1, (size_t)n * 16, cudaMemcpyDeviceToHost));
+      if (c->opt.sort_by_material) {
+        CK(cudaMemcpy(R->perm.data(), c->perm, (size_t)n * 4, cudaMemcpyDeviceToHost));
+      } else {
+        for (int i = 0; i < n; ++i) R->perm[i] = i;
+      }
+    }
+    ShadeParams sp;
+    sp.scene = c->dscene;
+    sp.in = in;
+    sp.out = out;
+    sp.hits = c->hits;
+    sp.perm = c->opt.sort_by_material ? c->perm : nullptr;
+    sp.ctr = c->ctr;
+    sp.status = c->shade_status;
+    sp.image = c->image_target;
+    sp.albedo = c->albedo;
+    sp.iter_state = c->iter_state;
+    sp.depth = d;
+    sp.rng_pixel = c->opt.rng_mode == B2PT_RNG_PIXEL;
+    sp.rec_s0 = c->rec_s0; sp.rec_s1 = c->rec_s1; sp.rec_s2 = c->rec_s2;
+    sp.rec_dead = c->rec_dead; sp.rec_live = c->rec_live;
+    const bool portable = c->opt.trig_mode == B2PT_TRIG_PORTABLE;
+    if (record) {
+      if (portable) launch_shade<1, true>(c, sp); else launch_shade<0, true>(c, sp);
+    } else {
+      if (portable) launch_shade<1, false>(c, sp); else launch_shade<0, false>(c, sp);
+    }
+    c->launches += 1;
+    if (record) {
+      CK(cudaStreamSynchronize(s));
+      int live = 0;
+      CK(cudaMemcpy(&live, &c->ctr->n_live[d + 1], sizeof(int), cudaMemcpyDeviceToHost));
+      R->n_live_out = live;
+      R->sh_s0.resize(n); R->sh_s1.resize(n); R->sh_s2.resize(n);
+      R->live.resize(live); R->dead.resize(n - live);
+      CK(cudaMemcpy(R->sh_s0.data(), c->rec_s0, (size_t)n * 16, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(R->sh_s1.data(), c->rec_s1, (size_t)n * 16, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(R->sh_s2.data(), c->rec_s2, (size_t)n * 16, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(R->live.data(), c->rec_live, (size_t)live * 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(R->dead.data(), c->rec_dead, (size_t)(n - live) * 4, cudaMemcpyDeviceToHost));
+    }
+  }
+  if (time_loop) CK(cudaEventRecordWithFlags(c->ev_loop_b, s, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int b2pt_render(B2ptCtx* c, int32_t iter_first, int32_t iter_count, int32_t iter_stride) {
+  if (!c) return fail(B2PT_ERR_INVALID, "ctx is NULL");
+  if (iter_count < 0 || iter_stride <= 0) return fail(B2PT_ERR_INVALID, "iter_count >= 0 and iter_stride > 0 required");
+  if (iter_count == 0) return 0;
+  CK(cudaSetDevice(c->device));
+  k_set_iter<<<1, 1, 0, c->stream>>>(c->iter_state, iter_first, iter_stride);
+  c->launches += 1;
+  const bool record = c->opt.record_stages != 0;
+  if (record || !c->opt.use_graph) {
+    for (int i = 0; i < iter_count; ++i) {
+      int rc = enqueue_iteration(c, record && i == iter_count - 1, i == iter_count - 1);
+      if (rc) return rc;
+    }
+    c->loop_timed = true;
+    return 0;
+  }
+  if (!c->graph_exec) {
+    const int64_t before = c->launches;
+    CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_iteration(c, false, true, true);
+    cudaError_t e = cudaStreamEndCapture(c->stream, &c->graph);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(B2PT_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    c->graph_kernels = (int)(c->launches - before);
+    c->launches = before;
+    CK(cudaGraphInstantiate(&c->graph_exec, c->graph, 0));
+  }
+  for (int i = 0; i < iter_count; ++i) {
+    CK(cudaGraphLaunch(c->graph_exec, c->stream));
+    c->launches += c->graph_kernels;
+  }
+  c->loop_timed = true;
+  return 0;
+}
+
+extern "C" int b2pt_sync(B2ptCtx* c) {
+  if (!c) return fail(B2PT_ERR_INVALID, "ctx is NULL");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int b2pt_read_accum(B2ptCtx* c, float* image_host, float* albedo_host) {
+  if (!c) return fail(B2PT_ERR_INVALID, "ctx is NULL");
+  CK(cudaSetDevice(c->device));
+  const size_t bytes = (size_t)c->P * 12;
+  if (image_host) CK(cudaMemcpyAsync(image_host, c->image_target, bytes, cudaMemcpyDeviceToHost, c->stream));
+  if (albedo_host) CK(cudaMemcpyAsync(albedo_host, c->albedo, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+extern "C" int b2pt_pathtrace(B2ptCtx* c, int32_t iter, float* image_host, float* albedo_host) {
+  int rc = b2pt_render(c, iter, 1, 1);
+  if (rc) return rc;
+  return b2pt_read_accum(c, image_host, albedo_host);
+}
+
+extern "C" int b2pt_reset_accum(B2ptCtx* c) {
+  if (!c) return fail(B2PT_ERR_INVALID, "ctx is NULL");
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemsetAsync(c->image_target, 0, (size_t)c->P * 12, c->stream));
+  CK(cudaMemsetAsync(c->albedo, 0, (size_t)c->P * 12, c->stream));
+  return 0;
+}
+
+extern "C" int b2pt_set_camera(B2ptCtx* c, const B2ptCamera* cam) {
+  if (!c || !cam) return fail(B2PT_ERR_INVALID, "ctx and cam must not be NULL");
+  if (cam->resolution[0] != c->W || cam->resolution[1] != c->H)
+    return fail(B2PT_ERR_INVALID, "the resolution of a context cannot change");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  c->gen.cam = to_dev_camera(*cam);
+  if (c->graph_exec) {  // the camera is baked into the captured kernel arguments
+    cudaGraphExecDestroy(c->graph_exec);
+    cudaGraphDestroy(c->graph);
+    c->graph_exec = nullptr;
+    c->graph = nullptr;
+  }
+  return b2pt_reset_accum(c);
+}
+
+extern "C" float* b2pt_device_image(B2ptCtx* c) { return c ? c->image_target : nullptr; }
+extern "C" float* b2pt_device_albedo(B2ptCtx* c) { return c ? c->albedo : nullptr; }
+extern "C" void* b2pt_stream(B2ptCtx* c) { return c ? (void*)c->stream : nullptr; }
+extern "C" int64_t b2pt_launch_count(B2ptCtx* c) { return c ? c->launches : 0; }
+
+extern "C" int b2pt_set_device_image(B2ptCtx* c, float* image_dev) {
+  if (!c) return fail(B2PT_ERR_INVALID, "ctx is NULL");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  c->image_target = image_dev ? image_dev : c->image;
+  if (c->graph_exec) {
+    cudaGraphExecDestroy(c->graph_exec);
+    cudaGraphDestroy(c->graph);
+    c->graph_exec = nullptr;
+    c->graph = nullptr;
+  }
+  return 0;
+}
+
+extern "C" float b2pt_last_loop_ms(B2ptCtx* c) {
+  if (!c || !c->loop_timed) return -1.0f;
+  cudaSetDevice(c->device);
+  if (cudaEventSynchronize(c->ev_loop_b) != cudaSuccess) return -1.0f;
+  float ms = -1.0f;
+  if (cudaEventElapsedTime(&ms, c->ev_loop_a, c->ev_loop_b) != cudaSuccess) return -1.0f;
+  return ms;
+}
+
+extern "C" int b2pt_live_counts(B2ptCtx* c, int32_t* n_live, int32_t cap) {
+  if (!c || !n_live) return fail(B2PT_ERR_INVALID, "ctx and n_live must not be NULL");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  Counters* h = (Counters*)malloc(sizeof(Counters));
+  if (!h) return fail(B2PT_ERR_NOMEM, "out of host memory");
+  cudaError_t e = cudaMemcpy(h, c->ctr, sizeof(Counters), cudaMemcpyDeviceToHost);
+  int k = 0;
+  if (e == cudaSuccess)
+    for (; k < cap && k <= c->loop_depth; ++k) n_live[k] = h->n_live[k];
+  free(h);
+  if (e != cudaSuccess) return fail(B2PT_ERR_CUDA, cudaGetErrorString(e));
+  return k;
+}
+
+// ---------------------------------------------------------------------------------
+// tone map (sendImageToPBO / sendDenosiedImageToPBO, pathtrace.cu:73-116)
+// ---------------------------------------------------------------------------------
+__global__ void k_tonemap(const float* __restrict__ src, int n, int iter, uchar4* dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float r = src[3 * (size_t)i], g = src[3 * (size_t)i + 1], b = src[3 * (size_t)i + 2];
+  int cr, cg, cb;
+  if (iter > 0) {
+    cr = (int)(r / iter * 255.0);
+    cg = (int)(g / iter * 255.0);
+    cb = (int)(b / iter * 255.0);
+  } else {
+    cr = (int)(r * 255.0);
+    cg = (int)(g * 255.0);
+    cb = (int)(b * 255.0);
+  }
+  uchar4 o;
+  o.x = (unsigned char)min(max(cr, 0), 255);
+  o.y = (unsigned char)min(max(cg, 0), 255);
+  o.z = (unsigned char)min(max(cb, 0), 255);
+  o.w = 0;
+  dst[i] = o;
+}
+
+extern "C" int b2pt_tonemap_rgba8(B2ptCtx* c, const float* src_dev, int32_t iter, uint8_t* rgba8_dev) {
+  if (!c || !rgba8_dev) return fail(B2PT_ERR_INVALID, "ctx and rgba8_dev must not be NULL");
+  CK(cudaSetDevice(c->device));
+  k_tonemap<<<(c->P + 255) / 256, 256, 0, c->stream>>>(src_dev ? src_dev : c->image_target, c->P, iter, (uchar4*)rgba8_dev);
+  c->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// stage dumps
+// ---------------------------------------------------------------------------------
+extern "C" int64_t b2pt_stage_read(B2ptCtx* c, int32_t depth, int32_t stage, void* dst, int64_t bytes) {
+  if (!c || !dst) return fail(B2PT_ERR_INVALID, "ctx and dst must not be NULL");
+  if (depth < 0 || depth >= (int)c->records.size()) return fail(B2PT_ERR_RANGE, "no record for that depth");
+  const StageRecord& R = c->records[depth];
+  const int n = R.n;
+  int cols = 1;
+  switch (stage) {
+    case B2PT_STAGE_RAY_ORIGIN: case B2PT_STAGE_RAY_DIR: case B2PT_STAGE_HIT_NORMAL: case B2PT_STAGE_SHADED_COLOR:
+    case B2PT_STAGE_SHADED_ORIGIN: case B2PT_STAGE_SHADED_DIR: cols = 3; break;
+    case B2PT_STAGE_HIT_UV: cols = 2; break;
+    default: cols = 1;
+  }
+  const int64_t need = (int64_t)n * cols * 4;
+  if (bytes < need) return fail(B2PT_ERR_RANGE, "destination too small");
+  float* f = (float*)dst;
+  int32_t* q = (int32_t*)dst;
+  switch (stage) {
+    case B2PT_STAGE_RAY_ORIGIN: unpack3(R.in_s0, n, f); break;
+    case B2PT_STAGE_RAY_DIR: unpack3(R.in_s1, n, f); break;
+    case B2PT_STAGE_RAY_PIXEL: for (int i = 0; i < n; ++i) memcpy(&q[i], &R.in_s0[i].w, 4); break;
+    case B2PT_STAGE_HIT_T: for (int i = 0; i < n; ++i) f[i] = R.h0[i].x; break;
+    case B2PT_STAGE_HIT_NORMAL:
+      for (int i = 0; i < n; ++i) { f[3 * i] = R.h0[i].y; f[3 * i + 1] = R.h0[i].z; f[3 * i + 2] = R.h0[i].w; }
+      break;
+    case B2PT_STAGE_HIT_UV: for (int i = 0; i < n; ++i) { f[2 * i] = R.h1[i].x; f[2 * i + 1] = R.h1[i].y; } break;
+    case B2PT_STAGE_HIT_GEOM:
+      for (int i = 0; i < n; ++i) { int gm; memcpy(&gm, &R.h1[i].z, 4); q[i] = (int16_t)(gm & 0xffff); }
+      break;
+    case B2PT_STAGE_HIT_FACE: for (int i = 0; i < n; ++i) memcpy(&q[i], &R.h1[i].w, 4); break;
+    case B2PT_STAGE_HIT_MATERIAL:
+      for (int i = 0; i < n; ++i) { int gm; memcpy(&gm, &R.h1[i].z, 4); q[i] = (gm >> 16) & 0xffff; }
+      break;
+    case B2PT_STAGE_SORT_PERM: memcpy(q, R.perm.data(), (size_t)n * 4); break;
+    case B2PT_STAGE_SHADED_COLOR: unpack3(R.sh_s2, n, f); break;
+    case B2PT_STAGE_SHADED_BOUNCES: for (int i = 0; i < n; ++i) memcpy(&q[i], &R.sh_s1[i].w, 4); break;
+    case B2PT_STAGE_SHADED_ORIGIN: unpack3(R.sh_s0, n, f); break;
+    case B2PT_STAGE_SHADED_DIR: unpack3(R.sh_s1, n, f); break;
+    case B2PT_STAGE_PARTITION_PIXEL:
+      memcpy(q, R.live.data(), R.live.size() * 4);
+      memcpy(q + R.live.size(), R.dead.data(), R.dead.size() * 4);
+      break;
+    default: return fail(B2PT_ERR_INVALID, "unknown stage id");
+  }
+  return need;
+}
+
+extern "C" int b2pt_bvh_info(B2ptCtx* c, int32_t geom, B2ptBvhInfo* info) {
+  if (!c || !info) return fail(B2PT_ERR_INVALID, "ctx and info must not be NULL");
+  if (geom < 0 || geom >= c->n_geoms || c->geom_mesh[geom] < 0) return fail(B2PT_ERR_RANGE, "geom has no BVH");
+  *info = c->meshes[c->geom_mesh[geom]].info;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// standalone primitives on host arrays
+// ---------------------------------------------------------------------------------
+struct Scratch {  // frees everything on scope exit
+  std::vector<void*> p;
+  ~Scratch() { for (void* q : p) cudaFree(q); }
+  template <typename T>
+  cudaError_t get(T** out, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess) p.push_back(q);
+    *out = (T*)q;
+    return e;
+  }
+};
+
+template <int MODE>
+static int scan_family_host(int n, const int* in_host, const uint8_t* flags_host, int* out_host, int* count_out) {
+  if (n < 0) return fail(B2PT_ERR_INVALID, "n < 0");
+  if (n == 0) { if (count_out) *count_out = 0; return 0; }
+  Scratch S;
+  int *din = nullptr, *dout = nullptr, *ddead = nullptr, *dcount = nullptr;
+  uint8_t* dflags = nullptr;
+  unsigned int* ticket = nullptr;
+  unsigned long long* status = nullptr;
+  const int tiles = (n + kScanTile - 1) / kScanTile;
+  if (MODE == 2) { CK(S.get(&dflags, (size_t)n)); CK(cudaMemcpy(dflags, flags_host, (size_t)n, cudaMemcpyHostToDevice)); }
+  else { CK(S.get(&din, (size_t)n)); CK(cudaMemcpy(din, in_host, (size_t)n * 4, cudaMemcpyHostToDevice)); }
+  CK(S.get(&dout, (size_t)n));
+  CK(S.get(&ddead, (size_t)n));
+  CK(S.get(&dcount, 1));
+  CK(S.get(&ticket, 1));
+  CK(S.get(&status, (size_t)tiles));
+  CK(cudaMemset(ticket, 0, 4));
+  CK(cudaMemset(dcount, 0, 4));
+  CK(cudaMemset(status, 0, (size_t)tiles * 8));
+  k_scan_family<MODE><<<tiles, kScanThreads>>>(din, dflags, n, dout, ddead, ticket, status, 1u, dcount);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  int count = 0;
+  CK(cudaMemcpy(&count, dcount, 4, cudaMemcpyDeviceToHost));
+  if (MODE == 0) {
+    CK(cudaMemcpy(out_host, dout, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  } else if (MODE == 1) {
+    CK(cudaMemcpy(out_host, dout, (size_t)count * 4, cudaMemcpyDeviceToHost));
+  } else {
+    CK(cudaMemcpy(out_host, dout, (size_t)count * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out_host + count, ddead, (size_t)(n - count) * 4, cudaMemcpyDeviceToHost));
+  }
+  if (count_out) *count_out = count;
+  return 0;
+}
+
+extern "C" int b2pt_scan_exclusive_i32(int32_t n, int32_t* out_host, const int32_t* in_host) {
+  if (n > 0 && (!out_host || !in_host)) return fail(B2PT_ERR_INVALID, "NULL array");
+  return scan_family_host<0>(n, in_host, nullptr, out_host, nullptr);
+}
+
+extern "C" int b2pt_compact_nonzero_i32(int32_t n, int32_t* out_host, const int32_t* in_host) {
+  if (n > 0 && (!out_host || !in_host)) return fail(B2PT_ERR_INVALID, "NULL array");
+  int count = 0;
+  int rc = scan_family_host<1>(n, in_host, nullptr, out_host, &count);
+  return rc ? rc : count;
+}
+
+extern "C" int b2pt_partition_perm(int32_t n, const uint8_t* flags_host, int32_t* perm_host) {
+  if (n > 0 && (!flags_host || !perm_host)) return fail(B2PT_ERR_INVALID, "NULL array");
+  int count = 0;
+  int rc = scan_family_host<2>(n, nullptr, flags_host, perm_host, &count);
+  return rc ? rc : count;
+}
+
+extern "C" int b2pt_sort_desc_perm(int32_t n, const int32_t* keys_host, int32_t* perm_host) {
+  if (n < 0) return fail(B2PT_ERR_INVALID, "n < 0");
+  if (n == 0) return 0;
+  if (!keys_host || !perm_host) return fail(B2PT_ERR_INVALID, "NULL array");
+  std::vector<uint8_t> k8((size_t)n);
+  for (int i = 0; i < n; ++i) {
+    if (keys_host[i] < 0 || keys_host[i] > 255) return fail(B2PT_ERR_RANGE, "keys must be in [0, 255]");
+    k8[i] = (uint8_t)keys_host[i];
+  }
+  Scratch S;
+  uint8_t* dkey = nullptr;
+  int* dperm = nullptr;
+  Counters* ctr = nullptr;
+  unsigned long long* status = nullptr;
+  const int tiles = (n + kSortTile - 1) / kSortTile;
+  CK(S.get(&dkey, (size_t)n));
+  CK(S.get(&dperm, (size_t)n));
+  CK(S.get(&ctr, 1));
+  CK(S.get(&status, (size_t)tiles * 256));
+  CK(cudaMemcpy(dkey, k8.data(), (size_t)n, cudaMemcpyHostToDevice));
+  CK(cudaMemset(ctr, 0, sizeof(Counters)));
+  CK(cudaMemset(status, 0, (size_t)tiles * 256 * 8));
+  CK(cudaMemcpy(&ctr->n_live[0], &n, 4, cudaMemcpyHostToDevice));
+  const unsigned int one = 1;
+  CK(cudaMemcpy(&ctr->serial, &one, 4, cudaMemcpyHostToDevice));
+  k_key_hist_u8<<<std::min((n + 255) / 256, 1184), 256>>>(dkey, n, &ctr->hist[0][0]);
+  MaterialSortPolicy mp;
+  mp.key = dkey;
+  mp.perm = dperm;
+  mp.ctr = ctr;
+  mp.status_ = status;
+  mp.depth = 0;
+  k_onesweep_pass<MaterialSortPolicy><<<tiles, kSortThreads>>>(mp);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(perm_host, dperm, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+extern "C" int b2pt_radix_sort_pairs_u32(int32_t n, uint32_t* keys_host, uint32_t* vals_host) {
+  if (n < 0) return fail(B2PT_ERR_INVALID, "n < 0");
+  if (n == 0) return 0;
+  if (!keys_host || !vals_host) return fail(B2PT_ERR_INVALID, "NULL array");
+  Scratch S;
+  uint32_t *dk = nullptr, *dv = nullptr;
+  CK(S.get(&dk, (size_t)n));
+  CK(S.get(&dv, (size_t)n));
+  CK(cudaMemcpy(dk, keys_host, (size_t)n * 4, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dv, vals_host, (size_t)n * 4, cudaMemcpyHostToDevice));
+  int rc = radix_sort_pairs_dev(dk, dv, n, 0, nullptr);
+  if (rc) return rc;
+  CK(cudaMemcpy(keys_host, dk, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(vals_host, dv, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}

@@ -1,0 +1,223 @@
+// k_lbvh.cuh -- on-GPU LBVH build for OBJ geoms.
+//
+// The reference has no acceleration structure: meshIntersectionTest walks every
+// face for every ray (apps/src/intersections.h:216-230, "//TODO BVH" at
+// apps/src/pathtrace.cu:331).  This builds, per mesh and entirely on the
+// device:
+//   1. centroid bounds (block reduction + ordered-int atomics)
+//   2. 30-bit Morton codes of the triangle centroids
+//   3. LSD radix sort of (code, face) pairs -- four onesweep passes (k_sort.cuh)
+//   4. the Karras 2012 hierarchy (one thread per internal node, duplicates
+//      broken by index)
+//   5. bottom-up refit with one atomic counter per internal node
+//   6. traversal nodes that hold BOTH children's boxes (64 B = 4 x float4):
+//        n0 = (Lmin.xyz, Lmax.x)  n1 = (Lmax.yz, Rmin.xy)
+//        n2 = (Rmin.z, Rmax.xyz)  n3 = (left, right, -, -)   child >= 0: node, < 0: ~leaf slot
+//      and triangles in leaf order as 3 x float4 (v0|face id, v1, v2).
+// Boxes are inflated by `pad` (a few 1e-6 of the mesh extent) so that the
+// conservative slab test can never cull a triangle the reference's exact test
+// would accept: the BVH prunes, it never decides.
+#pragma once
+
+#include <float.h>
+
+#include "pt_device.cuh"
+
+namespace b2pt {
+
+__device__ __forceinline__ unsigned int f2ord(float f) {
+  const unsigned int b = __float_as_uint(f);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__host__ __device__ __forceinline__ float ord2f(unsigned int o) {
+  const unsigned int b = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(b);
+#else
+  float f;
+  memcpy(&f, &b, 4);
+  return f;
+#endif
+}
+
+struct TriBounds {
+  unsigned int lo[3];  // ordered-int min of centroids
+  unsigned int hi[3];
+  int max_depth;
+};
+
+__global__ void k_bounds_init(TriBounds* b) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    for (int k = 0; k < 3; ++k) {
+      b->lo[k] = 0xffffffffu;
+      b->hi[k] = 0u;
+    }
+    b->max_depth = 0;
+  }
+}
+
+__device__ __forceinline__ V3 tri_centroid(const float* fp) {
+  const float minx = fminf(fminf(fp[0], fp[3]), fp[6]), maxx = fmaxf(fmaxf(fp[0], fp[3]), fp[6]);
+  const float miny = fminf(fminf(fp[1], fp[4]), fp[7]), maxy = fmaxf(fmaxf(fp[1], fp[4]), fp[7]);
+  const float minz = fminf(fminf(fp[2], fp[5]), fp[8]), maxz = fmaxf(fmaxf(fp[2], fp[5]), fp[8]);
+  return mk(0.5f * (minx + maxx), 0.5f * (miny + maxy), 0.5f * (minz + maxz));
+}
+
+__global__ void __launch_bounds__(256) k_centroid_bounds(const float* __restrict__ face_pos, int n, TriBounds* out) {
+  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float fp[9];
+    for (int k = 0; k < 9; ++k) fp[k] = face_pos[9 * (size_t)i + k];
+    const V3 c = tri_centroid(fp);
+    lo[0] = fminf(lo[0], c.x); lo[1] = fminf(lo[1], c.y); lo[2] = fminf(lo[2], c.z);
+    hi[0] = fmaxf(hi[0], c.x); hi[1] = fmaxf(hi[1], c.y); hi[2] = fmaxf(hi[2], c.z);
+  }
+  for (int k = 0; k < 3; ++k) {
+    for (int o = 16; o > 0; o >>= 1) {
+      lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+      hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+    }
+  }
+  if ((threadIdx.x & 31) == 0) {
+    for (int k = 0; k < 3; ++k) {
+      atomicMin(&out->lo[k], f2ord(lo[k]));
+      atomicMax(&out->hi[k], f2ord(hi[k]));
+    }
+  }
+}
+
+__device__ __forceinline__ unsigned int expand10(unsigned int v) {
+  v = (v * 0x00010001u) & 0xFF0000FFu;
+  v = (v * 0x00000101u) & 0x0F00F00Fu;
+  v = (v * 0x00000011u) & 0xC30C30C3u;
+  v = (v * 0x00000005u) & 0x49249249u;
+  return v;
+}
+
+__global__ void __launch_bounds__(256) k_morton(const float* __restrict__ face_pos, int n, const TriBounds* b,
+                                                uint32_t* code, uint32_t* val) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float fp[9];
+  for (int k = 0; k < 9; ++k) fp[k] = face_pos[9 * (size_t)i + k];
+  const V3 c = tri_centroid(fp);
+  const float lx = ord2f(b->lo[0]), ly = ord2f(b->lo[1]), lz = ord2f(b->lo[2]);
+  const float ex = fmaxf(ord2f(b->hi[0]) - lx, 1e-30f), ey = fmaxf(ord2f(b->hi[1]) - ly, 1e-30f);
+  const float ez = fmaxf(ord2f(b->hi[2]) - lz, 1e-30f);
+  const unsigned int qx = (unsigned int)fminf(fmaxf((c.x - lx) / ex * 1024.0f, 0.0f), 1023.0f);
+  const unsigned int qy = (unsigned int)fminf(fmaxf((c.y - ly) / ey * 1024.0f, 0.0f), 1023.0f);
+  const unsigned int qz = (unsigned int)fminf(fmaxf((c.z - lz) / ez * 1024.0f, 0.0f), 1023.0f);
+  code[i] = (expand10(qx) << 2) | (expand10(qy) << 1) | expand10(qz);
+  val[i] = (uint32_t)i;
+}
+
+// Leaves in Morton order: triangle triples and padded boxes.
+__global__ void __launch_bounds__(256) k_leaves(const float* __restrict__ face_pos, const uint32_t* __restrict__ sorted_face,
+                                                int n, float pad, float4* tris, float4* leaf_box) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const int f = (int)sorted_face[s];
+  float fp[9];
+  for (int k = 0; k < 9; ++k) fp[k] = face_pos[9 * (size_t)f + k];
+  tris[3 * (size_t)s + 0] = make_float4(fp[0], fp[1], fp[2], __int_as_float(f));
+  tris[3 * (size_t)s + 1] = make_float4(fp[3], fp[4], fp[5], 0.0f);
+  tris[3 * (size_t)s + 2] = make_float4(fp[6], fp[7], fp[8], 0.0f);
+  leaf_box[2 * (size_t)s + 0] = make_float4(fminf(fminf(fp[0], fp[3]), fp[6]) - pad, fminf(fminf(fp[1], fp[4]), fp[7]) - pad,
+                                            fminf(fminf(fp[2], fp[5]), fp[8]) - pad, 0.0f);
+  leaf_box[2 * (size_t)s + 1] = make_float4(fmaxf(fmaxf(fp[0], fp[3]), fp[6]) + pad, fmaxf(fmaxf(fp[1], fp[4]), fp[7]) + pad,
+                                            fmaxf(fmaxf(fp[2], fp[5]), fp[8]) + pad, 0.0f);
+}
+
+// delta(i, j): common prefix of codes i and j, ties broken by index (Karras 2012, sec. 4).
+__device__ __forceinline__ int lbvh_delta(const uint32_t* __restrict__ code, int n, int i, int j) {
+  if (j < 0 || j >= n) return -1;
+  const uint32_t a = code[i], b = code[j];
+  if (a == b) return 32 + __clz((unsigned int)i ^ (unsigned int)j);
+  return __clz(a ^ b);
+}
+
+// One thread per internal node i in [0, n-2]: children and parent links.
+// child encoding: >= 0 internal node, < 0 ~leaf slot.  parent[] has n-1 internal
+// entries followed by n leaf entries.
+__global__ void __launch_bounds__(256) k_karras(const uint32_t* __restrict__ code, int n, int2* children, int* parent) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1) return;
+  const int d = (lbvh_delta(code, n, i, i + 1) - lbvh_delta(code, n, i, i - 1)) >= 0 ? 1 : -1;
+  const int dmin = lbvh_delta(code, n, i, i - d);
+  int lmax = 2;
+  while (lbvh_delta(code, n, i, i + lmax * d) > dmin) lmax <<= 1;
+  int l = 0;
+  for (int t = lmax >> 1; t >= 1; t >>= 1)
+    if (lbvh_delta(code, n, i, i + (l + t) * d) > dmin) l += t;
+  const int j = i + l * d;
+  const int dnode = lbvh_delta(code, n, i, j);
+  int s = 0;
+  for (int div = 2, t = (l + div - 1) / div; ; div <<= 1, t = (l + div - 1) / div) {
+    if (lbvh_delta(code, n, i, i + (s + t) * d) > dnode) s += t;
+    if (t <= 1) break;
+  }
+  const int gamma = i + s * d + min(d, 0);
+  const int lo = min(i, j), hi = max(i, j);
+  const int left = (lo == gamma) ? ~gamma : gamma;
+  const int right = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
+  children[i] = make_int2(left, right);
+  if (left >= 0) parent[left] = i; else parent[(n - 1) + gamma] = i;
+  if (right >= 0) parent[right] = i; else parent[(n - 1) + gamma + 1] = i;
+  if (i == 0) parent[0] = -1;
+}
+
+// Bottom-up refit: the second thread to reach a node computes its box.
+__global__ void __launch_bounds__(256) k_refit(int n, const int2* __restrict__ children, const int* __restrict__ parent,
+                                               const float4* __restrict__ leaf_box, float4* node_box, int* visit,
+                                               TriBounds* info) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  int node = parent[(n - 1) + s];
+  int depth = 1;
+  while (node >= 0) {
+    if (atomicAdd(&visit[node], 1) == 0) return;  // first arrival: the sibling subtree is not done yet
+    __threadfence();
+    const int2 c = children[node];
+    const volatile float4* lb = c.x >= 0 ? node_box + 2 * (size_t)c.x : leaf_box + 2 * (size_t)(~c.x);
+    const volatile float4* rb = c.y >= 0 ? node_box + 2 * (size_t)c.y : leaf_box + 2 * (size_t)(~c.y);
+    const float lminx = lb[0].x, lminy = lb[0].y, lminz = lb[0].z, lmaxx = lb[1].x, lmaxy = lb[1].y, lmaxz = lb[1].z;
+    const float rminx = rb[0].x, rminy = rb[0].y, rminz = rb[0].z, rmaxx = rb[1].x, rmaxy = rb[1].y, rmaxz = rb[1].z;
+    node_box[2 * (size_t)node + 0] = make_float4(fminf(lminx, rminx), fminf(lminy, rminy), fminf(lminz, rminz), 0.0f);
+    node_box[2 * (size_t)node + 1] = make_float4(fmaxf(lmaxx, rmaxx), fmaxf(lmaxy, rmaxy), fmaxf(lmaxz, rmaxz), 0.0f);
+    __threadfence();
+    node = parent[node];
+    ++depth;
+  }
+  (void)depth;
+}
+
+// Depth of every leaf (tree statistics only).
+__global__ void __launch_bounds__(256) k_tree_depth(int n, const int* __restrict__ parent, TriBounds* info) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  int node = parent[(n - 1) + s];
+  int depth = 1;
+  while (node >= 0) {
+    node = parent[node];
+    ++depth;
+  }
+  atomicMax(&info->max_depth, depth);
+}
+
+// Traversal nodes: both children's boxes in the parent.
+__global__ void __launch_bounds__(256) k_emit_nodes(int n, const int2* __restrict__ children,
+                                                    const float4* __restrict__ leaf_box,
+                                                    const float4* __restrict__ node_box, float4* nodes) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1) return;
+  const int2 c = children[i];
+  const float4* lb = c.x >= 0 ? node_box + 2 * (size_t)c.x : leaf_box + 2 * (size_t)(~c.x);
+  const float4* rb = c.y >= 0 ? node_box + 2 * (size_t)c.y : leaf_box + 2 * (size_t)(~c.y);
+  const float4 l0 = lb[0], l1 = lb[1], r0 = rb[0], r1 = rb[1];
+  nodes[4 * (size_t)i + 0] = make_float4(l0.x, l0.y, l0.z, l1.x);
+  nodes[4 * (size_t)i + 1] = make_float4(l1.y, l1.z, r0.x, r0.y);
+  nodes[4 * (size_t)i + 2] = make_float4(r0.z, r1.x, r1.y, r1.z);
+  nodes[4 * (size_t)i + 3] = make_float4(__int_as_float(c.x), __int_as_float(c.y), 0.0f, 0.0f);
+}
+
+}  // namespace b2pt

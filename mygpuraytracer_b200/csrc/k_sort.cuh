@@ -1,0 +1,188 @@
+// k_sort.cuh -- single-pass radix partitioning (onesweep) and its two users.
+//
+// (1) Material sort.  Replaces thrust::sort_by_key(dev_intersections, dev_paths,
+//     sortByMaterial()) (apps/src/pathtrace.cu:512-516,612): a STABLE sort by
+//     DESCENDING materialId whose 32-byte keys and 44-byte values the reference
+//     moves through every merge pass.  Here the key is one byte, written by
+//     k_intersect together with a per-depth material histogram, and the output
+//     is only the permutation perm[sorted slot] = pre-sort slot (4 B/path); the
+//     payload is gathered once, by the shade kernel.  The stable order by
+//     (255 - material) is the unique stable descending order, so the
+//     permutation is identical to thrust's.
+// (2) LSD radix sort of (Morton code, face) pairs for the LBVH build: four
+//     8-bit passes of the same kernel.
+//
+// One pass = one kernel: a tile ranks its 4096 keys locally (warp match_any),
+// publishes its per-bin counts, and resolves its per-bin exclusive prefix by
+// decoupled look-back over the tiles before it.  Tiles are handed out by a
+// device ticket so a tile's predecessors are always resident or finished.
+// Bin bases come from a histogram computed beforehand (by k_intersect for the
+// material sort, by k_radix_hist for the LSD sort).
+#pragma once
+
+#include "pt_device.cuh"
+
+namespace b2pt {
+
+constexpr int kSortThreads = 256;
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kSortRows = 16;                           // 32-key rows per warp
+constexpr int kSortTile = kSortWarps * kSortRows * 32;  // 4096 keys
+static_assert(kSortThreads == kMaxMaterials, "one thread per bin");
+
+// Policy for the material sort of depth `depth`.
+struct MaterialSortPolicy {
+  const uint8_t* key;
+  int* perm;
+  Counters* ctr;
+  unsigned long long* status_;
+  int depth;
+  __device__ __forceinline__ int n() const { return ctr->n_live[depth]; }
+  __device__ __forceinline__ unsigned int* ticket() const { return &ctr->sort_ticket[depth]; }
+  __device__ __forceinline__ unsigned long long* status() const { return status_; }
+  __device__ __forceinline__ unsigned int epoch() const {
+    return ctr->serial * (unsigned int)(kMaxDepth + 1) + (unsigned int)depth + 1u;
+  }
+  // ascending digit == descending material
+  __device__ __forceinline__ unsigned int digit(int idx) const { return 255u - (unsigned int)key[idx]; }
+  __device__ __forceinline__ unsigned int bin_total(int bin) const { return ctr->hist[depth][255 - bin]; }
+  __device__ __forceinline__ void scatter(int idx, unsigned int pos) const { perm[pos] = idx; }
+};
+
+// Policy for one 8-bit pass of the LSD pair sort.
+struct RadixPassPolicy {
+  const uint32_t* key_in;
+  const uint32_t* val_in;
+  uint32_t* key_out;
+  uint32_t* val_out;
+  const unsigned int* hist;  // 256 bin totals of this digit
+  unsigned int* ticket_;
+  unsigned long long* status_;
+  unsigned int epoch_;
+  int n_;
+  int shift;
+  __device__ __forceinline__ int n() const { return n_; }
+  __device__ __forceinline__ unsigned int* ticket() const { return ticket_; }
+  __device__ __forceinline__ unsigned long long* status() const { return status_; }
+  __device__ __forceinline__ unsigned int epoch() const { return epoch_; }
+  __device__ __forceinline__ unsigned int digit(int idx) const { return (key_in[idx] >> shift) & 255u; }
+  __device__ __forceinline__ unsigned int bin_total(int bin) const { return hist[bin]; }
+  __device__ __forceinline__ void scatter(int idx, unsigned int pos) const {
+    key_out[pos] = key_in[idx];
+    val_out[pos] = val_in[idx];
+  }
+};
+
+template <typename Policy>
+__global__ void __launch_bounds__(kSortThreads) k_onesweep_pass(Policy p) {
+  __shared__ unsigned int wcnt[kSortWarps][256];
+  __shared__ unsigned int bin_base[256];
+  __shared__ unsigned int tile_excl[256];
+  __shared__ unsigned int warp_tot[kSortWarps];
+  __shared__ unsigned int s_tile;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = p.n();
+  if (tid == 0) s_tile = atomicAdd(p.ticket(), 1u);
+  for (int i = tid; i < kSortWarps * 256; i += kSortThreads) (&wcnt[0][0])[i] = 0;
+  __syncthreads();
+  const unsigned int tile = s_tile;
+  if ((long long)tile * kSortTile >= (long long)n) return;
+  const unsigned int epoch = p.epoch();
+
+  // ---- local ranking: warp w owns 512 consecutive keys, 32 at a time ----------
+  const int wbase = (int)tile * kSortTile + warp * (kSortRows * 32);
+  unsigned short lrank[kSortRows];
+  unsigned short ldig[kSortRows];
+#pragma unroll
+  for (int r = 0; r < kSortRows; ++r) {
+    const int idx = wbase + r * 32 + lane;
+    const bool valid = idx < n;
+    const unsigned int dig = valid ? p.digit(idx) : 256u + (unsigned int)lane;  // invalid lanes match nobody
+    const unsigned int peers = __match_any_sync(0xffffffffu, dig);
+    unsigned int before = 0;
+    if (valid) before = wcnt[warp][dig];
+    __syncwarp();
+    if (valid && lane == __ffs(peers) - 1) wcnt[warp][dig] = before + __popc(peers);
+    __syncwarp();
+    lrank[r] = (unsigned short)(before + __popc(peers & ((1u << lane) - 1u)));
+    ldig[r] = (unsigned short)dig;
+  }
+  __syncthreads();
+
+  // ---- per bin: offsets of the warps inside the tile, then look-back -----------
+  {
+    const int b = tid;  // one thread per bin
+    unsigned int run = 0;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) {
+      const unsigned int c = wcnt[w][b];
+      wcnt[w][b] = run;
+      run += c;
+    }
+    const unsigned int total = p.bin_total(b);
+    unsigned int excl = 0;
+    if (total != 0) {  // bins nobody holds are never read
+      unsigned long long* mine = p.status() + (size_t)tile * 256 + b;
+      st_volatile_u64(mine, lb_pack(epoch, tile == 0 ? 2u : 1u, run));
+      if (tile > 0) {
+        for (int t = (int)tile - 1; t >= 0; --t) {
+          const unsigned long long* theirs = p.status() + (size_t)t * 256 + b;
+          unsigned long long w;
+          do {
+            w = ld_volatile_u64(theirs);
+          } while (lb_epoch(w) != epoch || lb_flag(w) == 0u);
+          excl += lb_value(w);
+          if (lb_flag(w) == 2u) break;
+        }
+        st_volatile_u64(mine, lb_pack(epoch, 2u, excl + run));
+      }
+    }
+    tile_excl[b] = excl;
+    // exclusive scan of the bin totals -> bin bases
+    unsigned int v = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int t = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += t;
+    }
+    if (lane == 31) warp_tot[warp] = v;
+    __syncthreads();
+    unsigned int add = 0;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) add += (w < warp) ? warp_tot[w] : 0u;
+    bin_base[b] = v - total + add;
+  }
+  __syncthreads();
+
+  // ---- scatter ----------------------------------------------------------------------
+#pragma unroll
+  for (int r = 0; r < kSortRows; ++r) {
+    const int idx = wbase + r * 32 + lane;
+    if (idx < n) {
+      const unsigned int dig = ldig[r];
+      p.scatter(idx, bin_base[dig] + tile_excl[dig] + wcnt[warp][dig] + lrank[r]);
+    }
+  }
+}
+
+// All four 8-bit digit histograms of a key array in one read.
+__global__ void __launch_bounds__(256) k_radix_hist(const uint32_t* __restrict__ key, int n, unsigned int* hist /*[4][256]*/) {
+  __shared__ unsigned int sh[4][256];
+  for (int i = threadIdx.x; i < 1024; i += 256) (&sh[0][0])[i] = 0;
+  __syncthreads();
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    const uint32_t k = key[i];
+    atomicAdd(&sh[0][k & 255u], 1u);
+    atomicAdd(&sh[1][(k >> 8) & 255u], 1u);
+    atomicAdd(&sh[2][(k >> 16) & 255u], 1u);
+    atomicAdd(&sh[3][(k >> 24) & 255u], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 1024; i += 256) {
+    const unsigned int c = (&sh[0][0])[i];
+    if (c) atomicAdd(&hist[i], c);
+  }
+}
+
+}  // namespace b2pt

@@ -1,0 +1,122 @@
+// pt_device.cuh -- device-side data layout of the wavefront loop.
+//
+// HBM layout (P = W*H paths, all arrays 16-byte aligned, read and written with
+// 128-bit accesses):
+//
+//   path state, SoA, double buffered (A/B)          48 B/path
+//     s0[i] = (origin.xyz, pixelIndex)      PathSegment::ray.origin / pixelIndex
+//     s1[i] = (direction.xyz, remainingBounces)
+//     s2[i] = (color.rgb, unused)           PathSegment::color (throughput)
+//   hit records, SoA                                 32 B/path
+//     h0[i] = (t, normal.xyz)               ShadeableIntersection::t / surfaceNormal
+//     h1[i] = (u, v, geom | material<<16, face)
+//   sort keys          uint8 material id              1 B/path
+//   sort permutation   int32                          4 B/path
+//
+// The reference's AoS structs are apps/src/sceneStructs.h:105-121 (44-byte
+// PathSegment, 32-byte ShadeableIntersection used as the sort key).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "pt_math.cuh"
+
+namespace b2pt {
+
+constexpr int kMaxMaterials = 256;  // sort key is one byte
+constexpr int kMaxGeoms = 64;       // analytic geoms + meshes, staged in shared memory
+constexpr int kMaxDepth = 62;
+
+struct PathBuf {
+  float4* s0;
+  float4* s1;
+  float4* s2;
+};
+
+struct HitBuf {
+  float4* h0;
+  float4* h1;
+};
+
+struct DevTexture {
+  const uint8_t* texels;
+  int w, h, channels;
+};
+
+// One geom as the kernels read it (Geom, apps/src/sceneStructs.h:50-70).
+struct DevGeom {
+  Mat34 inv;   // inverseTransform
+  Mat34 fwd;   // transform
+  Mat34 invT;  // invTranspose
+  int type;
+  int material;
+  int mesh;   // index into DevScene::meshes, -1 for analytic geoms
+  int rigid;  // 1 if object-space and world-space distances agree (scale == 1)
+};
+
+struct DevMesh {
+  const float4* nodes;    // 4 x float4 per internal BVH node (see k_lbvh.cuh)
+  const float4* tris;     // 3 x float4 per triangle in BVH leaf order: (v0,face) (v1,-) (v2,-)
+  const float* face_pos;  // 9 floats per face, original order
+  const float* face_uv;   // 6 floats per face, original order
+  int n_faces;
+  int root;  // >= 0: internal node index; < 0: ~leaf (single-triangle mesh)
+  DevTexture kd, ks, bump, ke;
+};
+
+struct DevMaterial {  // Material, apps/src/sceneStructs.h:72-82
+  float color[3];
+  float specular_exponent;
+  float specular_color[3];
+  float has_reflective;
+  float has_refractive;
+  float ior;
+  float emittance;
+};
+
+struct DevCamera {  // Camera, apps/src/sceneStructs.h:84-93
+  int res_x, res_y;
+  V3 position, view, up, right;
+  float plx, ply;
+};
+
+struct DevScene {
+  const DevGeom* geoms;
+  const DevMesh* meshes;
+  const DevMaterial* materials;
+  int n_geoms, n_meshes, n_materials;
+};
+
+// Per-iteration device counters; zeroed by k_iter_begin.  Nothing in the
+// depth loop is read back by the host: every kernel takes its element count
+// from here (the reference syncs three times per depth).
+struct Counters {
+  unsigned int serial;                    // iterations started (lookback epochs)
+  int n_live[kMaxDepth + 2];              // paths entering depth d
+  unsigned int ray_ticket[kMaxDepth + 1];    // dynamic work distribution, intersect
+  unsigned int sort_ticket[kMaxDepth + 1];   // tile order of the sort
+  unsigned int shade_ticket[kMaxDepth + 1];  // tile order of shade + compaction
+  unsigned int hist[kMaxDepth + 1][kMaxMaterials];  // material histogram per depth
+  unsigned long long segments;            // total path segments since creation
+};
+
+// Decoupled look-back status word: epoch in the high half so the arrays are
+// never cleared; flag 1 = tile aggregate, 2 = inclusive prefix.
+__device__ __forceinline__ unsigned long long lb_pack(unsigned int epoch, unsigned int flag, unsigned int value) {
+  return ((unsigned long long)epoch << 32) | ((unsigned long long)flag << 30) | (unsigned long long)value;
+}
+__device__ __forceinline__ unsigned int lb_epoch(unsigned long long w) { return (unsigned int)(w >> 32); }
+__device__ __forceinline__ unsigned int lb_flag(unsigned long long w) { return (unsigned int)(w >> 30) & 3u; }
+__device__ __forceinline__ unsigned int lb_value(unsigned long long w) { return (unsigned int)w & 0x3fffffffu; }
+
+__device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+}  // namespace b2pt

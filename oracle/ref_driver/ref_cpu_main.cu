@@ -101,10 +101,12 @@ int main(int argc, char** argv) {
   for (size_t i = 0; i < scene->geoms.size(); ++i) {
     Geom& g = scene->geoms[i];
     g.dev_faces = scene->allFaces[i].data();
-    g.kd = scene->kdTextures[i];
-    g.ks = scene->ksTextures[i];
-    g.ke = scene->keTextures[i];
-    g.bump = scene->bumpTextures[i];
+    // the reference indexes these vectors unguarded (UB for OBJ files whose
+    // MTL names no maps); a missing entry means "no texture"
+    g.kd = i < scene->kdTextures.size() ? scene->kdTextures[i] : Texture();
+    g.ks = i < scene->ksTextures.size() ? scene->ksTextures[i] : Texture();
+    g.ke = i < scene->keTextures.size() ? scene->keTextures[i] : Texture();
+    g.bump = i < scene->bumpTextures.size() ? scene->bumpTextures[i] : Texture();
   }
   if (a.iters <= 0) return 0;
 
@@ -225,6 +227,11 @@ int main(int argc, char** argv) {
         std::copy(itmp.begin(), itmp.begin() + num_paths, isects.begin());
         std::copy(ptmp.begin(), ptmp.begin() + num_paths, paths.begin());
         if (dump) ref_write_npy(w.name(depth, "sort_perm"), "<i4", order.data(), 4, num_paths, 1);
+      }
+      if (dump) {
+        std::vector<int32_t> px(num_paths);
+        for (int i = 0; i < num_paths; ++i) px[i] = paths[i].pixelIndex;
+        ref_write_npy(w.name(depth, "sorted_pixel"), "<i4", px.data(), 4, num_paths, 1);
       }
       depth++;
       // shadeFakeMaterial, :397-498
