@@ -1,0 +1,395 @@
+#!/usr/bin/env python
+"""bench.py -- Mpaths/s of the wavefront path-tracing loop (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (config.workload): scenes/cornellSpaceship.txt at 1920x1080, depth 8
+-- the configuration BASELINE.json's metric is quoted on -- with the generated
+STAND-IN MESH (the reference's spaceship OBJ is missing from its checkout) and
+the reference's four 4096x4096 textures when the build copied them, procedural
+ones otherwise (config.textures says which).
+
+A step is ONE iteration (one sample per pixel through the whole depth loop) on
+every rank.  Ranks shard samples per pixel: rank r of N renders iteration
+indices r+1, r+1+N, ... into its own accumulator; after the K timed steps the
+accumulators are combined with one NCCL reduce (inside the timed region).
+`value` = N*K*W*H paths / max-over-ranks device time, scaling "weak".
+
+Keys beyond the base contract:
+  e2e           the same metric through the reference-facing call
+                b2pt_pathtrace(): every step renders one iteration and copies
+                the running sum and the albedo AOV to pinned HOST buffers, as
+                the reference's pathtrace() does (apps/src/pathtrace.cu:663-668)
+  roofline      the dominant kernel (k_intersect): algorithmic bytes (56 B per
+                path segment: 24 B ray read + 32 B hit record written) over its
+                device time measured with CUDA events in this run, against the
+                measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  roofline_iter Bytes_iter = 84*P + 280*S over the step
+  cpu_baseline  the reference's own intersections.h / interactions.h compiled
+                for the host (oracle/_ref/ref_cpu, kind "reference") or the C
+                oracle (kind "port") on a bounded sample of the same scene
+  reference_gpu the reference's unmodified pathtrace.cu built for sm_100a
+                (oracle/_ref/ref_gpu) on the same workload, same GPU, when the
+                binary travelled to the box (the >=10x comparator of north_star)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "Mpaths/s"
+SCENE = "cornellSpaceship"
+WIDTH, HEIGHT, DEPTH = 1920, 1080, 8
+CPU_SAMPLE = (48, 27)  # resolution of the bounded CPU sample (same scene, mesh, depth): ~10 s per iteration on 8 cores
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+# ---------------------------------------------------------------------------------------
+# workload
+# ---------------------------------------------------------------------------------------
+def prepare_assets(triangles: int):
+    from mygpuraytracer_b200 import assets
+
+    ref_tex = os.path.join(ROOT, "oracle", "_ref", "run", "textures")
+    root = assets.prepare(reference_textures=ref_tex if os.path.isdir(ref_tex) else None)
+    assets.set_mesh(root, triangles)
+    return root, ("reference JPEGs" if assets.textures_are_reference(root) else "procedural 4096x4096 (reference JPEGs absent)")
+
+
+def workload_config(args, n_tris: int, textures: str):
+    return {
+        "workload": f"scenes/{SCENE}.txt {args.width}x{args.height} depth {args.depth}, STAND-IN MESH {n_tris} triangles "
+                    f"(reference OBJ missing), AA on, DOF off, material sort on",
+        "scene": SCENE, "width": args.width, "height": args.height, "depth": args.depth,
+        "triangles": n_tris, "textures": textures,
+        "step": "one iteration (1 spp) per rank", "sharding": "samples-per-pixel, one NCCL reduce per frame",
+        "l2": "working set per step (path state 2x48 B + hits 32 B per path, 4 textures, BVH) > 126 MB L2; no flush",
+        "rng": "slot-keyed minstd (reference mode)", "trig": "native",
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------
+# CPU legs
+# ---------------------------------------------------------------------------------------
+def cpu_sample(root: str, args, steps: int = 1, res=CPU_SAMPLE):
+    """Time the reference's CPU code on a bounded sample: the same scene file,
+    mesh, textures and depth at a reduced resolution, `steps` iterations."""
+    from mygpuraytracer_b200 import assets
+
+    w, h = res
+    scene_txt = assets.scene_file(SCENE, w, h, depth=args.depth, root=root)
+    sample = f"{SCENE} {w}x{h} depth {args.depth}, same mesh/textures, {steps} iteration(s) of {w * h} paths"
+    try:
+        from oracle import harness
+
+        if harness.have("ref_cpu"):
+            # run from the asset tree's bin/ so '../models/...' resolves to the same files
+            cmd = [os.path.join(harness.REF_DIR, "ref_cpu"), "--scene", scene_txt, "--iters", str(steps)]
+            t0 = time.time()
+            p = subprocess.run(cmd, cwd=os.path.join(root, "bin"), capture_output=True, text=True, timeout=1800)
+            wall = time.time() - t0
+            for line in p.stdout.splitlines():
+                if line.startswith("REF_CPU_RESULT"):
+                    r = json.loads(line.split(" ", 1)[1])
+                    return {"value": r["mpaths_per_s"], "unit": METRIC, "cores": r["threads"], "kind": "reference",
+                            "sample": sample, "ms_per_iteration": r["ms_per_iter"], "wall_s": round(wall, 2)}
+            log("ref_cpu produced no result line:", p.stderr[-500:])
+    except Exception as e:  # fall through to the port
+        log("ref_cpu unavailable:", e)
+    from mygpuraytracer_b200 import abi, api
+    from oracle import oracle
+
+    pod = api.Scene(scene_txt).pod
+    t0 = time.time()
+    oracle.render(pod, abi.default_options(), 1, steps, 1)
+    dt = time.time() - t0
+    return {"value": w * h * steps / dt / 1e6, "unit": METRIC, "cores": oracle.num_threads(), "kind": "port",
+            "sample": sample, "ms_per_iteration": 1e3 * dt / steps, "wall_s": round(dt, 2)}
+
+
+def reference_gpu(root: str, args):
+    """The unmodified reference pathtrace.cu (sm_100a) on the full workload."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_gpu")
+    if not os.access(exe, os.X_OK) or args.ref_gpu_iters <= 0:
+        return None
+    from mygpuraytracer_b200 import assets
+
+    scene_txt = assets.scene_file(SCENE, args.width, args.height, depth=args.depth, root=root)
+    try:
+        p = subprocess.run([exe, "--scene", scene_txt, "--time", "--iters", str(args.ref_gpu_iters), "--warmup", "0"],
+                           cwd=os.path.join(root, "bin"), capture_output=True, text=True, timeout=args.ref_gpu_timeout)
+        for line in p.stdout.splitlines():
+            if line.startswith("REF_GPU_RESULT"):
+                r = json.loads(line.split(" ", 1)[1])
+                return {"what": "reference apps/src/pathtrace.cu, unmodified, nvcc -O3 sm_100a, same GPU and workload",
+                        "iterations": r["iters"], "ms_per_iteration_loop": r["loop_ms_per_iter"],
+                        "ms_per_iteration_call": r["call_ms_per_iter"], "mpaths_per_s": r["mpaths_per_s_call"]}
+        return {"error": (p.stderr or p.stdout)[-300:]}
+    except subprocess.TimeoutExpired:
+        return {"error": f"timed out after {args.ref_gpu_timeout}s"}
+
+
+# ---------------------------------------------------------------------------------------
+# arms
+# ---------------------------------------------------------------------------------------
+def run_reference(args, rank: int, world: int):
+    if rank != 0:
+        return
+    root, textures = prepare_assets(args.triangles)
+    from mygpuraytracer_b200 import standin_mesh
+
+    n_tris = len(standin_mesh.build(args.triangles)[3])
+    # Size the sample so that steps+warmup iterations fit in ~150 s: the brute-force
+    # reference costs O(paths x triangles), so time scales with the pixel count.
+    probe = cpu_sample(root, args, 1, (16, 9))
+    per_pixel_s = probe["ms_per_iteration"] * 1e-3 / (16 * 9)
+    budget_s = 150.0 / max(1, args.steps + min(args.warmup, 1))
+    pixels = max(16 * 9, min(CPU_SAMPLE[0] * CPU_SAMPLE[1], int(budget_s / per_pixel_s)))
+    h = max(9, int((pixels * 9 / 16) ** 0.5))
+    w = max(16, pixels // h)
+    r = cpu_sample(root, args, max(1, args.steps + min(args.warmup, 1)), (w, h))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": METRIC, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["ms_per_iteration"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, n_tris, textures),
+        "cpu_baseline": {"value": r["value"], "unit": METRIC, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": f"each step is one iteration of the bounded sample ({w}x{h}); Mpaths/s is size independent",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, rank: int, world: int, local_rank: int):
+    import numpy as np
+    import torch
+
+    from mygpuraytracer_b200 import abi, api, assets, standin_mesh
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    if rank == 0:
+        root, textures = prepare_assets(args.triangles)
+    if dist:
+        dist.barrier()
+    if rank != 0:
+        root, textures = prepare_assets(args.triangles)
+    t0 = time.time()
+    scene = api.Scene(assets.scene_file(SCENE, args.width, args.height, depth=args.depth, root=root))
+    load_s = time.time() - t0
+    pod = scene.pod
+    n_tris = len(pod.face_pos)
+    P = pod.n_pixels
+    opt = abi.default_options(device=local_rank)
+    r = api.Renderer(scene, opt)
+    mesh_geom = int(np.nonzero(pod.geoms["type"] == abi.OBJ)[0][0])
+    bvh = r.bvh_info(mesh_geom)
+
+    # everything on one torch stream: kernels, the NCCL reduce and the timing events
+    stream = torch.cuda.Stream()
+    acc = torch.zeros(P * 3, dtype=torch.float32, device="cuda")
+    r.set_stream_ptr(stream.cuda_stream)
+    r.set_device_image_ptr(acc.data_ptr())
+
+    K, W = args.steps, args.warmup
+    first = rank + 1
+
+    def barrier():
+        if dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput --------------------------------------------------------
+    with torch.cuda.stream(stream):
+        r.render(first, W, world)
+        barrier()
+        acc.zero_()
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        launches0 = r.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        r.render(first + W * world, K, world)
+        if dist:
+            dist.reduce(acc, dst=0)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if rank == 0 else None
+        launches = r.launch_count() - launches0
+        live = r.live_counts()
+    t = torch.tensor([ms], device="cuda")
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * K * P / (ms_max * 1e-3) / 1e6
+    segments = int(live[: args.depth].sum())
+
+    # ---- per-kernel times of one iteration (CUDA events around every launch) ------------------
+    with torch.cuda.stream(stream):
+        prof = [r.profile_iteration(first + (W + K + i) * world) for i in range(3)]
+        barrier()
+    prof = {k: statistics.median(p[k] for p in prof) for k in prof[0]}
+
+    # ---- end to end: the reference-facing call with host buffers ------------------------------
+    host_img = torch.empty(P * 3, dtype=torch.float32).pin_memory()
+    host_alb = torch.empty(P * 3, dtype=torch.float32).pin_memory()
+    img_np, alb_np = host_img.numpy().reshape(P, 3), host_alb.numpy().reshape(P, 3)
+    with torch.cuda.stream(stream):
+        r.reset()
+        for i in range(min(W, 3)):
+            r.pathtrace(first + i * world, img_np, alb_np)
+        barrier()
+        e0.record(stream)
+        for i in range(K):
+            r.pathtrace(first + (W + i) * world, img_np, alb_np)
+        if dist:
+            dist.reduce(acc, dst=0)
+        e1.record(stream)
+        barrier()
+        e2e_ms = e0.elapsed_time(e1)
+    t = torch.tensor([e2e_ms], device="cuda")
+    if dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * K * P / (float(t.item()) * 1e-3) / 1e6
+    checksum = float(np.float64(img_np.sum()))
+
+    if rank == 0:
+        peak, peak_src = hbm_peak()
+        isect_bytes = 56.0 * segments
+        isect_gbs = isect_bytes / (prof["intersect"] * 1e-3) / 1e9 if prof["intersect"] > 0 else 0.0
+        iter_bytes = 84.0 * P + 280.0 * segments
+        iter_gbs = iter_bytes / (ms_max / K * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, n_tris, textures),
+            "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 2 * P * 12,
+                    "call": "b2pt_pathtrace(ctx, iter, host_image, host_albedo) -- pathtrace() of apps/src/pathtrace.h:9",
+                    "ms_per_step": float(t.item()) / K},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"kernel": "k_intersect<BVH>", "bound": "hbm", "achieved": isect_gbs, "peak": peak, "unit": "GB/s",
+                         "frac": isect_gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_step": isect_bytes, "launches_per_step": args.depth,
+                         "ms_per_step": prof["intersect"],
+                         "note": "BVH traversal is latency/issue bound, not HBM bound; see profiles/ for pipe utilisation"},
+            "roofline_iter": {"bytes_per_step": iter_bytes, "achieved": iter_gbs, "peak": peak, "unit": "GB/s",
+                              "frac": iter_gbs / peak, "formula": "84*P + 280*S"},
+            "kernel_ms_per_step": prof,
+            "segments_per_step": segments, "live_paths_per_depth": [int(x) for x in live[: args.depth + 1]],
+            "bvh": {"triangles": int(bvh.n_faces), "nodes": int(bvh.n_nodes), "max_depth": int(bvh.max_depth),
+                    "build_ms": float(bvh.build_ms)},
+            "scene_load_s": round(load_s, 2), "image_checksum": checksum,
+        }
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = {k: v for k, v in cpu_sample(root, args, 1).items()}
+            rg = reference_gpu(root, args)
+            if rg is not None:
+                line["reference_gpu"] = rg
+        print(json.dumps(line), flush=True)
+    r.close()
+    if dist:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--width", type=int, default=WIDTH)
+    ap.add_argument("--height", type=int, default=HEIGHT)
+    ap.add_argument("--depth", type=int, default=DEPTH)
+    ap.add_argument("--triangles", type=int, default=250_000)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / reference_gpu legs")
+    ap.add_argument("--ref-gpu-iters", type=int, default=1)
+    ap.add_argument("--ref-gpu-timeout", type=int, default=240)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

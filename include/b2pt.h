@@ -210,6 +210,11 @@ int b2pt_set_device_image(B2ptCtx* ctx, float* image_dev);
 /* The CUDA stream (cudaStream_t) all work of this context is queued on. */
 void* b2pt_stream(B2ptCtx* ctx);
 
+/* Queue all further work on a caller-owned stream (e.g. the stream a
+ * collective library runs on, so render -> reduce needs no host sync).
+ * NULL restores the context's own stream.  Synchronises the old stream. */
+int b2pt_set_stream(B2ptCtx* ctx, void* cuda_stream);
+
 /* Mirror of timer().getGpuElapsedTimeForPreviousOperation()
  * (apps/src/main.cpp:263): milliseconds of the depth loop of the last
  * rendered iteration (the window of apps/src/pathtrace.cu:583-653). */
@@ -227,6 +232,12 @@ int b2pt_tonemap_rgba8(B2ptCtx* ctx, const float* src_dev, int32_t iter, uint8_t
  * paths entering depth d (n_live[0] = W*H).  Returns the number of depths
  * written (<= cap).  Synchronises. */
 int b2pt_live_counts(B2ptCtx* ctx, int32_t* n_live, int32_t cap);
+
+/* Per-kernel device time of ONE iteration, measured with CUDA events around
+ * every launch (no graph): ms[0] generate, ms[1] intersect (sum over depths),
+ * ms[2] material sort, ms[3] shade+compact+gather, ms[4] whole iteration.
+ * The iteration is rendered and accumulated like any other.  Synchronous. */
+int b2pt_profile_iteration(B2ptCtx* ctx, int32_t iter, float ms[5]);
 
 /* Kernel launches issued by this context since creation. */
 int64_t b2pt_launch_count(B2ptCtx* ctx);

@@ -186,6 +186,8 @@ SYMBOLS = {
     "b2pt_device_albedo": (_vp, [_vp]),
     "b2pt_set_device_image": (C.c_int, [_vp, _vp]),
     "b2pt_stream": (_vp, [_vp]),
+    "b2pt_set_stream": (C.c_int, [_vp, _vp]),
+    "b2pt_profile_iteration": (C.c_int, [_vp, _i32, _f32p]),
     "b2pt_last_loop_ms": (C.c_float, [_vp]),
     "b2pt_tonemap_rgba8": (C.c_int, [_vp, _vp, _i32, _vp]),
     "b2pt_live_counts": (C.c_int, [_vp, _i32p, _i32]),

@@ -209,6 +209,14 @@ class Renderer:
     def set_device_image_ptr(self, ptr: int) -> None:
         _check(self.lib.b2pt_set_device_image(self._h, C.c_void_p(ptr)))
 
+    def set_stream_ptr(self, ptr: int) -> None:
+        _check(self.lib.b2pt_set_stream(self._h, C.c_void_p(ptr) if ptr else None))
+
+    def profile_iteration(self, iteration: int) -> Dict[str, float]:
+        ms = (C.c_float * 5)()
+        _check(self.lib.b2pt_profile_iteration(self._h, iteration, ms))
+        return dict(zip(["generate", "intersect", "sort", "shade", "iteration"], [float(x) for x in ms]))
+
     def stream_ptr(self) -> int:
         return int(self.lib.b2pt_stream(self._h) or 0)
 

@@ -104,7 +104,8 @@ struct StageRecord {
 
 struct B2ptCtx {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // where work is queued
+  cudaStream_t own_stream = nullptr;  // created by the context
   B2ptOptions opt{};
   int W = 0, H = 0, P = 0, depth = 0, loop_depth = 0;
   int n_geoms = 0, n_materials = 0;
@@ -381,7 +382,8 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, c->device));
   c->sm_count = prop.multiProcessorCount;
-  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  c->stream = c->own_stream;
   CK(cudaEventCreate(&c->ev_loop_a));
   CK(cudaEventCreate(&c->ev_loop_b));
 
@@ -505,7 +507,7 @@ extern "C" void b2pt_destroy(B2ptCtx* c) {
   for (void* p : c->allocs) cudaFree(p);
   if (c->ev_loop_a) cudaEventDestroy(c->ev_loop_a);
   if (c->ev_loop_b) cudaEventDestroy(c->ev_loop_b);
-  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
 }
 
@@ -552,10 +554,24 @@ static void unpack3(const std::vector<float4>& v, int n, float* dst) {
 }
 
 // Queue the kernels of one iteration (also the body that gets graph-captured).
-static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool capturing = false) {
+struct KernelTimes {  // optional per-launch event timing (b2pt_profile_iteration)
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> kind;  // kind of the launch that FOLLOWS event i
+  cudaStream_t s = nullptr;
+  void mark(int k) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    ev.push_back(e);
+    kind.push_back(k);
+  }
+};
+
+static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool capturing = false, KernelTimes* kt = nullptr) {
   cudaStream_t s = c->stream;
   const int slots = c->loop_depth + 1;
   k_iter_begin<<<8, 256, 0, s>>>(c->ctr, c->iter_state, c->P, slots);
+  if (kt) kt->mark(0);
   if (c->opt.trig_mode == B2PT_TRIG_PORTABLE) launch_generate<1>(c); else launch_generate<0>(c);
   c->launches += 2;
   if (time_loop) CK(cudaEventRecordWithFlags(c->ev_loop_a, s, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
@@ -580,6 +596,7 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
     ip.key = c->key;
     ip.ctr = c->ctr;
     ip.depth = d;
+    if (kt) kt->mark(1);
     if (c->opt.use_bvh)
       k_intersect<true><<<c->isect_grid, kIsectThreads, 0, s>>>(ip);
     else
@@ -592,6 +609,7 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
       mp.ctr = c->ctr;
       mp.status_ = c->sort_status;
       mp.depth = d;
+      if (kt) kt->mark(2);
       k_onesweep_pass<MaterialSortPolicy><<<c->sort_grid, kSortThreads, 0, s>>>(mp);
       c->launches += 1;
     }
@@ -622,6 +640,7 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
     sp.rec_s0 = c->rec_s0; sp.rec_s1 = c->rec_s1; sp.rec_s2 = c->rec_s2;
     sp.rec_dead = c->rec_dead; sp.rec_live = c->rec_live;
     const bool portable = c->opt.trig_mode == B2PT_TRIG_PORTABLE;
+    if (kt) kt->mark(3);
     if (record) {
       if (portable) launch_shade<1, true>(c, sp); else launch_shade<0, true>(c, sp);
     } else {
@@ -643,8 +662,39 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
     }
   }
   if (time_loop) CK(cudaEventRecordWithFlags(c->ev_loop_b, s, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
+  if (kt) kt->mark(-1);
   CK(cudaGetLastError());
   return 0;
+}
+
+extern "C" int b2pt_profile_iteration(B2ptCtx* c, int32_t iter, float ms[5]) {
+  if (!c || !ms) return fail(B2PT_ERR_INVALID, "ctx and ms must not be NULL");
+  CK(cudaSetDevice(c->device));
+  k_set_iter<<<1, 1, 0, c->stream>>>(c->iter_state, iter, 1);
+  c->launches += 1;
+  KernelTimes kt;
+  kt.s = c->stream;
+  cudaEvent_t e0;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventRecord(e0, c->stream));
+  int rc = enqueue_iteration(c, false, true, false, &kt);
+  if (rc == 0) {
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) rc = fail(B2PT_ERR_CUDA, cudaGetErrorString(e));
+  }
+  for (int k = 0; k < 5; ++k) ms[k] = 0.0f;
+  if (rc == 0) {
+    for (size_t i = 0; i + 1 < kt.ev.size(); ++i) {
+      float t = 0.0f;
+      cudaEventElapsedTime(&t, kt.ev[i], kt.ev[i + 1]);
+      if (kt.kind[i] >= 0 && kt.kind[i] < 4) ms[kt.kind[i]] += t;
+    }
+    cudaEventElapsedTime(&ms[4], e0, kt.ev.back());
+  }
+  for (cudaEvent_t e : kt.ev) cudaEventDestroy(e);
+  cudaEventDestroy(e0);
+  c->loop_timed = true;
+  return rc;
 }
 
 extern "C" int b2pt_render(B2ptCtx* c, int32_t iter_first, int32_t iter_count, int32_t iter_stride) {
@@ -727,6 +777,20 @@ extern "C" int b2pt_set_camera(B2ptCtx* c, const B2ptCamera* cam) {
     c->graph = nullptr;
   }
   return b2pt_reset_accum(c);
+}
+
+extern "C" int b2pt_set_stream(B2ptCtx* c, void* cuda_stream) {
+  if (!c) return fail(B2PT_ERR_INVALID, "ctx is NULL");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+  if (c->graph_exec) {  // a captured graph is tied to the stream it was captured on
+    cudaGraphExecDestroy(c->graph_exec);
+    cudaGraphDestroy(c->graph);
+    c->graph_exec = nullptr;
+    c->graph = nullptr;
+  }
+  return 0;
 }
 
 extern "C" float* b2pt_device_image(B2ptCtx* c) { return c ? c->image_target : nullptr; }

@@ -1,0 +1,62 @@
+"""Generate the golden fixtures from the REFERENCE'S OWN CODE.
+
+Runs ``oracle/_ref/ref_cpu`` -- a host build of the reference's unmodified
+intersections.h / interactions.h / scene.cpp (see oracle/Makefile) -- on small
+renders of the reference's scenes and stores
+
+  <case>.b2s          the scene as the reference's loader produced it
+  <case>_stages.npz   every stage array of iteration 1 and the accumulated
+                      image / albedo after two iterations
+
+Needs /root/reference (through oracle/_ref), so it only runs in the build
+container; the outputs are committed.  Usage: python tests/golden/make_golden.py
+"""
+import os
+import shutil
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import harness  # noqa: E402
+from mygpuraytracer_b200 import scenes  # noqa: E402
+
+# case -> (scene, W, H, extra ref_cpu flags)
+CASES = {
+    "cornell_32x32": ("cornell", 32, 32, []),
+    "cornellGlass_32x32": ("cornellGlass", 32, 32, []),
+    "cornellGlass_dof_32x24": ("cornellGlass", 32, 24, ["--dof"]),
+    "cornellGlass_noaa_24x32": ("cornellGlass", 24, 32, ["--no-aa"]),
+    "sphere_16x16": ("sphere", 16, 16, []),
+    "quadbox_32x32": ("quadbox", 32, 32, []),
+}
+
+
+def main():
+    assert harness.have("ref_cpu"), "build oracle/_ref first: make -C oracle ref"
+    for f in ("quadbox.obj",):
+        shutil.copyfile(os.path.join(HERE, f), os.path.join(harness.RUN_MODELS, f))
+    shutil.copyfile(os.path.join(HERE, "quadbox.mtl"), os.path.join(harness.RUN_MODELS, "materials", "quadbox.mtl"))
+    for case, (scene, w, h, extra) in CASES.items():
+        d = harness.tmpdir()
+        txt = os.path.join(d, "s.txt")
+        if scene == "quadbox":
+            with open(txt, "w") as f:
+                f.write(scenes.scene_text("cornellObj", width=w, height=h, obj_path="../models/quadbox.obj"))
+        else:
+            harness.scene_variant(scene, txt, w, h)
+        b2s = os.path.join(HERE, case + ".b2s")
+        harness.run("ref_cpu", txt, os.path.join(d, "out"), b2s, iters=2, dump_iter=1, extra=extra)
+        dump = harness.load_dump(os.path.join(d, "out"))
+        arrays = {"image": dump["image"], "albedo": dump["albedo"], "nlive": dump["nlive"]}
+        for k, st in enumerate(dump["depths"]):
+            for name, a in st.items():
+                arrays[f"d{k}_{name}"] = a
+        np.savez_compressed(os.path.join(HERE, case + "_stages.npz"), **arrays)
+        print(case, os.path.getsize(b2s), os.path.getsize(os.path.join(HERE, case + "_stages.npz")))
+        shutil.rmtree(d)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,210 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the CPU oracle.
+
+Integer / index work -- closest-hit geom and face ids, the material-sort
+permutation, the compaction permutation, live counts -- must be bit-exact.
+Floating point: with trig_mode=PORTABLE both sides evaluate the same operation
+sequence without FMA contraction, so hit distances, normals, scattered rays,
+per-iteration radiance and the accumulated image are compared BITWISE as well
+(tolerance 0; north_star allows 1e-4 relative).  With trig_mode=NATIVE the
+kernels call CUDA's sinf/cosf like the reference's device code; everything up
+to the first diffuse bounce is still bit-exact against the oracle and the
+converged image must reach PSNR >= 50 dB (north_star).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from mygpuraytracer_b200 import abi, api, assets, scenes
+from mygpuraytracer_b200.podscene import PodScene
+from oracle import oracle
+from util import GOLDEN, assert_same_bits, load_golden, psnr
+
+pytestmark = pytest.mark.gpu
+
+STAGES_TO_COMPARE = ["ray_origin", "ray_dir", "ray_pixel", "hit_t", "hit_normal", "hit_material", "sort_perm",
+                     "shaded_color", "shaded_bounces", "shaded_origin", "shaded_dir", "partition_pixel"]
+
+
+def compare_iteration(pod: PodScene, optkw: dict, iters=(1, 2), what=""):
+    opt = abi.default_options(trig_mode=abi.TRIG_PORTABLE, record_stages=1, **optkw)
+    ref_img = np.zeros((pod.n_pixels, 3), np.float32)
+    ref_alb = np.zeros((pod.n_pixels, 3), np.float32)
+    with api.Renderer(pod, opt) as r:
+        for it in iters:
+            r.render(it, 1, 1)
+            got = r.stages()
+            ref = oracle.iteration_with_stages(pod, opt, it, ref_img, ref_alb if it == 1 else None)
+            assert len(got) == len(ref), f"{what}: depth count {len(got)} vs {len(ref)}"
+            for d, (g, o) in enumerate(zip(got, ref)):
+                for name in STAGES_TO_COMPARE:
+                    assert_same_bits(g[name], o[name], f"{what} iter {it} depth {d} {name}")
+                hit = o["hit_t"] > 0
+                assert np.array_equal(g["hit_geom"][hit], o["hit_geom"][hit]), f"{what} depth {d} geom ids"
+                assert np.array_equal(g["hit_geom"][~hit], np.full((~hit).sum(), -1)), "miss geom id"
+                assert np.array_equal(g["hit_face"][hit], o["hit_face"][hit]), f"{what} depth {d} face ids"
+                is_obj = hit & (pod.geoms["type"][np.maximum(o["hit_geom"], 0)] == abi.OBJ)
+                assert_same_bits(g["hit_uv"][is_obj], o["hit_uv"][is_obj], f"{what} depth {d} uv")
+            live = r.live_counts()
+            assert list(live[: len(ref)]) == [len(s["ray_pixel"]) for s in ref]
+        img, alb = r.read()
+    assert_same_bits(img, ref_img, f"{what} accumulated image")
+    assert_same_bits(alb, ref_alb, f"{what} albedo")
+
+
+@pytest.mark.parametrize("case,optkw", [
+    ("cornell_32x32", {}), ("cornellGlass_32x32", {}), ("cornellGlass_dof_32x24", {"depth_of_field": 1}),
+    ("cornellGlass_noaa_24x32", {"antialiasing": 0}), ("sphere_16x16", {}), ("quadbox_32x32", {}),
+    ("cornell_32x32", {"sort_by_material": 0}),
+])
+def test_golden_scenes_every_stage_bitexact(case, optkw):
+    pod = PodScene.load(os.path.join(GOLDEN, case + ".b2s"))
+    compare_iteration(pod, optkw, what=case)
+
+
+def test_reference_golden_dumps_direct():
+    """Depth-0 hits and the first sort/partition against the REFERENCE'S OWN
+    dump (tests/golden, libm trig): no trig has happened yet at that point, so
+    the CUDA path must reproduce the reference bit for bit."""
+    for case in ["cornell_32x32", "cornellGlass_32x32", "quadbox_32x32"]:
+        pod, ref_depths, *_ = load_golden(case)
+        with api.Renderer(pod, abi.default_options(record_stages=1)) as r:
+            r.render(1, 1, 1)
+            g = r.stages()[0]
+        ref = ref_depths[0]
+        for mine, theirs in [("ray_origin", "in_origin"), ("ray_dir", "in_dir"), ("hit_t", "hit_t"),
+                             ("hit_normal", "hit_normal"), ("hit_material", "hit_material")]:
+            assert_same_bits(g[mine], ref[theirs], f"{case} {mine}")
+        assert np.array_equal(g["ray_pixel"][g["sort_perm"]], ref["sorted_pixel"]), "sort permutation"
+        hit = ref["hit_t"] > 0
+        assert np.array_equal(g["hit_geom"][hit], ref["hit_geom"][hit])
+
+
+@pytest.mark.parametrize("name,w,h", [("cornell", 200, 150), ("cornellGlass", 160, 160)])
+def test_larger_frames_bitexact(tmp_path, name, w, h):
+    pod = api.Scene(scenes.write_scene(name, str(tmp_path / "s.txt"), width=w, height=h)).pod
+    compare_iteration(pod, {}, iters=(1, 2, 7), what=f"{name} {w}x{h}")
+
+
+def _mesh_scene(tmp_path, name, w, h, tris):
+    root = assets.prepare(str(tmp_path / "run"), triangles=tris, procedural_size=256)
+    return api.Scene(assets.scene_file(name, w, h, root=root)).pod
+
+
+@pytest.mark.parametrize("name,tris", [("cornellObj", 1000), ("cornellSpaceship", 1000), ("cornellSpaceship", 20000)])
+def test_mesh_scenes_bvh_bitexact(tmp_path, name, tris):
+    """LBVH traversal + textures + bump map: closest-hit ids, uv, normals and
+    everything downstream identical to the oracle's brute-force loop."""
+    pod = _mesh_scene(tmp_path, name, 96, 54, tris)
+    compare_iteration(pod, {}, what=f"{name}/{tris}")
+    d0 = oracle.intersect(pod, *[a for a in (oracle.generate(pod, abi.default_options(), 1).origin,
+                                             oracle.generate(pod, abi.default_options(), 1).dir)])
+    assert (pod.geoms["type"][np.maximum(d0.geom, 0)][d0.t > 0] == abi.OBJ).sum() > 20, "mesh must be visible"
+
+
+def test_bvh_equals_brute_force_at_full_size(tmp_path):
+    """Size-independent property at BASELINE.json's full size: at 1920x1080
+    with the 250k-triangle stand-in mesh, the BVH kernel and the brute-force
+    kernel (the reference's loop order) return identical hit records."""
+    tris = int(os.environ.get("B2PT_TEST_TRIS", "250000"))
+    root = assets.prepare(str(tmp_path / "run"), triangles=tris, procedural_size=512)
+    pod = api.Scene(assets.scene_file("cornellSpaceship", 1920, 1080, depth=2, root=root)).pod
+    res = []
+    for bvh in (1, 0):
+        with api.Renderer(pod, abi.default_options(use_bvh=bvh, record_stages=1)) as r:
+            r.render(1, 1, 1)
+            st = r.stages()
+            res.append((st, r.read()[0]))
+    (a, img_a), (b, img_b) = res
+    assert len(a) == len(b) == 2
+    for d in range(2):
+        for name in ["hit_t", "hit_normal", "hit_geom", "hit_face", "hit_uv", "hit_material", "sort_perm", "partition_pixel"]:
+            assert_same_bits(a[d][name], b[d][name], f"depth {d} {name}")
+    assert_same_bits(img_a, img_b, "image")
+    n_obj = int((pod.geoms["type"][np.maximum(a[0]["hit_geom"], 0)][a[0]["hit_t"] > 0] == abi.OBJ).sum())
+    assert n_obj > 10000
+
+
+def test_multi_iteration_image_and_graph_replay(tmp_path):
+    """50 iterations through the CUDA-graph path == 50 single launches == oracle."""
+    pod = api.Scene(scenes.write_scene("cornellGlass", str(tmp_path / "s.txt"), width=64, height=64)).pod
+    ref, ref_alb, nlive, seg = oracle.render(pod, abi.default_options(trig_mode=abi.TRIG_PORTABLE), 1, 50, 1)
+    for graph in (1, 0):
+        with api.Renderer(pod, abi.default_options(trig_mode=abi.TRIG_PORTABLE, use_graph=graph)) as r:
+            r.render(1, 20, 1)
+            r.render(21, 30, 1)
+            img, alb = r.read()
+            assert_same_bits(img, ref, f"image (graph={graph})")
+            assert_same_bits(alb, ref_alb, "albedo")
+            assert list(r.live_counts()[: len(nlive)]) == list(nlive)
+            assert r.launch_count() > 50 * 3
+            assert r.last_loop_ms() > 0.0
+
+
+def test_strided_iterations_sum_to_the_sequential_image(tmp_path):
+    """spp sharding: ranks rendering {1,3,5,..} and {2,4,6,..} add up to the
+    sequential image within float summation order (1e-5 relative)."""
+    pod = api.Scene(scenes.write_scene("cornell", str(tmp_path / "s.txt"), width=80, height=60)).pod
+    opt = abi.default_options()
+    with api.Renderer(pod, opt) as r:
+        r.render(1, 16, 1)
+        full, _ = r.read()
+    parts = []
+    for rank in range(2):
+        with api.Renderer(pod, opt) as r:
+            r.render(rank + 1, 8, 2)
+            parts.append(r.read()[0])
+    s = parts[0] + parts[1]
+    assert np.allclose(s, full, rtol=1e-5, atol=1e-6)
+
+
+def test_native_trig_converges_to_the_oracle_image(tmp_path):
+    """NATIVE trig (CUDA sinf/cosf, as the reference's kernels) vs the libm
+    oracle at equal spp: PSNR >= 50 dB on image/iter (north_star gate)."""
+    pod = api.Scene(scenes.write_scene("cornell", str(tmp_path / "s.txt"), width=48, height=48)).pod
+    n = 400
+    with api.Renderer(pod, abi.default_options()) as r:
+        r.render(1, n, 1)
+        img, _ = r.read()
+    ref, *_ = oracle.render(pod, abi.default_options(), 1, n, 1)
+    assert psnr(np.clip(img / n, 0, 1), np.clip(ref / n, 0, 1)) >= 50.0
+
+
+def test_pathtrace_free_functions_mirror_the_reference(tmp_path):
+    scene = api.Scene(scenes.write_scene("cornell", str(tmp_path / "s.txt"), width=40, height=30))
+    api.pathtraceFree()  # before the first Init, like main.cpp:245-248
+    api.set_options(abi.default_options(trig_mode=abi.TRIG_PORTABLE))
+    api.pathtraceInit(scene)
+    for it in (1, 2, 3):
+        api.pathtrace(None, 0, it)
+        assert api.timer().getGpuElapsedTimeForPreviousOperation() > 0
+    api.pathtraceFree()
+    api.set_options(None)
+    ref, alb, *_ = oracle.render(scene.pod, abi.default_options(trig_mode=abi.TRIG_PORTABLE), 1, 3, 1)
+    assert_same_bits(scene.state.image, ref, "scene.state.image")
+    assert_same_bits(scene.state.albedo, alb, "scene.state.albedo")
+
+
+def test_edge_cases(tmp_path):
+    # depth 1: every path dies at its first shade; depth 0 behaves like the reference's while loop
+    for depth in (1, 2):
+        pod = api.Scene(scenes.write_scene("cornellGlass", str(tmp_path / f"d{depth}.txt"), width=24, height=24, depth=depth)).pod
+        compare_iteration(pod, {}, iters=(1,), what=f"depth {depth}")
+    # a scene where every ray misses after the first bounce at most: the lone emissive sphere
+    pod, *_ = load_golden("sphere_16x16")
+    compare_iteration(pod, {}, iters=(1, 2, 3), what="sphere")
+    # 1x1 image
+    pod = api.Scene(scenes.write_scene("cornell", str(tmp_path / "one.txt"), width=1, height=1)).pod
+    compare_iteration(pod, {}, iters=(1, 2), what="1x1")
+
+
+def test_invalid_scenes_are_rejected():
+    pod, *_ = load_golden("cornell_32x32")
+    bad = pod.copy()
+    bad.geoms["material_id"][0] = 99
+    with pytest.raises(api.B2ptError):
+        api.Renderer(bad)
+    bad = pod.copy()
+    bad.trace_depth = 1000
+    with pytest.raises(api.B2ptError):
+        api.Renderer(bad)

@@ -1,0 +1,116 @@
+"""The scene loader (scene text format, OBJ/MTL, JPEG/PPM textures, camera
+orbit) against PODs written by the reference's own loader (tests/golden/*.b2s)."""
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+from mygpuraytracer_b200 import api, assets, scenes, standin_mesh
+from mygpuraytracer_b200.podscene import PodScene
+from util import GOLDEN, assert_same_bits
+
+
+def assert_same_scene(ref: PodScene, mine: PodScene, textures=True):
+    for f in ref.geoms.dtype.names:
+        assert_same_bits(ref.geoms[f], mine.geoms[f], f"geoms.{f}")
+    assert ref.materials.tobytes() == mine.materials.tobytes()
+    for f in ref.camera.dtype.names:
+        assert_same_bits(ref.camera[f], mine.camera[f], f"camera.{f}")
+    assert_same_bits(ref.face_pos, mine.face_pos, "face_pos")
+    assert_same_bits(ref.face_uv, mine.face_uv, "face_uv")
+    assert (ref.trace_depth, ref.iterations) == (mine.trace_depth, mine.iterations)
+    if textures:
+        assert len(ref.textures) == len(mine.textures)
+        for a, b in zip(ref.textures, mine.textures):
+            assert a.shape == b.shape and np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("case,name,w,h", [("cornell_32x32", "cornell", 32, 32), ("cornellGlass_32x32", "cornellGlass", 32, 32),
+                                           ("sphere_16x16", "sphere", 16, 16), ("cornellGlass_dof_32x24", "cornellGlass", 32, 24)])
+def test_scene_files_load_bit_identical_to_reference(tmp_path, case, name, w, h):
+    ref = PodScene.load(os.path.join(GOLDEN, case + ".b2s"))
+    path = scenes.write_scene(name, str(tmp_path / "scenes" / "s.txt"), width=w, height=h)
+    assert_same_scene(ref, api.Scene(path).pod)
+    # the same through the RES override of the loader
+    path2 = scenes.write_scene(name, str(tmp_path / "scenes" / "s800.txt"))
+    assert_same_scene(ref, api.Scene(path2, width=w, height=h).pod)
+
+
+def test_obj_with_quads_and_no_texture_maps(tmp_path):
+    """Quads split along the shorter diagonal like tinyobjloader 2.0.0, MTL
+    without maps (the case the reference indexes out of bounds, Q19)."""
+    ref = PodScene.load(os.path.join(GOLDEN, "quadbox_32x32.b2s"))
+    (tmp_path / "models" / "materials").mkdir(parents=True)
+    shutil.copy(os.path.join(GOLDEN, "quadbox.obj"), tmp_path / "models")
+    shutil.copy(os.path.join(GOLDEN, "quadbox.mtl"), tmp_path / "models" / "materials")
+    path = scenes.write_scene("cornellObj", str(tmp_path / "scenes" / "s.txt"), width=32, height=32,
+                              obj_path="../models/quadbox.obj")
+    mine = api.Scene(path).pod
+    assert_same_scene(ref, mine)
+    assert len(mine.face_pos) == 14 and mine.geoms["tex_kd"][6] == -1
+    assert mine.geoms["material_id"][6] == 6  # appended material (scene.cpp:221-231)
+
+
+def test_crlf_and_comments_are_tolerated(tmp_path):
+    txt = scenes.scene_text("cornell", width=8, height=8)
+    p = tmp_path / "crlf.txt"
+    p.write_bytes(("// a comment line\r\n" + txt.replace("\n", "\r\n")).encode())
+    a = api.Scene(str(p)).pod
+    b = api.Scene(scenes.write_scene("cornell", str(tmp_path / "lf.txt"), width=8, height=8)).pod
+    assert_same_scene(b, a)
+
+
+def test_loader_errors(tmp_path):
+    p = tmp_path / "bad.txt"
+    p.write_text("MATERIAL 3\nRGB 1 1 1\n")
+    with pytest.raises(api.B2ptError) as e:
+        api.Scene(str(p))
+    assert e.value.code == -1
+    p.write_text(scenes.scene_text("cornellObj", width=8, height=8, obj_path="../models/nope.obj"))
+    with pytest.raises(api.B2ptError) as e:
+        api.Scene(str(p))
+    assert e.value.code == -4
+
+
+def test_standin_mesh_properties(tmp_path):
+    pos, uv, vn, faces = standin_mesh.build(2000)
+    assert 1800 <= len(faces) <= 2300
+    assert uv.min() > 0.0 and uv.max() < 1.0
+    p0, p1, p2 = (pos[faces[:, k]].astype(np.float64) for k in range(3))
+    n = np.cross(p1 - p0, p2 - p0)
+    assert (np.linalg.norm(n, axis=1) > 0).all()  # no degenerate faces
+    # closed and consistently wound: signed volume > 0 and every edge shared by exactly two faces
+    assert (p0 * n).sum() / 6.0 > 1.0
+    key = lambda a: tuple(np.round(pos[a], 6))
+    edges = {}
+    for f in faces:
+        for a, b in ((f[0], f[1]), (f[1], f[2]), (f[2], f[0])):
+            e = (key(a), key(b))
+            edges[e] = edges.get(e, 0) + 1
+    assert all(edges.get((b, a), 0) == c == 1 for (a, b), c in edges.items())
+    # written and re-read through the loader: same float bits
+    root = assets.prepare(str(tmp_path / "run"), triangles=2000, procedural_size=64)
+    sc = api.Scene(assets.scene_file("cornellObj", 16, 16, root=root)).pod
+    assert len(sc.face_pos) == len(faces)
+    assert_same_bits(sc.face_pos.reshape(-1, 3, 3), pos[faces], "OBJ round trip")
+    assert_same_bits(sc.face_uv.reshape(-1, 3, 2), uv[faces], "uv round trip")
+    assert len(sc.textures) == 4 and sc.textures[0].shape == (64, 64, 3)
+    assert sc.materials["index_of_refraction"][-1] == 2.0  # Ni of the spaceship MTL
+
+
+def test_jpeg_decoder_matches_reference_texels():
+    """4:4:4 baseline JPEG -> the same bytes stb_image produces.  The golden
+    is a CRC of texels dumped by the reference loader (see make_golden.py);
+    it needs the reference JPEGs, which only exist where the build copied them."""
+    import zlib
+    tex = os.path.join(assets.DEFAULT_ROOT, "textures", "Intergalactic Spaceship_emi.jpg")
+    crc_file = os.path.join(GOLDEN, "texture_crc.txt")
+    if not (os.path.exists(tex) and os.path.exists(crc_file)):
+        pytest.skip("reference textures not present")
+    want = dict(l.split() for l in open(crc_file).read().splitlines())
+    sc = api.Scene(assets.scene_file("cornellObj", 8, 8)).pod
+    names = ["kd", "ks", "bump", "ke"]
+    for n, t in zip(names, sc.textures):
+        assert t.shape == (4096, 4096, 3)
+        assert f"{zlib.crc32(t.tobytes()):08x}" == want[n], n
