@@ -105,6 +105,11 @@ def test_default_build_of_the_reference_statistical(tmp_path):
     rel = np.abs(g["hit_t"][hit][same_geom] - o["hit_t"][hit][same_geom]) / o["hit_t"][hit][same_geom]
     assert rel.max() < 1e-4
     assert np.array_equal(g["ray_pixel"][g["sort_perm"]], o["sorted_pixel"]) or (~same_geom).sum() > 0
-    assert psnr(np.clip(img / n, 0, 1), np.clip(ref["image"] / n, 0, 1)) >= 50.0 or True  # equal spp, different rounding
-    # per-iteration radiance of iteration 1..n, summed: within 1e-4 relative on the image total
-    assert abs(float(img.sum()) - float(ref["image"].sum())) / float(ref["image"].sum()) < 2e-2
+    # Same seeds, same slots: almost every path stays within rounding of the
+    # reference's, only paths where a discrete decision flipped diverge.
+    close = np.isclose(img, ref["image"], rtol=1e-4, atol=1e-5).all(axis=1).mean()
+    p = psnr(np.clip(img / n, 0, 1), np.clip(ref["image"] / n, 0, 1))
+    print(f"default-build reference: {100 * close:.3f}% of pixels within 1e-4 after {n} spp, PSNR {p:.1f} dB, "
+          f"{int((~same_geom).sum())} depth-0 id flips")
+    assert close > 0.97
+    assert p >= 50.0
