@@ -77,6 +77,7 @@ def workload_config(args, n_tris: int, textures: str):
         "scene": SCENE, "width": args.width, "height": args.height, "depth": args.depth,
         "triangles": n_tris, "textures": textures,
         "step": "one iteration (1 spp) per rank", "sharding": "samples-per-pixel, one NCCL reduce per frame",
+        "streams_per_gpu": args.streams,
         "l2": "working set per step (path state 2x48 B + hits 32 B per path, 4 textures, BVH) > 126 MB L2; no flush",
         "rng": "slot-keyed minstd (reference mode)", "trig": "native",
     }
@@ -251,44 +252,70 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     n_tris = len(pod.face_pos)
     P = pod.n_pixels
     opt = abi.default_options(device=local_rank)
-    r = api.Renderer(scene, opt)
+    # KC contexts per GPU, each on its own stream with its own accumulator, render
+    # interleaved iteration indices (the same samples-per-pixel sharding used
+    # across GPUs).  One iteration is 26 short dependent kernels that cannot fill
+    # 148 SMs on their own (a depth-7 launch has 250 k rays); independent
+    # iterations in flight overlap each other's tails.
+    KC = max(1, args.streams)
+    rs = [api.Renderer(scene, opt) for _ in range(KC)]
+    r = rs[0]
     mesh_geom = int(np.nonzero(pod.geoms["type"] == abi.OBJ)[0][0])
     bvh = r.bvh_info(mesh_geom)
 
-    # everything on one torch stream: kernels, the NCCL reduce and the timing events
-    stream = torch.cuda.Stream()
-    acc = torch.zeros(P * 3, dtype=torch.float32, device="cuda")
-    r.set_stream_ptr(stream.cuda_stream)
-    r.set_device_image_ptr(acc.data_ptr())
+    streams = [torch.cuda.Stream() for _ in range(KC)]
+    accs = [torch.zeros(P * 3, dtype=torch.float32, device="cuda") for _ in range(KC)]
+    for rk, st, ac in zip(rs, streams, accs):
+        rk.set_stream_ptr(st.cuda_stream)
+        rk.set_device_image_ptr(ac.data_ptr())
+    stream, acc = streams[0], accs[0]
 
-    K, W = args.steps, args.warmup
-    first = rank + 1
+    W = args.warmup
+    K = args.steps                          # iterations per rank, split over the KC contexts
+    lanes = world * KC                      # independent iteration streams in the whole job
+
+    def first_of(c):
+        return rank * KC + c + 1
 
     def barrier():
         if dist:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def run(iter_base, total):
+        """Queue `total` iterations over the contexts (exactly), fork/join around stream 0."""
+        for c in range(1, KC):
+            streams[c].wait_stream(stream)
+        for c in range(KC):
+            count = total // KC + (1 if c < total % KC else 0)
+            with torch.cuda.stream(streams[c]):
+                rs[c].render(first_of(c) + iter_base * lanes, count, lanes)
+        for c in range(1, KC):
+            stream.wait_stream(streams[c])
+
     # ---- device-resident throughput --------------------------------------------------------
     with torch.cuda.stream(stream):
-        r.render(first, W, world)
+        run(0, max(W, KC))
         barrier()
-        acc.zero_()
+        for ac in accs:
+            ac.zero_()
         barrier()
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
-        launches0 = r.launch_count()
+        launches0 = sum(x.launch_count() for x in rs)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
-        r.render(first + W * world, K, world)
+        run(max(W, KC), K)
+        for c in range(1, KC):
+            acc.add_(accs[c])
         if dist:
             dist.reduce(acc, dst=0)
         e1.record(stream)
         barrier()
         ms = e0.elapsed_time(e1)
         clocks = sampler.stop() if rank == 0 else None
-        launches = r.launch_count() - launches0
+        launches = sum(x.launch_count() for x in rs) - launches0
         live = r.live_counts()
     t = torch.tensor([ms], device="cuda")
     if dist:
@@ -296,10 +323,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     ms_max = float(t.item())
     value = world * K * P / (ms_max * 1e-3) / 1e6
     segments = int(live[: args.depth].sum())
+    first = first_of(0)
 
     # ---- per-kernel times of one iteration (CUDA events around every launch) ------------------
     with torch.cuda.stream(stream):
-        prof = [r.profile_iteration(first + (W + K + i) * world) for i in range(3)]
+        prof = [r.profile_iteration(first + (2 * W + K + KC + i) * lanes) for i in range(3)]
         barrier()
     prof = {k: statistics.median(p[k] for p in prof) for k in prof[0]}
 
@@ -310,11 +338,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     with torch.cuda.stream(stream):
         r.reset()
         for i in range(min(W, 3)):
-            r.pathtrace(first + i * world, img_np, alb_np)
+            r.pathtrace(first + i * lanes, img_np, alb_np)
         barrier()
         e0.record(stream)
         for i in range(K):
-            r.pathtrace(first + (W + i) * world, img_np, alb_np)
+            r.pathtrace(first + (W + i) * lanes, img_np, alb_np)
         if dist:
             dist.reduce(acc, dst=0)
         e1.record(stream)
@@ -339,7 +367,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": 2 * P * 12,
                     "call": "b2pt_pathtrace(ctx, iter, host_image, host_albedo) -- pathtrace() of apps/src/pathtrace.h:9",
                     "ms_per_step": float(t.item()) / K},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "streams_per_gpu": KC,
             "clocks": clocks,
             "roofline": {"kernel": "k_intersect<BVH>", "bound": "hbm", "achieved": isect_gbs, "peak": peak, "unit": "GB/s",
                          "frac": isect_gbs / peak, "traffic": None, "peak_source": peak_src,
@@ -360,7 +388,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             if rg is not None:
                 line["reference_gpu"] = rg
         print(json.dumps(line), flush=True)
-    r.close()
+    for x in rs:
+        x.close()
     if dist:
         dist.barrier()
         dist.destroy_process_group()
@@ -376,6 +405,7 @@ def main():
     ap.add_argument("--height", type=int, default=HEIGHT)
     ap.add_argument("--depth", type=int, default=DEPTH)
     ap.add_argument("--triangles", type=int, default=250_000)
+    ap.add_argument("--streams", type=int, default=3, help="concurrent iteration streams (contexts) per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / reference_gpu legs")
     ap.add_argument("--ref-gpu-iters", type=int, default=1)
     ap.add_argument("--ref-gpu-timeout", type=int, default=240)

@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cfloat>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -92,6 +93,7 @@ struct MeshBuild {
   float4* tris = nullptr;
   float* face_pos = nullptr;
   float* face_uv = nullptr;
+  size_t bvh_bytes = 0;
   B2ptBvhInfo info{};
 };
 
@@ -134,7 +136,11 @@ struct B2ptCtx {
   int *rec_live = nullptr, *rec_dead = nullptr;
   std::vector<StageRecord> records;
 
-  int isect_grid = 0, sort_grid = 0, shade_grid = 0, gen_grid = 0;
+  unsigned long long* trav_stats = nullptr;  // [depth][24], B2PT_TRAVERSAL_STATS=1 only
+  void* l2_window_ptr = nullptr;
+  size_t l2_window_bytes = 0;
+  int isect_grid = 0, analytic_grid = 0, sort_grid = 0, shade_grid = 0, gen_grid = 0;
+  int* mesh_queue = nullptr;
   cudaEvent_t ev_loop_a = nullptr, ev_loop_b = nullptr;
   bool loop_timed = false;
   cudaGraph_t graph = nullptr;
@@ -152,6 +158,22 @@ struct B2ptCtx {
     return 0;
   }
 };
+
+// Keep the largest mesh's BVH (nodes + triangles) resident in L2: the walk is a
+// chain of dependent loads, so its speed is set by the latency of each step
+// (L2 hit ~250 cycles, HBM ~600+), and the streaming path-state / texture
+// traffic of the other kernels would otherwise keep evicting it.
+static void apply_l2_policy(B2ptCtx* c, cudaStream_t s) {
+  if (!c->l2_window_ptr || !c->l2_window_bytes) return;
+  cudaStreamAttrValue v;
+  memset(&v, 0, sizeof v);
+  v.accessPolicyWindow.base_ptr = c->l2_window_ptr;
+  v.accessPolicyWindow.num_bytes = c->l2_window_bytes;
+  v.accessPolicyWindow.hitRatio = 1.0f;
+  v.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+  v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  if (cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
+}
 
 static Mat34 rows_of(const float* m) {
   Mat34 r;
@@ -171,6 +193,27 @@ static int is_rigid(const float* m) {
       if (std::fabs(d - (a == b ? 1.0 : 0.0)) > 1e-5) return 0;
     }
   return 1;
+}
+
+// Padded world-space box of a geom whose object-space bounds are [lo, hi], and
+// the distance slack of its exact test (see may_beat in k_intersect.cuh).
+static void world_box(const float* m, const float lo[3], const float hi[3], DevGeom* D) {
+  float wl[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, wh[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (int c = 0; c < 8; ++c) {
+    const float p[3] = {(c & 1) ? hi[0] : lo[0], (c & 2) ? hi[1] : lo[1], (c & 4) ? hi[2] : lo[2]};
+    for (int r = 0; r < 3; ++r) {
+      const float w = m[r] * p[0] + m[4 + r] * p[1] + m[8 + r] * p[2] + m[12 + r];
+      wl[r] = std::min(wl[r], w);
+      wh[r] = std::max(wh[r], w);
+    }
+  }
+  float ext = 0.0f, scale = 0.0f;
+  for (int r = 0; r < 3; ++r) ext = std::max(ext, std::max(std::fabs(wl[r]), std::fabs(wh[r])));
+  for (int c = 0; c < 3; ++c)
+    scale = std::max(scale, std::sqrt(m[c * 4] * m[c * 4] + m[c * 4 + 1] * m[c * 4 + 1] + m[c * 4 + 2] * m[c * 4 + 2]));
+  const float pad = 1e-3f + 1e-4f * ext;
+  D->wmin = make_float4(wl[0] - pad, wl[1] - pad, wl[2] - pad, 2e-3f + 1.5e-4f * scale);
+  D->wmax = make_float4(wh[0] + pad, wh[1] + pad, wh[2] + pad, 0.0f);
 }
 
 static DevCamera to_dev_camera(const B2ptCamera& c) {
@@ -251,8 +294,12 @@ static int build_mesh(B2ptCtx* c, const float* pos_host, const float* uv_host, i
   if ((rc = c->dalloc(&out->face_uv, (size_t)n * 6))) return rc;
   CK(cudaMemcpyAsync(out->face_pos, pos_host, (size_t)n * 36, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(out->face_uv, uv_host, (size_t)n * 24, cudaMemcpyHostToDevice, s));
-  if ((rc = c->dalloc(&out->tris, (size_t)n * 3))) return rc;
-  if ((rc = c->dalloc(&out->nodes, (size_t)std::max(n - 1, 1) * 4))) return rc;
+  // nodes and triangles share one allocation so that a single L2 access-policy
+  // window can keep the whole acceleration structure resident
+  const size_t node_f4 = (size_t)std::max(n - 1, 1) * 8, tri_f4 = (size_t)n * 3;
+  if ((rc = c->dalloc(&out->nodes, node_f4 + tri_f4))) return rc;
+  out->tris = out->nodes + node_f4;
+  out->bvh_bytes = (node_f4 + tri_f4) * sizeof(float4);
   out->info.n_faces = n;
   out->info.n_nodes = std::max(n - 1, 0);
 
@@ -299,8 +346,9 @@ static int build_mesh(B2ptCtx* c, const float* pos_host, const float* uv_host, i
     k_karras<<<iblocks, 256, 0, s>>>(code, n, children, parent);
     k_refit<<<blocks, 256, 0, s>>>(n, children, parent, leaf_box, node_box, visit, bounds);
     k_tree_depth<<<blocks, 256, 0, s>>>(n, parent, bounds);
-    k_emit_nodes<<<iblocks, 256, 0, s>>>(n, children, leaf_box, node_box, out->nodes);
-    c->launches += 4;
+    k_node_depth<<<iblocks, 256, 0, s>>>(n, parent, visit);  // visit[] is free again: reuse it for the depths
+    k_emit_wide4<<<iblocks, 256, 0, s>>>(n, children, visit, leaf_box, node_box, out->nodes);
+    c->launches += 5;
   }
   CK(cudaEventRecord(e1, s));
   CK(cudaGetLastError());
@@ -402,6 +450,10 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
     D.material = G.material_id;
     D.mesh = -1;
     D.rigid = is_rigid(G.transform);
+    {
+      const float lo[3] = {-0.5f, -0.5f, -0.5f}, hi[3] = {0.5f, 0.5f, 0.5f};  // unit cube / r=0.5 sphere
+      world_box(G.transform, lo, hi, &D);
+    }
     if (G.material_id < 0 || G.material_id >= sc->n_materials)
       return fail(B2PT_ERR_INVALID, "geom material id out of range");
     if (G.type == B2PT_OBJ && G.face_count > 0) {
@@ -411,6 +463,16 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
       if ((rc = build_mesh(c, sc->face_pos + (size_t)G.face_begin * 9, sc->face_uv + (size_t)G.face_begin * 6,
                            G.face_count, &mb)))
         return rc;
+      {
+        float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        const float* fp = sc->face_pos + (size_t)G.face_begin * 9;
+        for (size_t v = 0; v < (size_t)G.face_count * 3; ++v)
+          for (int k = 0; k < 3; ++k) {
+            lo[k] = std::min(lo[k], fp[v * 3 + k]);
+            hi[k] = std::max(hi[k], fp[v * 3 + k]);
+          }
+        world_box(G.transform, lo, hi, &D);
+      }
       DevMesh M{};
       M.nodes = mb.nodes;
       M.tris = mb.tris;
@@ -426,6 +488,22 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
       c->geom_mesh[g] = D.mesh;
       hm.push_back(M);
       c->meshes.push_back(mb);
+    }
+  }
+  if (!c->meshes.empty() && !getenv("B2PT_NO_L2_PERSIST")) {
+    size_t best = 0;
+    for (size_t k = 1; k < c->meshes.size(); ++k)
+      if (c->meshes[k].bvh_bytes > c->meshes[best].bvh_bytes) best = k;
+    const size_t want = c->meshes[best].bvh_bytes;
+    const size_t cap = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, (size_t)prop.accessPolicyMaxWindowSize);
+    if (cap > 0) {
+      c->l2_window_ptr = c->meshes[best].nodes;
+      c->l2_window_bytes = std::min(want, cap);
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, c->l2_window_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        c->l2_window_ptr = nullptr;
+      }
+      apply_l2_policy(c, c->stream);
     }
   }
   DevGeom* dg = nullptr;
@@ -456,6 +534,7 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
   if ((rc = c->dalloc(&c->hits.h1, P))) return rc;
   if ((rc = c->dalloc(&c->key, P))) return rc;
   if ((rc = c->dalloc(&c->perm, P))) return rc;
+  if ((rc = c->dalloc(&c->mesh_queue, P))) return rc;
   if ((rc = c->dalloc(&c->ctr, 1))) return rc;
   if ((rc = c->dalloc(&c->iter_state, 4))) return rc;
   c->sort_grid = (int)((P + kSortTile - 1) / kSortTile);
@@ -480,13 +559,19 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
     if ((rc = c->dalloc(&c->rec_dead, P))) return rc;
   }
 
+  if (getenv("B2PT_TRAVERSAL_STATS")) {
+    if ((rc = c->dalloc(&c->trav_stats, (size_t)24 * (kMaxDepth + 1)))) return rc;
+    CK(cudaMemsetAsync(c->trav_stats, 0, sizeof(unsigned long long) * 24 * (kMaxDepth + 1), c->stream));
+  }
   // persistent grid of the intersect kernel: SMs x resident CTAs
   int occ = 0;
   if (opt.use_bvh)
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_intersect<true>, kIsectThreads, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_intersect_mesh<true>, kIsectThreads, 0));
   else
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_intersect<false>, kIsectThreads, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_intersect_mesh<false>, kIsectThreads, 0));
   c->isect_grid = c->sm_count * std::max(occ, 1);
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_intersect_analytic, 256, 0));
+  c->analytic_grid = (int)std::min<size_t>((P + 255) / 256, (size_t)c->sm_count * std::max(occ, 1) * 2);
 
   c->gen.cam = to_dev_camera(sc->camera);
   c->gen.trace_depth = sc->trace_depth;
@@ -502,6 +587,18 @@ extern "C" void b2pt_destroy(B2ptCtx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
+  if (c->trav_stats) {
+    std::vector<unsigned long long> h((size_t)24 * (kMaxDepth + 1));
+    cudaMemcpy(h.data(), c->trav_stats, h.size() * 8, cudaMemcpyDeviceToHost);
+    for (int d = 0; d < c->loop_depth; ++d) {
+      const unsigned long long* s = &h[(size_t)24 * d];
+      if (!s[0]) continue;
+      fprintf(stderr, "[b2pt traversal] depth %d: %llu walks, nodes/walk %.1f (max %llu), tris/walk %.1f (max %llu), log2 hist:",
+              d, s[0], (double)s[1] / s[0], s[3], (double)s[2] / s[0], s[4]);
+      for (int k = 0; k < 16; ++k) fprintf(stderr, " %llu", s[5 + k]);
+      fprintf(stderr, "\n");
+    }
+  }
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
   if (c->graph) cudaGraphDestroy(c->graph);
   for (void* p : c->allocs) cudaFree(p);
@@ -596,12 +693,18 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
     ip.key = c->key;
     ip.ctr = c->ctr;
     ip.depth = d;
+    ip.stats = c->trav_stats ? c->trav_stats + 24 * d : nullptr;
     if (kt) kt->mark(1);
-    if (c->opt.use_bvh)
-      k_intersect<true><<<c->isect_grid, kIsectThreads, 0, s>>>(ip);
-    else
-      k_intersect<false><<<c->isect_grid, kIsectThreads, 0, s>>>(ip);
+    ip.queue = c->mesh_queue;
+    k_intersect_analytic<<<c->analytic_grid, 256, 0, s>>>(ip);
     c->launches += 1;
+    if (c->dscene.n_meshes > 0) {
+      if (c->opt.use_bvh)
+        k_intersect_mesh<true><<<c->isect_grid, kIsectThreads, 0, s>>>(ip);
+      else
+        k_intersect_mesh<false><<<c->isect_grid, kIsectThreads, 0, s>>>(ip);
+      c->launches += 1;
+    }
     if (c->opt.sort_by_material) {
       MaterialSortPolicy mp;
       mp.key = c->key;
@@ -784,6 +887,7 @@ extern "C" int b2pt_set_stream(B2ptCtx* c, void* cuda_stream) {
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->stream));
   c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+  apply_l2_policy(c, c->stream);
   if (c->graph_exec) {  // a captured graph is tied to the stream it was captured on
     cudaGraphExecDestroy(c->graph_exec);
     cudaGraphDestroy(c->graph);

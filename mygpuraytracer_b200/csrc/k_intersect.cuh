@@ -22,6 +22,7 @@
 
 #include <float.h>
 
+#include "k_lbvh.cuh"
 #include "pt_device.cuh"
 
 namespace b2pt {
@@ -37,6 +38,8 @@ struct IsectParams {
   uint8_t* key;
   Counters* ctr;
   int depth;
+  int* queue;                 // rays that must walk a mesh (filled by k_intersect_analytic)
+  unsigned long long* stats;  // optional traversal statistics (B2PT_TRAVERSAL_STATS=1), else NULL
 };
 
 struct StackRef {
@@ -88,11 +91,12 @@ __device__ __forceinline__ float tri_exact(V3 qo, V3 qd, V3 v0, V3 v1, V3 v2, fl
   return length(qo - pt);
 }
 
-// Walk the LBVH of one mesh.  t_limit bounds the search (FLT_MAX, or the
-// closest analytic hit so far when the geom is rigid).  Returns the object
-// space distance of the closest triangle, or -1.
+// Walk the 4-wide LBVH of one mesh (k_emit_wide4).  t_limit bounds the search
+// (FLT_MAX, or the closest analytic hit so far when the geom is rigid).
+// Returns the object-space distance of the closest triangle, or -1.
 __device__ __forceinline__ float mesh_traverse(const DevMesh& m, V3 qo, V3 qd, float t_limit, int* face, float* bu,
-                                               float* bv, StackRef st) {
+                                               float* bv, StackRef st, unsigned long long* stats = nullptr) {
+  unsigned int n_nodes = 0, n_tris = 0;
   const V3 id = mk(1.0f / qd.x, 1.0f / qd.y, 1.0f / qd.z);
   float tbest = t_limit;
   float lim = t_limit >= FLT_MAX ? FLT_MAX : t_limit * 1.00001f + 1e-6f;
@@ -101,27 +105,45 @@ __device__ __forceinline__ float mesh_traverse(const DevMesh& m, V3 qo, V3 qd, f
   st.sp = 0;
   while (true) {
     if (node >= 0) {
-      const float4* n = m.nodes + 4 * (size_t)node;
-      const float4 n0 = __ldg(n), n1 = __ldg(n + 1), n2 = __ldg(n + 2), n3 = __ldg(n + 3);
-      float tnl, tfl, tnr, tfr;
-      slab(n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, qo, id, &tnl, &tfl);
-      slab(n1.z, n1.w, n2.x, n2.y, n2.z, n2.w, qo, id, &tnr, &tfr);
-      const bool hl = tnl <= tfl && tfl >= 0.0f && tnl <= lim;
-      const bool hr = tnr <= tfr && tfr >= 0.0f && tnr <= lim;
-      const int cl = __float_as_int(n3.x), cr = __float_as_int(n3.y);
-      if (hl && hr) {
-        const bool left_first = tnl <= tnr;
-        st.push(left_first ? cr : cl);
-        node = left_first ? cl : cr;
-        continue;
-      } else if (hl) {
-        node = cl;
-        continue;
-      } else if (hr) {
-        node = cr;
+      ++n_nodes;
+      const float4* n = m.nodes + 8 * (size_t)node;
+      const float4 lx = __ldg(n), ly = __ldg(n + 1), lz = __ldg(n + 2);
+      const float4 hx = __ldg(n + 3), hy = __ldg(n + 4), hz = __ldg(n + 5);
+      const float4 cf = __ldg(n + 6);
+      float tn[4];
+      int ch[4] = {__float_as_int(cf.x), __float_as_int(cf.y), __float_as_int(cf.z), __float_as_int(cf.w)};
+      {
+        float tf;
+        slab(lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, qo, id, &tn[0], &tf);
+        if (!(tn[0] <= tf && tf >= 0.0f && tn[0] <= lim)) ch[0] = kEmptyChild;
+        slab(lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, qo, id, &tn[1], &tf);
+        if (!(tn[1] <= tf && tf >= 0.0f && tn[1] <= lim)) ch[1] = kEmptyChild;
+        slab(lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, qo, id, &tn[2], &tf);
+        if (!(tn[2] <= tf && tf >= 0.0f && tn[2] <= lim)) ch[2] = kEmptyChild;
+        slab(lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, qo, id, &tn[3], &tf);
+        if (!(tn[3] <= tf && tf >= 0.0f && tn[3] <= lim)) ch[3] = kEmptyChild;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (ch[k] == kEmptyChild) tn[k] = FLT_MAX;
+      // sort the (up to four) hits by entry distance: 5-comparator network
+#define B2PT_CSWAP(a, b)                                   \
+  if (tn[b] < tn[a]) {                                     \
+    const float tt = tn[a]; tn[a] = tn[b]; tn[b] = tt;     \
+    const int cc = ch[a]; ch[a] = ch[b]; ch[b] = cc;       \
+  }
+      B2PT_CSWAP(0, 1) B2PT_CSWAP(2, 3) B2PT_CSWAP(0, 2) B2PT_CSWAP(1, 3) B2PT_CSWAP(1, 2)
+#undef B2PT_CSWAP
+      if (ch[0] != kEmptyChild) {
+        // nearest first; the others go on the stack farthest first
+        if (ch[3] != kEmptyChild) st.push(ch[3]);
+        if (ch[2] != kEmptyChild) st.push(ch[2]);
+        if (ch[1] != kEmptyChild) st.push(ch[1]);
+        node = ch[0];
         continue;
       }
     } else {
+      ++n_tris;
       const int slot = ~node;
       const float4* tp = m.tris + 3 * (size_t)slot;
       const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
@@ -140,6 +162,14 @@ __device__ __forceinline__ float mesh_traverse(const DevMesh& m, V3 qo, V3 qd, f
     }
     if (st.sp == 0) break;
     node = st.pop();
+  }
+  if (stats) {
+    atomicAdd(&stats[0], 1ull);
+    atomicAdd(&stats[1], (unsigned long long)n_nodes);
+    atomicAdd(&stats[2], (unsigned long long)n_tris);
+    atomicMax(&stats[3], (unsigned long long)n_nodes);
+    atomicMax(&stats[4], (unsigned long long)n_tris);
+    atomicAdd(&stats[5 + min(15u, 31u - __clz(n_nodes | 1u))], 1ull);  // log2 histogram of node visits
   }
   *face = best;
   return best >= 0 ? tbest : -1.0f;
@@ -181,17 +211,238 @@ __device__ __forceinline__ V3 fetch_texel(const DevTexture& tx, float u, float v
   return mk((float)r / 255.f, (float)g / 255.f, (float)b / 255.f);
 }
 
-template <bool USE_BVH>
-__global__ void __launch_bounds__(kIsectThreads, 2) k_intersect(IsectParams p) {
-  __shared__ DevGeom sgeom[kMaxGeoms];
-  __shared__ unsigned int shist[kMaxMaterials];
-  __shared__ int sstack[USE_BVH ? kShortStack * kIsectThreads : 1];
+// boxIntersectionTest, apps/src/intersections.h:48-90.  Returns the world-space
+// distance (or -1) and the object-space axis normal of the face that was hit.
+__device__ __forceinline__ float box_exact(const DevGeom& G, V3 o, V3 d, V3* axis_normal) {
+  const V3 qo = xform(G.inv, o, 1.0f);
+  const V3 qd = normalize(xform(G.inv, d, 0.0f));
+  float tmin = -1e38f, tmax = 1e38f;
+  V3 nmin = mk(0, 0, 0), nmax = mk(0, 0, 0);
+  {
+    const float t1 = (-0.5f - qo.x) / qd.x, t2 = (+0.5f - qo.x) / qd.x;
+    const float ta = glm_min(t1, t2), tb = glm_max(t1, t2);
+    const V3 nn = mk(t2 < t1 ? +1.0f : -1.0f, 0, 0);
+    if (ta > 0 && ta > tmin) { tmin = ta; nmin = nn; }
+    if (tb < tmax) { tmax = tb; nmax = nn; }
+  }
+  {
+    const float t1 = (-0.5f - qo.y) / qd.y, t2 = (+0.5f - qo.y) / qd.y;
+    const float ta = glm_min(t1, t2), tb = glm_max(t1, t2);
+    const V3 nn = mk(0, t2 < t1 ? +1.0f : -1.0f, 0);
+    if (ta > 0 && ta > tmin) { tmin = ta; nmin = nn; }
+    if (tb < tmax) { tmax = tb; nmax = nn; }
+  }
+  {
+    const float t1 = (-0.5f - qo.z) / qd.z, t2 = (+0.5f - qo.z) / qd.z;
+    const float ta = glm_min(t1, t2), tb = glm_max(t1, t2);
+    const V3 nn = mk(0, 0, t2 < t1 ? +1.0f : -1.0f);
+    if (ta > 0 && ta > tmin) { tmin = ta; nmin = nn; }
+    if (tb < tmax) { tmax = tb; nmax = nn; }
+  }
+  if (tmax >= tmin && tmax > 0) {
+    if (tmin <= 0) { tmin = tmax; nmin = nmax; }
+    // getPointOnRay (:27-29) normalises the direction again
+    const V3 ip = xform(G.fwd, qo + normalize(qd) * (tmin - .0001f), 1.0f);
+    *axis_normal = nmin;
+    return length(o - ip);
+  }
+  return -1.0f;
+}
 
+// sphereIntersectionTest, apps/src/intersections.h:102-144.  *kind: 2 hit from
+// outside, 3 from inside; *obj: the object-space hit point (normal source).
+__device__ __forceinline__ float sphere_exact(const DevGeom& G, V3 o, V3 d, V3* obj, int* kind) {
+  const V3 ro = xform(G.inv, o, 1.0f);
+  const V3 rd = normalize(xform(G.inv, d, 0.0f));
+  const float vdd = dot(ro, rd);
+  const float radicand = vdd * vdd - (dot(ro, ro) - 0.25f);
+  if (radicand < 0) return -1.0f;
+  const float sq = sqrtf(radicand);
+  const float first = -vdd;
+  const float t1 = first + sq, t2 = first - sq;
+  if (t1 < 0 && t2 < 0) return -1.0f;
+  float ts;
+  if (t1 > 0 && t2 > 0) { ts = fminf(t1, t2); *kind = 2; } else { ts = fmaxf(t1, t2); *kind = 3; }
+  const V3 p = ro + normalize(rd) * (ts - .0001f);
+  *obj = p;
+  return length(o - xform(G.fwd, p, 1.0f));
+}
+
+// Conservative world-space pre-test against a geom's padded bounding box.
+// Returns false only if the exact test is certain to miss, or certain to
+// return a distance that cannot beat t_best (strictly closer hits win).
+__device__ __forceinline__ bool may_beat(const DevGeom& G, V3 o, V3 id, float t_best, bool world_metric) {
+  float tn, tf;
+  slab(G.wmin.x, G.wmin.y, G.wmin.z, G.wmax.x, G.wmax.y, G.wmax.z, o, id, &tn, &tf);
+  if (!(tn <= tf) || tf < 0.0f) return false;
+  // G.wmin.w = slack: the exact tests pull the hit point back by 1e-4 in OBJECT
+  // space (getPointOnRay), i.e. by up to 1e-4 * scale in world space
+  if (world_metric && t_best < FLT_MAX && tn > t_best * 1.0001f + G.wmin.w) return false;
+  return true;
+}
+
+// The mesh part of the winner's record: uv, geometric normal, bump map
+// (apps/src/intersections.h:226,235-279).
+__device__ __forceinline__ void mesh_record(const DevGeom& G, const DevMesh& M, int face, float bu, float bv, V3* nrm_out,
+                                            float* tu_out, float* tv_out) {
+  const float* fp = M.face_pos + 9 * (size_t)face;
+  const float* fu = M.face_uv + 6 * (size_t)face;
+  const V3 v0 = mk(__ldg(fp), __ldg(fp + 1), __ldg(fp + 2));
+  const V3 v1 = mk(__ldg(fp + 3), __ldg(fp + 4), __ldg(fp + 5));
+  const V3 v2 = mk(__ldg(fp + 6), __ldg(fp + 7), __ldg(fp + 8));
+  const float u0x = __ldg(fu), u0y = __ldg(fu + 1), u1x = __ldg(fu + 2), u1y = __ldg(fu + 3);
+  const float u2x = __ldg(fu + 4), u2y = __ldg(fu + 5);
+  const float w = 1 - bu - bv;
+  const float tu = (w * u0x + bu * u1x) + bv * u2x;
+  const float tv = (w * u0y + bu * u1y) + bv * u2y;
+  const V3 e1 = v1 - v0, e2 = v2 - v0;
+  V3 nrm = normalize(xform(G.invT, normalize(cross(e1, e2)), 0.0f));
+  if (M.bump.channels) {
+    const float d1x = u1x - u0x, d1y = u1y - u0y, d2x = u2x - u0x, d2y = u2y - u0y;
+    const float f = 1.0f / (d1x * d2y - d2x * d1y);
+    V3 tang = mk(f * (d2y * e1.x - d1y * e2.x), f * (d2y * e1.y - d1y * e2.y), f * (d2y * e1.z - d1y * e2.z));
+    tang = normalize(tang);
+    V3 bit = mk(f * (-d2x * e1.x + d1x * e2.x), f * (-d2x * e1.y + d1x * e2.y), f * (-d2x * e1.z + d1x * e2.z));
+    bit = normalize(bit);
+    const V3 T = normalize(xform(G.fwd, tang, 0.0f));
+    const V3 B = normalize(xform(G.fwd, bit, 0.0f));
+    V3 tsn = normalize(fetch_texel(M.bump, tu, tv));
+    tsn = normalize(mk(tsn.x * 2.0f - 1.0f, tsn.y * 2.0f - 1.0f, tsn.z * 2.0f - 1.0f));
+    nrm = normalize(mk((T.x * tsn.x + B.x * tsn.y) + nrm.x * tsn.z, (T.y * tsn.x + B.y * tsn.y) + nrm.y * tsn.z,
+                       (T.z * tsn.x + B.z * tsn.y) + nrm.z * tsn.z));
+  }
+  *nrm_out = nrm;
+  *tu_out = tu;
+  *tv_out = tv;
+}
+
+// Closest hit in two kernels per depth.
+//
+//  k_intersect_analytic  one thread per ray against the analytic geoms (cubes,
+//     spheres): a cheap padded world-box pre-test skips geoms that cannot win,
+//     the survivors run the exact reference tests.  The record of the best
+//     analytic hit (or the miss), the sort key and the material histogram are
+//     written at once.  Rays whose path crosses a mesh's box in front of that
+//     hit are appended to a device queue (one atomic per warp).
+//  k_intersect_mesh      persistent warps drain the queue, 32 rays at a time, all
+//     lanes walking (in the first version only the few lanes of a batch that
+//     touched the mesh were active during the walk: 11 of 32).  Rays the mesh
+//     wins get their record, key and histogram entry rewritten.
+// The closest hit is the lexicographic minimum of (t, geom id) over all geoms,
+// which is what the reference's strict `<` loop in geom order returns.
+__global__ void __launch_bounds__(256) k_intersect_analytic(IsectParams p) {
+  __shared__ DevGeom sgeom[kMaxGeoms];
+  __shared__ int shist[kMaxMaterials];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int n_geoms = p.scene.n_geoms;
+  {
+    const float4* src = reinterpret_cast<const float4*>(p.scene.geoms);
+    float4* dst = reinterpret_cast<float4*>(sgeom);
+    const int words = n_geoms * (int)(sizeof(DevGeom) / 16);
+    for (int i = tid; i < words; i += blockDim.x) dst[i] = __ldg(src + i);
+    for (int i = tid; i < kMaxMaterials; i += blockDim.x) shist[i] = 0;
+  }
+  __syncthreads();
+  const int n = p.ctr->n_live[p.depth];
+  const int n_meshes = p.scene.n_meshes;
+  // whole warps stride over the rays so that the ballots below are warp-wide
+  for (int base = (blockIdx.x * blockDim.x + tid) & ~31; base < n; base += gridDim.x * blockDim.x) {
+    const int i = base + lane;
+    const bool valid = i < n;
+    int mat = 0;
+    bool want_mesh = false;
+    if (valid) {
+      const float4 a = p.in.s0[i];
+      const float4 b = p.in.s1[i];
+      const V3 o = mk(a.x, a.y, a.z), d = mk(b.x, b.y, b.z);
+      const V3 id = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+      float t_min = FLT_MAX;
+      int hit = -1, kind = 0;
+      V3 aux = mk(0, 0, 0);  // box: axis normal; sphere: object-space point
+      // Pass 1 (warp-coherent, cheap): which geoms does this ray's path cross?
+      unsigned long long cand = 0ull;
+      for (int g = 0; g < n_geoms; ++g) {
+        const DevGeom& G = sgeom[g];
+        if ((G.type == 1 || G.type == 0) && may_beat(G, o, id, FLT_MAX, true)) cand |= 1ull << g;
+      }
+      // Pass 2: each lane runs the exact tests of ITS candidates (typically 1-3
+      // of the 8-9 geoms), in geom order; the warp iterates max-popcount times
+      // instead of once per geom.
+      while (cand) {
+        const int g = __ffsll((long long)cand) - 1;
+        cand &= cand - 1ull;
+        const DevGeom& G = sgeom[g];
+        if (!may_beat(G, o, id, t_min, true)) continue;
+        float t;
+        V3 taux = mk(0, 0, 0);
+        int tkind = 1;
+        if (G.type == 1) t = box_exact(G, o, d, &taux); else t = sphere_exact(G, o, d, &taux, &tkind);
+        if (t > 0.0f && t_min > t) {  // candidates are visited in index order: strict < keeps the lowest id
+          t_min = t;
+          hit = g;
+          kind = tkind;
+          aux = taux;
+        }
+      }
+      float4 h0, h1;
+      if (hit < 0) {
+        h0 = make_float4(-1.0f, 0.0f, 0.0f, 0.0f);
+        h1 = make_float4(0.0f, 0.0f, __int_as_float(0xffff), __int_as_float(-1));
+      } else {
+        const DevGeom& G = sgeom[hit];
+        V3 nrm = normalize(xform(G.invT, aux, 0.0f));
+        if (kind == 3) nrm = -nrm;
+        mat = G.material;
+        h0 = make_float4(t_min, nrm.x, nrm.y, nrm.z);
+        h1 = make_float4(0.0f, 0.0f, __int_as_float((hit & 0xffff) | (mat << 16)), __int_as_float(-1));
+      }
+      p.out.h0[i] = h0;
+      p.out.h1[i] = h1;
+      p.key[i] = (uint8_t)mat;
+      if (n_meshes > 0) {
+        for (int g = 0; g < n_geoms && !want_mesh; ++g) {
+          const DevGeom& G = sgeom[g];
+          if (G.type == 3 && G.mesh >= 0) want_mesh = may_beat(G, o, id, t_min, G.rigid != 0);
+        }
+      }
+    }
+    const unsigned int active = __ballot_sync(0xffffffffu, valid);
+    if (valid) {
+      const unsigned int peers = __match_any_sync(active, mat);
+      if (lane == __ffs(peers) - 1) atomicAdd(&shist[mat], __popc(peers));
+    }
+    const unsigned int mm = __ballot_sync(0xffffffffu, want_mesh);
+    if (mm) {
+      unsigned int qbase = 0;
+      if (lane == 0) qbase = atomicAdd(&p.ctr->mesh_count[p.depth], (unsigned int)__popc(mm));
+      qbase = __shfl_sync(0xffffffffu, qbase, 0);
+      if (want_mesh) p.queue[qbase + __popc(mm & ((1u << lane) - 1u))] = i;
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < kMaxMaterials; i += blockDim.x) {
+    const int c = shist[i];
+    if (c) atomicAdd(&p.ctr->hist[p.depth][i], (unsigned int)c);
+  }
+  if (blockIdx.x == 0 && tid == 0) atomicAdd(&p.ctr->segments, (unsigned long long)n);
+}
+
+// Persistent warps take 32 queued rays at a time; every lane walks the 4-wide
+// LBVH for its own ray in one tight loop.  (A variant that refilled finished
+// lanes from the queue and finished long walks cooperatively kept more lanes
+// busy but executed so many more instructions per step that it was 20 % slower;
+// see profiles/r01_notes.md.)
+template <bool USE_BVH>
+__global__ void __launch_bounds__(kIsectThreads, 3) k_intersect_mesh(IsectParams p) {
+  __shared__ DevGeom sgeom[kMaxGeoms];
+  __shared__ int shist[kMaxMaterials];
+  __shared__ int sstack[USE_BVH ? kShortStack * kIsectThreads : 1];
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int n_geoms = p.scene.n_geoms;
+  const unsigned int total = p.ctr->mesh_count[p.depth];
+  if (total == 0) return;
   {
-    // stage the geoms: 160-byte structs copied as 16-byte words
     const float4* src = reinterpret_cast<const float4*>(p.scene.geoms);
     float4* dst = reinterpret_cast<float4*>(sgeom);
     const int words = n_geoms * (int)(sizeof(DevGeom) / 16);
@@ -199,184 +450,71 @@ __global__ void __launch_bounds__(kIsectThreads, 2) k_intersect(IsectParams p) {
     for (int i = tid; i < kMaxMaterials; i += kIsectThreads) shist[i] = 0;
   }
   __syncthreads();
-
-  const int n = p.ctr->n_live[p.depth];
-  unsigned int* ticket = &p.ctr->ray_ticket[p.depth];
+  unsigned int* head = &p.ctr->ray_ticket[p.depth];
   int local_stack[USE_BVH ? kLocalStack : 1];
-
   while (true) {
-    unsigned int base = 0;
-    if (lane == 0) base = atomicAdd(ticket, 32u);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base >= (unsigned int)n) break;
-    const int i = (int)base + lane;
-    const bool valid = i < n;
-    int mat = 0;
-    if (valid) {
+    unsigned int qb = 0;
+    if (lane == 0) qb = atomicAdd(head, 32u);
+    qb = __shfl_sync(0xffffffffu, qb, 0);
+    if (qb >= total) break;
+    if (qb + lane < total) {
+      const int i = p.queue[qb + lane];
       const float4 a = p.in.s0[i];
       const float4 b = p.in.s1[i];
+      const float4 h0 = p.out.h0[i];
+      const int gm = __float_as_int(p.out.h1[i].z);
       const V3 o = mk(a.x, a.y, a.z), d = mk(b.x, b.y, b.z);
-
-      float t_min = FLT_MAX;
-      int hit = -1;
-      int kind = 0;         // 1 box, 2 sphere (outside), 3 sphere (inside), 4 mesh
-      V3 aux = mk(0, 0, 0); // box: axis normal; sphere: object-space point; mesh: (u, v, -)
-      int face = -1;
-
+      const V3 id = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+      float t_min = h0.x > 0.0f ? h0.x : FLT_MAX;
+      int hit = h0.x > 0.0f ? (gm & 0xffff) : 0x7fffffff;
+      const int old_mat = (gm >> 16) & 0xffff;
+      int mhit = -1, mface = -1;
+      float mbu = 0, mbv = 0;
       for (int g = 0; g < n_geoms; ++g) {
         const DevGeom& G = sgeom[g];
-        float t = -1.0f;
-        V3 taux = mk(0, 0, 0);
-        int tkind = 0, tface = -1;
-        if (G.type == 1 /* CUBE */) {
-          // boxIntersectionTest, apps/src/intersections.h:48-90
-          const V3 qo = xform(G.inv, o, 1.0f);
-          const V3 qd = normalize(xform(G.inv, d, 0.0f));
-          float tmin = -1e38f, tmax = 1e38f;
-          V3 nmin = mk(0, 0, 0), nmax = mk(0, 0, 0);
-          {
-            const float t1 = (-0.5f - qo.x) / qd.x, t2 = (+0.5f - qo.x) / qd.x;
-            const float ta = glm_min(t1, t2), tb = glm_max(t1, t2);
-            const V3 nn = mk(t2 < t1 ? +1.0f : -1.0f, 0, 0);
-            if (ta > 0 && ta > tmin) { tmin = ta; nmin = nn; }
-            if (tb < tmax) { tmax = tb; nmax = nn; }
-          }
-          {
-            const float t1 = (-0.5f - qo.y) / qd.y, t2 = (+0.5f - qo.y) / qd.y;
-            const float ta = glm_min(t1, t2), tb = glm_max(t1, t2);
-            const V3 nn = mk(0, t2 < t1 ? +1.0f : -1.0f, 0);
-            if (ta > 0 && ta > tmin) { tmin = ta; nmin = nn; }
-            if (tb < tmax) { tmax = tb; nmax = nn; }
-          }
-          {
-            const float t1 = (-0.5f - qo.z) / qd.z, t2 = (+0.5f - qo.z) / qd.z;
-            const float ta = glm_min(t1, t2), tb = glm_max(t1, t2);
-            const V3 nn = mk(0, 0, t2 < t1 ? +1.0f : -1.0f);
-            if (ta > 0 && ta > tmin) { tmin = ta; nmin = nn; }
-            if (tb < tmax) { tmax = tb; nmax = nn; }
-          }
-          if (tmax >= tmin && tmax > 0) {
-            if (tmin <= 0) { tmin = tmax; nmin = nmax; }
-            // getPointOnRay (:27-29) normalises the direction again
-            const V3 ip = xform(G.fwd, qo + normalize(qd) * (tmin - .0001f), 1.0f);
-            t = length(o - ip);
-            taux = nmin;
-            tkind = 1;
-          }
-        } else if (G.type == 0 /* SPHERE */) {
-          // sphereIntersectionTest, apps/src/intersections.h:102-144
-          const V3 ro = xform(G.inv, o, 1.0f);
-          const V3 rd = normalize(xform(G.inv, d, 0.0f));
-          const float vdd = dot(ro, rd);
-          const float radicand = vdd * vdd - (dot(ro, ro) - 0.25f);
-          if (!(radicand < 0)) {
-            const float sq = sqrtf(radicand);
-            const float first = -vdd;
-            const float t1 = first + sq, t2 = first - sq;
-            if (!(t1 < 0 && t2 < 0)) {
-              float ts;
-              if (t1 > 0 && t2 > 0) { ts = fminf(t1, t2); tkind = 2; } else { ts = fmaxf(t1, t2); tkind = 3; }
-              const V3 obj = ro + normalize(rd) * (ts - .0001f);
-              const V3 ip = xform(G.fwd, obj, 1.0f);
-              t = length(o - ip);
-              taux = obj;
-            }
-          }
-        } else if (G.type == 3 /* OBJ */ && G.mesh >= 0) {
-          // meshIntersectionTest, apps/src/intersections.h:207-282
-          const DevMesh& M = p.scene.meshes[G.mesh];
-          const V3 qo = xform(G.inv, o, 1.0f);
-          const V3 qd = normalize(xform(G.inv, d, 0.0f));
-          float bu = 0, bv = 0;
-          if (USE_BVH) {
-            StackRef st;
-            st.sm = sstack + tid;
-            st.local = local_stack;
-            st.sp = 0;
-            const float lim = (G.rigid && t_min < FLT_MAX) ? t_min * 1.0001f + 1e-5f : FLT_MAX;
-            t = mesh_traverse(M, qo, qd, lim, &tface, &bu, &bv, st);
-          } else {
-            t = mesh_brute(M, qo, qd, &tface, &bu, &bv);
-          }
-          taux = mk(bu, bv, 0);
-          tkind = 4;
-        }
-        if (t > 0.0f && t_min > t) {
-          t_min = t;
-          hit = g;
-          kind = tkind;
-          aux = taux;
-          face = tface;
-        }
-      }
-
-      float4 h0, h1;
-      if (hit < 0) {
-        h0 = make_float4(-1.0f, 0.0f, 0.0f, 0.0f);
-        h1 = make_float4(0.0f, 0.0f, __int_as_float(0xffff), __int_as_float(-1));
-      } else {
-        const DevGeom& G = sgeom[hit];
-        V3 nrm;
-        float tu = 0.0f, tv = 0.0f;
-        if (kind == 1) {
-          nrm = normalize(xform(G.invT, aux, 0.0f));
-        } else if (kind == 2 || kind == 3) {
-          nrm = normalize(xform(G.invT, aux, 0.0f));
-          if (kind == 3) nrm = -nrm;
+        if (G.type != 3 || G.mesh < 0) continue;
+        if (!may_beat(G, o, id, t_min, G.rigid != 0)) continue;
+        const DevMesh& M = p.scene.meshes[G.mesh];
+        const V3 qo = xform(G.inv, o, 1.0f);
+        const V3 qd = normalize(xform(G.inv, d, 0.0f));
+        float bu = 0, bv = 0, t;
+        int tface = -1;
+        if (USE_BVH) {
+          StackRef st;
+          st.sm = sstack + tid;
+          st.local = local_stack;
+          st.sp = 0;
+          const float lim = (G.rigid && t_min < FLT_MAX) ? t_min * 1.0001f + 1e-5f : FLT_MAX;
+          t = mesh_traverse(M, qo, qd, lim, &tface, &bu, &bv, st, p.stats);
         } else {
-          const DevMesh& M = p.scene.meshes[G.mesh];
-          const float* fp = M.face_pos + 9 * (size_t)face;
-          const float* fu = M.face_uv + 6 * (size_t)face;
-          const V3 v0 = mk(__ldg(fp), __ldg(fp + 1), __ldg(fp + 2));
-          const V3 v1 = mk(__ldg(fp + 3), __ldg(fp + 4), __ldg(fp + 5));
-          const V3 v2 = mk(__ldg(fp + 6), __ldg(fp + 7), __ldg(fp + 8));
-          const float u0x = __ldg(fu), u0y = __ldg(fu + 1), u1x = __ldg(fu + 2), u1y = __ldg(fu + 3);
-          const float u2x = __ldg(fu + 4), u2y = __ldg(fu + 5);
-          const float bu = aux.x, bv = aux.y;
-          const float w = 1 - bu - bv;
-          tu = (w * u0x + bu * u1x) + bv * u2x;
-          tv = (w * u0y + bu * u1y) + bv * u2y;
-          const V3 e1 = v1 - v0, e2 = v2 - v0;
-          nrm = normalize(xform(G.invT, normalize(cross(e1, e2)), 0.0f));
-          if (M.bump.channels) {
-            // normal map, intersections.h:245-279
-            const float d1x = u1x - u0x, d1y = u1y - u0y, d2x = u2x - u0x, d2y = u2y - u0y;
-            const float f = 1.0f / (d1x * d2y - d2x * d1y);
-            V3 tang = mk(f * (d2y * e1.x - d1y * e2.x), f * (d2y * e1.y - d1y * e2.y), f * (d2y * e1.z - d1y * e2.z));
-            tang = normalize(tang);
-            V3 bit = mk(f * (-d2x * e1.x + d1x * e2.x), f * (-d2x * e1.y + d1x * e2.y),
-                        f * (-d2x * e1.z + d1x * e2.z));
-            bit = normalize(bit);
-            const V3 T = normalize(xform(G.fwd, tang, 0.0f));
-            const V3 B = normalize(xform(G.fwd, bit, 0.0f));
-            V3 tsn = normalize(fetch_texel(M.bump, tu, tv));
-            tsn = normalize(mk(tsn.x * 2.0f - 1.0f, tsn.y * 2.0f - 1.0f, tsn.z * 2.0f - 1.0f));
-            nrm = normalize(mk((T.x * tsn.x + B.x * tsn.y) + nrm.x * tsn.z, (T.y * tsn.x + B.y * tsn.y) + nrm.y * tsn.z,
-                               (T.z * tsn.x + B.z * tsn.y) + nrm.z * tsn.z));
-          }
+          t = mesh_brute(M, qo, qd, &tface, &bu, &bv);
         }
-        mat = G.material;
-        h0 = make_float4(t_min, nrm.x, nrm.y, nrm.z);
-        h1 = make_float4(tu, tv, __int_as_float((hit & 0xffff) | (mat << 16)), __int_as_float(face));
+        if (t > 0.0f && (t < t_min || (t == t_min && g < hit))) {
+          t_min = t; hit = g; mhit = g; mface = tface; mbu = bu; mbv = bv;
+        }
       }
-      p.out.h0[i] = h0;
-      p.out.h1[i] = h1;
-      p.key[i] = (uint8_t)mat;
+      if (mhit >= 0) {
+        const DevGeom& G = sgeom[mhit];
+        V3 nrm;
+        float tu, tv;
+        mesh_record(G, p.scene.meshes[G.mesh], mface, mbu, mbv, &nrm, &tu, &tv);
+        const int mat = G.material;
+        p.out.h0[i] = make_float4(t_min, nrm.x, nrm.y, nrm.z);
+        p.out.h1[i] = make_float4(tu, tv, __int_as_float((mhit & 0xffff) | (mat << 16)), __int_as_float(mface));
+        p.key[i] = (uint8_t)mat;
+        if (mat != old_mat) {
+          atomicAdd(&shist[mat], 1);
+          atomicSub(&shist[old_mat], 1);
+        }
+      }
     }
-    // material histogram for the one-pass sort: one shared atomic per distinct
-    // material per warp
-    const unsigned int active = __ballot_sync(0xffffffffu, valid);
-    if (valid) {
-      const unsigned int peers = __match_any_sync(active, mat);
-      if (lane == __ffs(peers) - 1) atomicAdd(&shist[mat], (unsigned int)__popc(peers));
-    }
+    __syncwarp();
   }
   __syncthreads();
   for (int i = tid; i < kMaxMaterials; i += kIsectThreads) {
-    const unsigned int c = shist[i];
-    if (c) atomicAdd(&p.ctr->hist[p.depth][i], c);
+    const int c = shist[i];
+    if (c) atomicAdd(&p.ctr->hist[p.depth][i], (unsigned int)c);
   }
-  if (blockIdx.x == 0 && tid == 0) atomicAdd(&p.ctr->segments, (unsigned long long)n);
 }
 
 }  // namespace b2pt

@@ -10,10 +10,9 @@
 //   4. the Karras 2012 hierarchy (one thread per internal node, duplicates
 //      broken by index)
 //   5. bottom-up refit with one atomic counter per internal node
-//   6. traversal nodes that hold BOTH children's boxes (64 B = 4 x float4):
-//        n0 = (Lmin.xyz, Lmax.x)  n1 = (Lmax.yz, Rmin.xy)
-//        n2 = (Rmin.z, Rmax.xyz)  n3 = (left, right, -, -)   child >= 0: node, < 0: ~leaf slot
-//      and triangles in leaf order as 3 x float4 (v0|face id, v1, v2).
+//   6. 4-wide traversal nodes (k_emit_wide4): a binary node at even depth plus its
+//      grandchildren's boxes in one 128-byte line, and triangles in leaf order as
+//      3 x float4 (v0|face id, v1, v2).
 // Boxes are inflated by `pad` (a few 1e-6 of the mesh extent) so that the
 // conservative slab test can never cull a triangle the reference's exact test
 // would accept: the BVH prunes, it never decides.
@@ -204,20 +203,61 @@ __global__ void __launch_bounds__(256) k_tree_depth(int n, const int* __restrict
   atomicMax(&info->max_depth, depth);
 }
 
-// Traversal nodes: both children's boxes in the parent.
-__global__ void __launch_bounds__(256) k_emit_nodes(int n, const int2* __restrict__ children,
-                                                    const float4* __restrict__ leaf_box,
-                                                    const float4* __restrict__ node_box, float4* nodes) {
+// Depth of every internal node (number of ancestors).
+__global__ void __launch_bounds__(256) k_node_depth(int n, const int* __restrict__ parent, int* depth) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1) return;
+  int d = 0;
+  for (int p = parent[i]; p >= 0; p = parent[p]) ++d;
+  depth[i] = d;
+}
+
+// 4-wide traversal nodes: every binary node at EVEN depth becomes a wide node
+// whose children are its grandchildren (or a child that is a leaf), so a walk
+// makes half as many dependent memory round trips.  One wide node is exactly
+// one 128-byte line, boxes stored per axis for the four slots:
+//   f0 = min.x[0..3]  f1 = min.y  f2 = min.z  f3 = max.x  f4 = max.y  f5 = max.z
+//   f6 = child ids as int bits (>= 0: wide node, < 0: ~leaf slot, kEmptyChild: unused)   f7 = pad
+// Wide nodes keep the index of the binary node they come from.
+constexpr int kEmptyChild = 0x40000000;
+
+__global__ void __launch_bounds__(256) k_emit_wide4(int n, const int2* __restrict__ children, const int* __restrict__ depth,
+                                                    const float4* __restrict__ leaf_box, const float4* __restrict__ node_box,
+                                                    float4* nodes) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1) return;
+  if (depth[i] & 1) return;
+  int id[4] = {kEmptyChild, kEmptyChild, kEmptyChild, kEmptyChild};
+  int k = 0;
   const int2 c = children[i];
-  const float4* lb = c.x >= 0 ? node_box + 2 * (size_t)c.x : leaf_box + 2 * (size_t)(~c.x);
-  const float4* rb = c.y >= 0 ? node_box + 2 * (size_t)c.y : leaf_box + 2 * (size_t)(~c.y);
-  const float4 l0 = lb[0], l1 = lb[1], r0 = rb[0], r1 = rb[1];
-  nodes[4 * (size_t)i + 0] = make_float4(l0.x, l0.y, l0.z, l1.x);
-  nodes[4 * (size_t)i + 1] = make_float4(l1.y, l1.z, r0.x, r0.y);
-  nodes[4 * (size_t)i + 2] = make_float4(r0.z, r1.x, r1.y, r1.z);
-  nodes[4 * (size_t)i + 3] = make_float4(__int_as_float(c.x), __int_as_float(c.y), 0.0f, 0.0f);
+  const int side[2] = {c.x, c.y};
+  for (int s = 0; s < 2; ++s) {
+    if (side[s] < 0) {
+      id[k++] = side[s];
+    } else {
+      const int2 g = children[side[s]];
+      id[k++] = g.x;
+      id[k++] = g.y;
+    }
+  }
+  float lo[3][4], hi[3][4];
+  for (int q = 0; q < 4; ++q) {
+    float4 b0 = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, 0.0f), b1 = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, 0.0f);
+    if (id[q] != kEmptyChild) {
+      const float4* b = id[q] >= 0 ? node_box + 2 * (size_t)id[q] : leaf_box + 2 * (size_t)(~id[q]);
+      b0 = b[0];
+      b1 = b[1];
+    }
+    lo[0][q] = b0.x; lo[1][q] = b0.y; lo[2][q] = b0.z;
+    hi[0][q] = b1.x; hi[1][q] = b1.y; hi[2][q] = b1.z;
+  }
+  float4* o = nodes + 8 * (size_t)i;
+  for (int a = 0; a < 3; ++a) {
+    o[a] = make_float4(lo[a][0], lo[a][1], lo[a][2], lo[a][3]);
+    o[3 + a] = make_float4(hi[a][0], hi[a][1], hi[a][2], hi[a][3]);
+  }
+  o[6] = make_float4(__int_as_float(id[0]), __int_as_float(id[1]), __int_as_float(id[2]), __int_as_float(id[3]));
+  o[7] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
 }  // namespace b2pt

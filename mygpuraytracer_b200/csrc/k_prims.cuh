@@ -45,25 +45,6 @@ __device__ __forceinline__ unsigned int block_exclusive_scan(unsigned int v, uns
   return incl - v + smem[warp];
 }
 
-// Resolve the exclusive prefix of `tile` by decoupled look-back (one thread).
-__device__ __forceinline__ unsigned int lookback_exclusive(unsigned long long* status, unsigned int tile, unsigned int epoch,
-                                                           unsigned int total) {
-  unsigned int excl = 0;
-  st_volatile_u64(status + tile, lb_pack(epoch, tile == 0 ? 2u : 1u, total));
-  if (tile > 0) {
-    for (int t = (int)tile - 1; t >= 0; --t) {
-      unsigned long long w;
-      do {
-        w = ld_volatile_u64(status + t);
-      } while (lb_epoch(w) != epoch || lb_flag(w) == 0u);
-      excl += lb_value(w);
-      if (lb_flag(w) == 2u) break;
-    }
-    st_volatile_u64(status + tile, lb_pack(epoch, 2u, excl + total));
-  }
-  return excl;
-}
-
 // MODE 0: out[i] = exclusive prefix sum of in.
 // MODE 1: stable compaction of the non-zero elements of in; *count = kept.
 // MODE 2: in is a byte predicate; perm gets kept indices at [rank] and the
@@ -92,9 +73,12 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_family(const int* __restr
   }
   unsigned int total;
   unsigned int excl = block_exclusive_scan(sum, &total, smem);
-  if (threadIdx.x == 0) {
-    s_excl = lookback_exclusive(status, tile, epoch, total);
-    if (MODE != 0 && ((long long)tile + 1) * kScanTile >= (long long)n) *count = (int)(s_excl + total);
+  if (threadIdx.x < 32) {
+    const unsigned int e = lookback_warp(status, 1, tile, epoch, total);
+    if (threadIdx.x == 0) {
+      s_excl = e;
+      if (MODE != 0 && ((long long)tile + 1) * kScanTile >= (long long)n) *count = (int)(e + total);
+    }
   }
   __syncthreads();
   excl += s_excl;

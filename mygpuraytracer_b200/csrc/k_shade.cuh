@@ -252,21 +252,8 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade_compact(ShadeParams p) 
     }
     if (lane < kShadeWarps) warp_cnt[lane] = incl - v;  // exclusive offsets of the warps
     const unsigned int total = __shfl_sync(0xffffffffu, incl, kShadeWarps - 1);
+    const unsigned int excl = lookback_warp(p.status, 1, tile, epoch, total);
     if (lane == 0) {
-      unsigned int excl = 0;
-      unsigned long long* mine = p.status + tile;
-      st_volatile_u64(mine, lb_pack(epoch, tile == 0 ? 2u : 1u, total));
-      if (tile > 0) {
-        for (int t = (int)tile - 1; t >= 0; --t) {
-          unsigned long long w;
-          do {
-            w = ld_volatile_u64(p.status + t);
-          } while (lb_epoch(w) != epoch || lb_flag(w) == 0u);
-          excl += lb_value(w);
-          if (lb_flag(w) == 2u) break;
-        }
-        st_volatile_u64(mine, lb_pack(epoch, 2u, excl + total));
-      }
       s_excl = excl;
       // the last tile knows the live count of the next depth
       if (((long long)tile + 1) * kShadeThreads >= (long long)n) p.ctr->n_live[p.depth + 1] = (int)(excl + total);

@@ -47,6 +47,7 @@ struct MaterialSortPolicy {
   __device__ __forceinline__ unsigned int digit(int idx) const { return 255u - (unsigned int)key[idx]; }
   __device__ __forceinline__ unsigned int bin_total(int bin) const { return ctr->hist[depth][255 - bin]; }
   __device__ __forceinline__ void scatter(int idx, unsigned int pos) const { perm[pos] = idx; }
+  static constexpr bool kFewBins = true;  // a handful of materials: one warp looks back per bin
 };
 
 // Policy for one 8-bit pass of the LSD pair sort.
@@ -71,6 +72,7 @@ struct RadixPassPolicy {
     key_out[pos] = key_in[idx];
     val_out[pos] = val_in[idx];
   }
+  static constexpr bool kFewBins = false;  // all 256 bins are populated: one thread per bin
 };
 
 template <typename Policy>
@@ -111,6 +113,8 @@ __global__ void __launch_bounds__(kSortThreads) k_onesweep_pass(Policy p) {
   __syncthreads();
 
   // ---- per bin: offsets of the warps inside the tile, then look-back -----------
+  __shared__ unsigned int tile_cnt[256];
+  __shared__ unsigned int bin_tot[256];
   {
     const int b = tid;  // one thread per bin
     unsigned int run = 0;
@@ -121,8 +125,10 @@ __global__ void __launch_bounds__(kSortThreads) k_onesweep_pass(Policy p) {
       run += c;
     }
     const unsigned int total = p.bin_total(b);
+    tile_cnt[b] = run;
+    bin_tot[b] = total;
     unsigned int excl = 0;
-    if (total != 0) {  // bins nobody holds are never read
+    if (!Policy::kFewBins && total != 0) {  // bins nobody holds are never read
       unsigned long long* mine = p.status() + (size_t)tile * 256 + b;
       st_volatile_u64(mine, lb_pack(epoch, tile == 0 ? 2u : 1u, run));
       if (tile > 0) {
@@ -152,6 +158,14 @@ __global__ void __launch_bounds__(kSortThreads) k_onesweep_pass(Policy p) {
 #pragma unroll
     for (int w = 0; w < kSortWarps; ++w) add += (w < warp) ? warp_tot[w] : 0u;
     bin_base[b] = v - total + add;
+  }
+  if (Policy::kFewBins) {
+    // warp w resolves bins w, w+8, ...; only bins that exist anywhere are looked back
+    for (int b = warp; b < 256; b += kSortWarps) {
+      if (bin_tot[b] == 0) continue;  // warp-uniform
+      const unsigned int e = lookback_warp(p.status() + b, 256, tile, epoch, tile_cnt[b]);
+      if (lane == 0) tile_excl[b] = e;
+    }
   }
   __syncthreads();
 

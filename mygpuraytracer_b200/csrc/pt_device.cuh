@@ -53,10 +53,12 @@ struct DevGeom {
   int material;
   int mesh;   // index into DevScene::meshes, -1 for analytic geoms
   int rigid;  // 1 if object-space and world-space distances agree (scale == 1)
+  float4 wmin;  // padded world-space bounding box; .w = distance slack of the exact test
+  float4 wmax;
 };
 
 struct DevMesh {
-  const float4* nodes;    // 4 x float4 per internal BVH node (see k_lbvh.cuh)
+  const float4* nodes;    // 8 x float4 (one 128-byte line) per 4-wide BVH node (see k_lbvh.cuh)
   const float4* tris;     // 3 x float4 per triangle in BVH leaf order: (v0,face) (v1,-) (v2,-)
   const float* face_pos;  // 9 floats per face, original order
   const float* face_uv;   // 6 floats per face, original order
@@ -94,7 +96,8 @@ struct DevScene {
 struct Counters {
   unsigned int serial;                    // iterations started (lookback epochs)
   int n_live[kMaxDepth + 2];              // paths entering depth d
-  unsigned int ray_ticket[kMaxDepth + 1];    // dynamic work distribution, intersect
+  unsigned int ray_ticket[kMaxDepth + 1];    // head of the mesh-ray queue (k_intersect_mesh)
+  unsigned int mesh_count[kMaxDepth + 1];    // tail of the mesh-ray queue (k_intersect_analytic)
   unsigned int sort_ticket[kMaxDepth + 1];   // tile order of the sort
   unsigned int shade_ticket[kMaxDepth + 1];  // tile order of shade + compaction
   unsigned int hist[kMaxDepth + 1][kMaxMaterials];  // material histogram per depth
@@ -117,6 +120,39 @@ __device__ __forceinline__ unsigned long long ld_volatile_u64(const unsigned lon
 }
 __device__ __forceinline__ void st_volatile_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Decoupled look-back by a FULL WARP: publishes `total` as the aggregate of
+// `tile`, inspects 32 predecessors per step (each lane spins on its own status
+// word), sums the aggregates down to the nearest inclusive prefix, publishes
+// the tile's inclusive prefix and returns its exclusive prefix (to all lanes).
+// `status` points at this scan's array; consecutive tiles are `stride` words apart.
+__device__ __forceinline__ unsigned int lookback_warp(unsigned long long* status, size_t stride, unsigned int tile,
+                                                      unsigned int epoch, unsigned int total) {
+  const int lane = threadIdx.x & 31;
+  if (lane == 0) st_volatile_u64(status + (size_t)tile * stride, lb_pack(epoch, tile == 0 ? 2u : 1u, total));
+  unsigned int excl = 0;
+  for (int base = (int)tile - 1; base >= 0; base -= 32) {
+    const int t = base - lane;
+    unsigned int flag = 2u, value = 0u;  // lanes before tile 0 act as an empty inclusive prefix
+    if (t >= 0) {
+      unsigned long long w;
+      do {
+        w = ld_volatile_u64(status + (size_t)t * stride);
+      } while (lb_epoch(w) != epoch || lb_flag(w) == 0u);
+      flag = lb_flag(w);
+      value = lb_value(w);
+    }
+    const unsigned int incl = __ballot_sync(0xffffffffu, flag == 2u);
+    const int first = incl ? __ffs(incl) - 1 : 32;  // nearest inclusive prefix among these 32
+    unsigned int v = lane <= first ? value : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    excl += v;
+    if (incl) break;
+  }
+  if (tile > 0 && lane == 0) st_volatile_u64(status + (size_t)tile * stride, lb_pack(epoch, 2u, excl + total));
+  return excl;
 }
 
 }  // namespace b2pt
