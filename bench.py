@@ -58,6 +58,29 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version
+# banner) write to file descriptor 1 too, so everything but the result line is
+# sent to stderr: fd 1 is pointed at fd 2 and the line goes to a saved copy.
+_RESULT_FD = None
+
+
+def capture_stdout():
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 # ---------------------------------------------------------------------------------------
 # workload
 # ---------------------------------------------------------------------------------------
@@ -224,7 +247,7 @@ def run_reference(args, rank: int, world: int):
         "e2e": {"value": r["value"], "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": f"each step is one iteration of the bounded sample ({w}x{h}); Mpaths/s is size independent",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args, rank: int, world: int, local_rank: int):
@@ -387,7 +410,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             rg = reference_gpu(root, args)
             if rg is not None:
                 line["reference_gpu"] = rg
-        print(json.dumps(line), flush=True)
+        emit(line)
     for x in rs:
         x.close()
     if dist:
@@ -410,6 +433,7 @@ def main():
     ap.add_argument("--ref-gpu-iters", type=int, default=1)
     ap.add_argument("--ref-gpu-timeout", type=int, default=240)
     args = ap.parse_args()
+    capture_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
