@@ -122,7 +122,10 @@ struct B2ptCtx {
   PathBuf buf[2]{};
   HitBuf hits{};
   uint8_t* key = nullptr;
+  uint8_t* live = nullptr;
   int* perm = nullptr;
+  int* apos = nullptr;
+  unsigned long long* sort_status_live = nullptr;
   Counters* ctr = nullptr;
   int* iter_state = nullptr;
   unsigned long long* sort_status = nullptr;
@@ -534,6 +537,8 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
   if ((rc = c->dalloc(&c->hits.h1, P))) return rc;
   if ((rc = c->dalloc(&c->key, P))) return rc;
   if ((rc = c->dalloc(&c->perm, P))) return rc;
+  if ((rc = c->dalloc(&c->live, P))) return rc;
+  if ((rc = c->dalloc(&c->apos, P))) return rc;
   if ((rc = c->dalloc(&c->mesh_queue, P))) return rc;
   if ((rc = c->dalloc(&c->ctr, 1))) return rc;
   if ((rc = c->dalloc(&c->iter_state, 4))) return rc;
@@ -541,6 +546,7 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
   c->shade_grid = (int)((P + kShadeThreads - 1) / kShadeThreads);
   c->gen_grid = (int)std::min<size_t>((P + 255) / 256, (size_t)c->sm_count * 8);
   if ((rc = c->dalloc(&c->sort_status, (size_t)c->sort_grid * 256))) return rc;
+  if ((rc = c->dalloc(&c->sort_status_live, (size_t)c->sort_grid * 256))) return rc;
   if ((rc = c->dalloc(&c->shade_status, (size_t)c->shade_grid))) return rc;
   if ((rc = c->dalloc(&c->image, P * 3))) return rc;
   if ((rc = c->dalloc(&c->albedo, P * 3))) return rc;
@@ -548,6 +554,7 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
   CK(cudaMemsetAsync(c->ctr, 0, sizeof(Counters), c->stream));
   CK(cudaMemsetAsync(c->iter_state, 0, 4 * sizeof(int), c->stream));
   CK(cudaMemsetAsync(c->sort_status, 0, (size_t)c->sort_grid * 256 * 8, c->stream));
+  CK(cudaMemsetAsync(c->sort_status_live, 0, (size_t)c->sort_grid * 256 * 8, c->stream));
   CK(cudaMemsetAsync(c->shade_status, 0, (size_t)c->shade_grid * 8, c->stream));
   CK(cudaMemsetAsync(c->image, 0, P * 12, c->stream));
   CK(cudaMemsetAsync(c->albedo, 0, P * 12, c->stream));
@@ -639,7 +646,10 @@ static void launch_generate(B2ptCtx* c) {
 
 template <int TRIG, bool RECORD>
 static void launch_shade(B2ptCtx* c, const ShadeParams& sp) {
-  k_shade_compact<TRIG, RECORD><<<c->shade_grid, kShadeThreads, 0, c->stream>>>(sp);
+  if (sp.apos)
+    k_shade_compact<TRIG, RECORD, true><<<c->shade_grid, kShadeThreads, 0, c->stream>>>(sp);
+  else
+    k_shade_compact<TRIG, RECORD, false><<<c->shade_grid, kShadeThreads, 0, c->stream>>>(sp);
 }
 
 static void unpack3(const std::vector<float4>& v, int n, float* dst) {
@@ -691,6 +701,7 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
     ip.in = in;
     ip.out = c->hits;
     ip.key = c->key;
+    ip.live = c->live;
     ip.ctr = c->ctr;
     ip.depth = d;
     ip.stats = c->trav_stats ? c->trav_stats + 24 * d : nullptr;
@@ -706,14 +717,17 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
       c->launches += 1;
     }
     if (c->opt.sort_by_material) {
-      MaterialSortPolicy mp;
+      MatSortParams mp;
       mp.key = c->key;
+      mp.live = c->live;
       mp.perm = c->perm;
+      mp.apos = c->apos;
       mp.ctr = c->ctr;
-      mp.status_ = c->sort_status;
+      mp.status = c->sort_status;
+      mp.status_live = c->sort_status_live;
       mp.depth = d;
       if (kt) kt->mark(2);
-      k_onesweep_pass<MaterialSortPolicy><<<c->sort_grid, kSortThreads, 0, s>>>(mp);
+      k_sort_material<<<c->sort_grid, kSortThreads, 0, s>>>(mp);
       c->launches += 1;
     }
     if (record) {
@@ -733,6 +747,8 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
     sp.out = out;
     sp.hits = c->hits;
     sp.perm = c->opt.sort_by_material ? c->perm : nullptr;
+    sp.apos = c->opt.sort_by_material ? c->apos : nullptr;
+    sp.live = c->live;
     sp.ctr = c->ctr;
     sp.status = c->shade_status;
     sp.image = c->image_target;
@@ -767,6 +783,13 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
   if (time_loop) CK(cudaEventRecordWithFlags(c->ev_loop_b, s, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
   if (kt) kt->mark(-1);
   CK(cudaGetLastError());
+  if (record) {
+    // the survival flags k_intersect predicted must be what the shade then did
+    unsigned int mism = 0;
+    CK(cudaStreamSynchronize(s));
+    CK(cudaMemcpy(&mism, &c->ctr->pred_mismatch, sizeof mism, cudaMemcpyDeviceToHost));
+    if (mism) return fail(B2PT_ERR_STATE, "internal: survival prediction disagreed with the shade kernel");
+  }
   return 0;
 }
 

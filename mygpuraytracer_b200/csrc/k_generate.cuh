@@ -35,7 +35,11 @@ __global__ void k_iter_begin(Counters* c, int* iter_state, int n_paths, int dept
   }
   if (tid == 0) c->n_live[depth_slots] = 0;
   unsigned int* h = &c->hist[0][0];
-  for (int i = tid; i < depth_slots * kMaxMaterials; i += nth) h[i] = 0;
+  unsigned int* hl = &c->hist_live[0][0];
+  for (int i = tid; i < depth_slots * kMaxMaterials; i += nth) {
+    h[i] = 0;
+    hl[i] = 0;
+  }
 }
 
 // ConcentricSampleDisk, apps/src/pathtrace.cu:225-239.

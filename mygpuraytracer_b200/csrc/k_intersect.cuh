@@ -36,6 +36,7 @@ struct IsectParams {
   PathBuf in;
   HitBuf out;
   uint8_t* key;
+  uint8_t* live;  // 1 if the path will survive the coming shade (decided here, see will_survive)
   Counters* ctr;
   int depth;
   int* queue;                 // rays that must walk a mesh (filled by k_intersect_analytic)
@@ -316,6 +317,15 @@ __device__ __forceinline__ void mesh_record(const DevGeom& G, const DevMesh& M, 
   *tv_out = tv;
 }
 
+// Whether a path survives the coming shade is already decided by its hit record
+// (shadeFakeMaterial, apps/src/pathtrace.cu:463-496): a miss, an emissive
+// material, the last bounce and an emissive texel (interactions.h:182-186) kill
+// it, everything else scatters.  Computing the flag here lets the material sort
+// rank the survivors as well, so the shade kernel needs no scan of its own.
+__device__ __forceinline__ bool will_survive(const DevMaterial* __restrict__ mats, int mat, int bounces, bool emissive_texel) {
+  return !(__ldg(&mats[mat].emittance) > 0.0f) && bounces > 1 && !emissive_texel;
+}
+
 // Closest hit in two kernels per depth.
 //
 //  k_intersect_analytic  one thread per ray against the analytic geoms (cubes,
@@ -333,6 +343,7 @@ __device__ __forceinline__ void mesh_record(const DevGeom& G, const DevMesh& M, 
 __global__ void __launch_bounds__(256) k_intersect_analytic(IsectParams p) {
   __shared__ DevGeom sgeom[kMaxGeoms];
   __shared__ int shist[kMaxMaterials];
+  __shared__ int slive[kMaxMaterials];
   const int tid = threadIdx.x, lane = tid & 31;
   const int n_geoms = p.scene.n_geoms;
   {
@@ -340,7 +351,10 @@ __global__ void __launch_bounds__(256) k_intersect_analytic(IsectParams p) {
     float4* dst = reinterpret_cast<float4*>(sgeom);
     const int words = n_geoms * (int)(sizeof(DevGeom) / 16);
     for (int i = tid; i < words; i += blockDim.x) dst[i] = __ldg(src + i);
-    for (int i = tid; i < kMaxMaterials; i += blockDim.x) shist[i] = 0;
+    for (int i = tid; i < kMaxMaterials; i += blockDim.x) {
+      shist[i] = 0;
+      slive[i] = 0;
+    }
   }
   __syncthreads();
   const int n = p.ctr->n_live[p.depth];
@@ -350,7 +364,7 @@ __global__ void __launch_bounds__(256) k_intersect_analytic(IsectParams p) {
     const int i = base + lane;
     const bool valid = i < n;
     int mat = 0;
-    bool want_mesh = false;
+    bool want_mesh = false, survives = false;
     if (valid) {
       const float4 a = p.in.s0[i];
       const float4 b = p.in.s1[i];
@@ -393,12 +407,14 @@ __global__ void __launch_bounds__(256) k_intersect_analytic(IsectParams p) {
         V3 nrm = normalize(xform(G.invT, aux, 0.0f));
         if (kind == 3) nrm = -nrm;
         mat = G.material;
+        survives = will_survive(p.scene.materials, mat, __float_as_int(b.w), false);
         h0 = make_float4(t_min, nrm.x, nrm.y, nrm.z);
         h1 = make_float4(0.0f, 0.0f, __int_as_float((hit & 0xffff) | (mat << 16)), __int_as_float(-1));
       }
       p.out.h0[i] = h0;
       p.out.h1[i] = h1;
       p.key[i] = (uint8_t)mat;
+      p.live[i] = survives ? 1 : 0;
       if (n_meshes > 0) {
         for (int g = 0; g < n_geoms && !want_mesh; ++g) {
           const DevGeom& G = sgeom[g];
@@ -410,6 +426,8 @@ __global__ void __launch_bounds__(256) k_intersect_analytic(IsectParams p) {
     if (valid) {
       const unsigned int peers = __match_any_sync(active, mat);
       if (lane == __ffs(peers) - 1) atomicAdd(&shist[mat], __popc(peers));
+      const unsigned int lpeers = peers & __ballot_sync(active, survives);
+      if (lpeers && lane == __ffs(lpeers) - 1) atomicAdd(&slive[mat], __popc(lpeers));
     }
     const unsigned int mm = __ballot_sync(0xffffffffu, want_mesh);
     if (mm) {
@@ -423,6 +441,8 @@ __global__ void __launch_bounds__(256) k_intersect_analytic(IsectParams p) {
   for (int i = tid; i < kMaxMaterials; i += blockDim.x) {
     const int c = shist[i];
     if (c) atomicAdd(&p.ctr->hist[p.depth][i], (unsigned int)c);
+    const int cl = slive[i];
+    if (cl) atomicAdd(&p.ctr->hist_live[p.depth][i], (unsigned int)cl);
   }
   if (blockIdx.x == 0 && tid == 0) atomicAdd(&p.ctr->segments, (unsigned long long)n);
 }
@@ -436,6 +456,7 @@ template <bool USE_BVH>
 __global__ void __launch_bounds__(kIsectThreads, 3) k_intersect_mesh(IsectParams p) {
   __shared__ DevGeom sgeom[kMaxGeoms];
   __shared__ int shist[kMaxMaterials];
+  __shared__ int slive[kMaxMaterials];
   __shared__ int sstack[USE_BVH ? kShortStack * kIsectThreads : 1];
   const int tid = threadIdx.x;
   const int lane = tid & 31;
@@ -447,7 +468,10 @@ __global__ void __launch_bounds__(kIsectThreads, 3) k_intersect_mesh(IsectParams
     float4* dst = reinterpret_cast<float4*>(sgeom);
     const int words = n_geoms * (int)(sizeof(DevGeom) / 16);
     for (int i = tid; i < words; i += kIsectThreads) dst[i] = __ldg(src + i);
-    for (int i = tid; i < kMaxMaterials; i += kIsectThreads) shist[i] = 0;
+    for (int i = tid; i < kMaxMaterials; i += kIsectThreads) {
+      shist[i] = 0;
+      slive[i] = 0;
+    }
   }
   __syncthreads();
   unsigned int* head = &p.ctr->ray_ticket[p.depth];
@@ -502,10 +526,24 @@ __global__ void __launch_bounds__(kIsectThreads, 3) k_intersect_mesh(IsectParams
         p.out.h0[i] = make_float4(t_min, nrm.x, nrm.y, nrm.z);
         p.out.h1[i] = make_float4(tu, tv, __int_as_float((mhit & 0xffff) | (mat << 16)), __int_as_float(mface));
         p.key[i] = (uint8_t)mat;
+        // survival: an emissive texel turns the hit into a light (interactions.h:171-186)
+        const DevMesh& MM = p.scene.meshes[G.mesh];
+        bool emissive = false;
+        const DevMaterial& mm = p.scene.materials[mat];
+        // scatterRay only looks at the emission map in its OBJ branch (not reflective, not refractive)
+        if (MM.ke.channels && !(__ldg(&mm.has_reflective) > 0) && !(__ldg(&mm.has_refractive) > 0)) {
+          const V3 e = fetch_texel(MM.ke, tu, tv);
+          emissive = e.x > FLT_EPSILON || e.y > FLT_EPSILON || e.z > FLT_EPSILON;
+        }
+        const bool survives = will_survive(p.scene.materials, mat, __float_as_int(b.w), emissive);
+        const bool old_live = p.live[i] != 0;
+        p.live[i] = survives ? 1 : 0;
         if (mat != old_mat) {
           atomicAdd(&shist[mat], 1);
           atomicSub(&shist[old_mat], 1);
         }
+        if (old_live) atomicSub(&slive[old_mat], 1);
+        if (survives) atomicAdd(&slive[mat], 1);
       }
     }
     __syncwarp();
@@ -514,6 +552,8 @@ __global__ void __launch_bounds__(kIsectThreads, 3) k_intersect_mesh(IsectParams
   for (int i = tid; i < kMaxMaterials; i += kIsectThreads) {
     const int c = shist[i];
     if (c) atomicAdd(&p.ctr->hist[p.depth][i], (unsigned int)c);
+    const int cl = slive[i];
+    if (cl) atomicAdd(&p.ctr->hist_live[p.depth][i], (unsigned int)cl);
   }
 }
 

@@ -34,6 +34,7 @@ struct ShadeParams {
   PathBuf out;
   HitBuf hits;
   const int* perm;  // NULL: identity (SORT_BY_MATERIAL 0)
+  const int* apos;  // survivors in front of each sorted slot (k_sort_material); NULL: scan here
   Counters* ctr;
   unsigned long long* status;  // [tiles] look-back words
   float* image;
@@ -47,6 +48,7 @@ struct ShadeParams {
   float4* rec_s2;
   int* rec_dead;  // pixelIndex of dead paths in stable order
   int* rec_live;  // pixelIndex of live paths in stable order
+  const uint8_t* live;  // the prediction of k_intersect (checked in record mode)
 };
 
 // calculateRandomDirectionInHemisphere, apps/src/interactions.h:12-44.
@@ -71,7 +73,32 @@ __device__ __forceinline__ V3 hemisphere(V3 normal, uint32_t& rng) {
   return (normal * up + p1 * (cs * over)) + p2 * (sn * over);
 }
 
-template <int TRIG, bool RECORD>
+// Survivors go to slot `pos` of the next depth's path buffer; a path that dies
+// is gathered: image[pixelIndex] += color * PI (finalGather, pathtrace.cu:501-510,
+// PI of :44).  Adding an exact zero leaves the non-negative accumulator unchanged.
+template <bool RECORD>
+__device__ __forceinline__ void write_result(const ShadeParams& p, int j, unsigned int pos, bool alive, V3 o, V3 d, V3 col,
+                                             int pixel, int bounces) {
+  if (alive) {
+    p.out.s0[pos] = make_float4(o.x, o.y, o.z, __int_as_float(pixel));
+    p.out.s1[pos] = make_float4(d.x, d.y, d.z, __int_as_float(bounces));
+    p.out.s2[pos] = make_float4(col.x, col.y, col.z, 0.0f);
+    if (RECORD) p.rec_live[pos] = pixel;
+  } else {
+    if (col.x != 0.0f || col.y != 0.0f || col.z != 0.0f) {
+      float* px = p.image + 3 * (size_t)pixel;
+      px[0] += col.x * 3.14159265358f;
+      px[1] += col.y * 3.14159265358f;
+      px[2] += col.z * 3.14159265358f;
+    }
+    if (RECORD) p.rec_dead[j - (int)pos] = pixel;
+  }
+}
+
+// PRECOMP: the compaction ranks come from k_sort_material (apos); the kernel is
+// then embarrassingly parallel -- no shared memory, no barrier, no look-back.
+// Without the material sort (SORT_BY_MATERIAL 0) it scans the survivors itself.
+template <int TRIG, bool RECORD, bool PRECOMP>
 __global__ void __launch_bounds__(kShadeThreads) k_shade_compact(ShadeParams p) {
   __shared__ unsigned int warp_cnt[kShadeWarps];
   __shared__ unsigned int s_tile;
@@ -79,7 +106,11 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade_compact(ShadeParams p) 
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = p.ctr->n_live[p.depth];
-  if (tid == 0) s_tile = atomicAdd(&p.ctr->shade_ticket[p.depth], 1u);
+  if (PRECOMP) {
+    if (tid == 0) s_tile = blockIdx.x;  // no ordering between tiles is needed
+  } else {
+    if (tid == 0) s_tile = atomicAdd(&p.ctr->shade_ticket[p.depth], 1u);
+  }
   __syncthreads();
   const unsigned int tile = s_tile;
   if ((long long)tile * kShadeThreads >= (long long)n) return;
@@ -239,7 +270,15 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade_compact(ShadeParams p) 
   }
 
   // ---- stable compaction: rank among the survivors --------------------------------
-  const unsigned int ballot = __ballot_sync(0xffffffffu, alive);
+  unsigned int ballot = 0;
+  if (PRECOMP) {
+    if (!valid) return;
+    const unsigned int pos = (unsigned int)p.apos[j];
+    write_result<RECORD>(p, j, pos, alive, o, d, col, pixel, bounces);
+    if (RECORD && alive != (p.live[p.perm ? p.perm[j] : j] != 0)) atomicAdd(&p.ctr->pred_mismatch, 1u);
+    return;
+  }
+  ballot = __ballot_sync(0xffffffffu, alive);
   if (lane == 0) warp_cnt[warp] = __popc(ballot);
   __syncthreads();
   if (warp == 0) {
@@ -262,22 +301,7 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade_compact(ShadeParams p) 
   __syncthreads();
   if (!valid) return;
   const unsigned int pos = s_excl + warp_cnt[warp] + __popc(ballot & ((1u << lane) - 1u));
-  if (alive) {
-    p.out.s0[pos] = make_float4(o.x, o.y, o.z, __int_as_float(pixel));
-    p.out.s1[pos] = make_float4(d.x, d.y, d.z, __int_as_float(bounces));
-    p.out.s2[pos] = make_float4(col.x, col.y, col.z, 0.0f);
-    if (RECORD) p.rec_live[pos] = pixel;
-  } else {
-    // finalGather: image[pixelIndex] += color * PI (PI of pathtrace.cu:44).
-    // Adding an exact zero leaves the non-negative accumulator unchanged.
-    if (col.x != 0.0f || col.y != 0.0f || col.z != 0.0f) {
-      float* px = p.image + 3 * (size_t)pixel;
-      px[0] += col.x * 3.14159265358f;
-      px[1] += col.y * 3.14159265358f;
-      px[2] += col.z * 3.14159265358f;
-    }
-    if (RECORD) p.rec_dead[j - (int)pos] = pixel;
-  }
+  write_result<RECORD>(p, j, pos, alive, o, d, col, pixel, bounces);
 }
 
 }  // namespace b2pt

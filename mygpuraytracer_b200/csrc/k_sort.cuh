@@ -199,4 +199,144 @@ __global__ void __launch_bounds__(256) k_radix_hist(const uint32_t* __restrict__
   }
 }
 
+// Material sort + compaction ranks in one pass.
+//
+// For every path the kernel produces its sorted slot j (stable, descending
+// material: the permutation of thrust::sort_by_key at pathtrace.cu:612) AND the
+// number A of SURVIVING paths in front of it in that sorted order.  k_intersect
+// already decided which paths survive the shade (will_survive), so
+//   survivor at sorted slot j  -> slot A of the next depth   (the live prefix of
+//   dead path at sorted slot j -> place j - A of the dead tail    stable_partition, :649)
+// and the shade kernel needs no scan, no barrier and no look-back of its own.
+// Ranks inside a tile come from warp match_any on the material digit, with a
+// ballot of the survivors folded in; tile prefixes come from two decoupled
+// look-backs per material that exists (all paths / survivors).
+struct MatSortParams {
+  const uint8_t* key;
+  const uint8_t* live;
+  int* perm;   // perm[j] = pre-sort slot
+  int* apos;   // apos[j] = survivors in front of sorted slot j
+  Counters* ctr;
+  unsigned long long* status;       // [tiles][256] all paths
+  unsigned long long* status_live;  // [tiles][256] survivors
+  int depth;
+};
+
+__global__ void __launch_bounds__(kSortThreads) k_sort_material(MatSortParams p) {
+  __shared__ unsigned int wcnt[kSortWarps][256];
+  __shared__ unsigned int wlive[kSortWarps][256];
+  __shared__ unsigned int bin_base[256], live_base[256], tile_excl[256], tile_lexcl[256];
+  __shared__ unsigned int tile_cnt[256], tile_lcnt[256], bin_tot[256], bin_ltot[256];
+  __shared__ unsigned int warp_tot[kSortWarps], warp_ltot[kSortWarps];
+  __shared__ unsigned int s_tile;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = p.ctr->n_live[p.depth];
+  if (tid == 0) s_tile = atomicAdd(&p.ctr->sort_ticket[p.depth], 1u);
+  for (int i = tid; i < kSortWarps * 256; i += kSortThreads) {
+    (&wcnt[0][0])[i] = 0;
+    (&wlive[0][0])[i] = 0;
+  }
+  __syncthreads();
+  const unsigned int tile = s_tile;
+  if ((long long)tile * kSortTile >= (long long)n) return;
+  const unsigned int epoch = p.ctr->serial * (unsigned int)(kMaxDepth + 1) + (unsigned int)p.depth + 1u;
+
+  const int wbase = (int)tile * kSortTile + warp * (kSortRows * 32);
+  unsigned short lrank[kSortRows], larank[kSortRows], ldig[kSortRows];
+#pragma unroll
+  for (int r = 0; r < kSortRows; ++r) {
+    const int idx = wbase + r * 32 + lane;
+    const bool valid = idx < n;
+    const unsigned int dig = valid ? 255u - (unsigned int)p.key[idx] : 256u + (unsigned int)lane;
+    const bool alive = valid && p.live[idx] != 0;
+    const unsigned int peers = __match_any_sync(0xffffffffu, dig);
+    const unsigned int lpeers = peers & __ballot_sync(0xffffffffu, alive);
+    unsigned int before = 0, lbefore = 0;
+    if (valid) {
+      before = wcnt[warp][dig];
+      lbefore = wlive[warp][dig];
+    }
+    __syncwarp();
+    if (valid && lane == __ffs(peers) - 1) {
+      wcnt[warp][dig] = before + __popc(peers);
+      wlive[warp][dig] = lbefore + __popc(lpeers);
+    }
+    __syncwarp();
+    const unsigned int lt = (1u << lane) - 1u;
+    lrank[r] = (unsigned short)(before + __popc(peers & lt));
+    larank[r] = (unsigned short)(lbefore + __popc(lpeers & lt));
+    ldig[r] = (unsigned short)dig;
+  }
+  __syncthreads();
+  {
+    const int b = tid;  // one thread per bin
+    unsigned int run = 0, lrun = 0;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) {
+      const unsigned int c = wcnt[w][b], cl = wlive[w][b];
+      wcnt[w][b] = run;
+      wlive[w][b] = lrun;
+      run += c;
+      lrun += cl;
+    }
+    const unsigned int total = p.ctr->hist[p.depth][255 - b];
+    const unsigned int ltotal = p.ctr->hist_live[p.depth][255 - b];
+    tile_cnt[b] = run;
+    tile_lcnt[b] = lrun;
+    bin_tot[b] = total;
+    bin_ltot[b] = ltotal;
+    tile_excl[b] = 0;
+    tile_lexcl[b] = 0;
+    // exclusive scans of the two histograms over the bins -> bases
+    unsigned int v = total, vl = ltotal;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned int t = __shfl_up_sync(0xffffffffu, v, o);
+      const unsigned int tl = __shfl_up_sync(0xffffffffu, vl, o);
+      if (lane >= o) {
+        v += t;
+        vl += tl;
+      }
+    }
+    if (lane == 31) {
+      warp_tot[warp] = v;
+      warp_ltot[warp] = vl;
+    }
+    __syncthreads();
+    unsigned int add = 0, ladd = 0;
+#pragma unroll
+    for (int w = 0; w < kSortWarps; ++w) {
+      add += (w < warp) ? warp_tot[w] : 0u;
+      ladd += (w < warp) ? warp_ltot[w] : 0u;
+    }
+    bin_base[b] = v - total + add;
+    live_base[b] = vl - ltotal + ladd;
+    // the number of survivors is the live count of the next depth
+    if (tile == 0 && b == 255) p.ctr->n_live[p.depth + 1] = (int)(vl + ladd);
+  }
+  // warp w resolves bins w, w+8, ...; only bins that exist anywhere are looked back
+  for (int b = warp; b < 256; b += kSortWarps) {
+    if (bin_tot[b] == 0) continue;  // warp-uniform
+    const unsigned int e = lookback_warp(p.status + b, 256, tile, epoch, tile_cnt[b]);
+    unsigned int el = 0;
+    if (bin_ltot[b] != 0) el = lookback_warp(p.status_live + b, 256, tile, epoch, tile_lcnt[b]);
+    if (lane == 0) {
+      tile_excl[b] = e;
+      tile_lexcl[b] = el;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kSortRows; ++r) {
+    const int idx = wbase + r * 32 + lane;
+    if (idx < n) {
+      const unsigned int dig = ldig[r];
+      const unsigned int j = bin_base[dig] + tile_excl[dig] + wcnt[warp][dig] + lrank[r];
+      p.perm[j] = idx;
+      p.apos[j] = (int)(live_base[dig] + tile_lexcl[dig] + wlive[warp][dig] + larank[r]);
+    }
+  }
+}
+
 }  // namespace b2pt

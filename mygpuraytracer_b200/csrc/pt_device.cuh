@@ -100,7 +100,9 @@ struct Counters {
   unsigned int mesh_count[kMaxDepth + 1];    // tail of the mesh-ray queue (k_intersect_analytic)
   unsigned int sort_ticket[kMaxDepth + 1];   // tile order of the sort
   unsigned int shade_ticket[kMaxDepth + 1];  // tile order of shade + compaction
-  unsigned int hist[kMaxDepth + 1][kMaxMaterials];  // material histogram per depth
+  unsigned int hist[kMaxDepth + 1][kMaxMaterials];       // material histogram per depth
+  unsigned int hist_live[kMaxDepth + 1][kMaxMaterials];  // ... of the paths that will survive the shade
+  unsigned int pred_mismatch;                            // record mode: shade disagreed with the prediction
   unsigned long long segments;            // total path segments since creation
 };
 
