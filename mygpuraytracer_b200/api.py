@@ -41,7 +41,8 @@ from . import abi
 from .podscene import PodScene
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb2pt.so")
+# B2PT_LIB: an alternative build of the same library (kernel experiments, tools/build_variants.py)
+LIB_PATH = os.environ.get("B2PT_LIB") or os.path.join(_HERE, "libb2pt.so")
 _lib: Optional[C.CDLL] = None
 
 

@@ -32,6 +32,7 @@
 #include "k_prims.cuh"
 #include "k_shade.cuh"
 #include "k_sort.cuh"
+#include "k_walk.cuh"
 #include "pt_device.cuh"
 
 using namespace b2pt;
@@ -142,6 +143,9 @@ struct B2ptCtx {
   unsigned long long* trav_stats = nullptr;  // [depth][24], B2PT_TRAVERSAL_STATS=1 only
   void* l2_window_ptr = nullptr;
   size_t l2_window_bytes = 0;
+  int walk_grid = 0, finish_grid = 0, long_grid = 0, long_walk = 32;
+  int2* long_queue = nullptr;
+  bool old_walk = false;
   int isect_grid = 0, analytic_grid = 0, sort_grid = 0, shade_grid = 0, gen_grid = 0;
   int* mesh_queue = nullptr;
   cudaEvent_t ev_loop_a = nullptr, ev_loop_b = nullptr;
@@ -540,6 +544,7 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
   if ((rc = c->dalloc(&c->live, P))) return rc;
   if ((rc = c->dalloc(&c->apos, P))) return rc;
   if ((rc = c->dalloc(&c->mesh_queue, P))) return rc;
+  if ((rc = c->dalloc(&c->long_queue, P * (size_t)std::max(1, (int)hm.size())))) return rc;
   if ((rc = c->dalloc(&c->ctr, 1))) return rc;
   if ((rc = c->dalloc(&c->iter_state, 4))) return rc;
   c->sort_grid = (int)((P + kSortTile - 1) / kSortTile);
@@ -577,6 +582,16 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
   else
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_intersect_mesh<false>, kIsectThreads, 0));
   c->isect_grid = c->sm_count * std::max(occ, 1);
+  c->old_walk = getenv("B2PT_OLD_WALK") != nullptr;
+  if (c->trav_stats)
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mesh_walk<true>, kWalkThreads, 0));
+  else
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mesh_walk<false>, kWalkThreads, 0));
+  c->walk_grid = c->sm_count * std::max(occ, 1);
+  c->finish_grid = c->sm_count * 8;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mesh_walk_long, kCoopThreads, 0));
+  c->long_grid = c->sm_count * std::max(occ, 1);
+  if (const char* e = getenv("B2PT_LONG_WALK")) c->long_walk = std::max(atoi(e), 1);
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_intersect_analytic, 256, 0));
   c->analytic_grid = (int)std::min<size_t>((P + 255) / 256, (size_t)c->sm_count * std::max(occ, 1) * 2);
 
@@ -707,14 +722,26 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
     ip.stats = c->trav_stats ? c->trav_stats + 24 * d : nullptr;
     if (kt) kt->mark(1);
     ip.queue = c->mesh_queue;
+    ip.long_queue = c->long_queue;
+    ip.long_walk = c->long_walk;
     k_intersect_analytic<<<c->analytic_grid, 256, 0, s>>>(ip);
     c->launches += 1;
     if (c->dscene.n_meshes > 0) {
-      if (c->opt.use_bvh)
-        k_intersect_mesh<true><<<c->isect_grid, kIsectThreads, 0, s>>>(ip);
-      else
-        k_intersect_mesh<false><<<c->isect_grid, kIsectThreads, 0, s>>>(ip);
-      c->launches += 1;
+      if (c->opt.use_bvh && !c->old_walk) {
+        if (c->trav_stats)
+          k_mesh_walk<true><<<c->walk_grid, kWalkThreads, 0, s>>>(ip);
+        else
+          k_mesh_walk<false><<<c->walk_grid, kWalkThreads, 0, s>>>(ip);
+        k_mesh_walk_long<<<c->long_grid, kCoopThreads, 0, s>>>(ip);
+        k_mesh_finish<<<c->finish_grid, 256, 0, s>>>(ip);
+        c->launches += 3;
+      } else {
+        if (c->opt.use_bvh)
+          k_intersect_mesh<true><<<c->isect_grid, kIsectThreads, 0, s>>>(ip);
+        else
+          k_intersect_mesh<false><<<c->isect_grid, kIsectThreads, 0, s>>>(ip);
+        c->launches += 1;
+      }
     }
     if (c->opt.sort_by_material) {
       MatSortParams mp;

@@ -30,6 +30,8 @@ __global__ void k_iter_begin(Counters* c, int* iter_state, int n_paths, int dept
     if (i > 0) c->n_live[i] = 0;
     c->ray_ticket[i] = 0;
     c->mesh_count[i] = 0;
+    c->long_count[i] = 0;
+    c->long_ticket[i] = 0;
     c->sort_ticket[i] = 0;
     c->shade_ticket[i] = 0;
   }

@@ -40,6 +40,8 @@ struct IsectParams {
   Counters* ctr;
   int depth;
   int* queue;                 // rays that must walk a mesh (filled by k_intersect_analytic)
+  int2* long_queue;           // (ray, geom) walks that outgrew one lane (filled by k_mesh_walk)
+  int long_walk;              // steps after which k_mesh_walk hands a walk to k_mesh_walk_long
   unsigned long long* stats;  // optional traversal statistics (B2PT_TRAVERSAL_STATS=1), else NULL
 };
 

@@ -98,6 +98,8 @@ struct Counters {
   int n_live[kMaxDepth + 2];              // paths entering depth d
   unsigned int ray_ticket[kMaxDepth + 1];    // head of the mesh-ray queue (k_intersect_mesh)
   unsigned int mesh_count[kMaxDepth + 1];    // tail of the mesh-ray queue (k_intersect_analytic)
+  unsigned int long_count[kMaxDepth + 1];    // tail of the long-walk queue (k_mesh_walk)
+  unsigned int long_ticket[kMaxDepth + 1];   // head of the long-walk queue (k_mesh_walk_long)
   unsigned int sort_ticket[kMaxDepth + 1];   // tile order of the sort
   unsigned int shade_ticket[kMaxDepth + 1];  // tile order of shade + compaction
   unsigned int hist[kMaxDepth + 1][kMaxMaterials];       // material histogram per depth

@@ -1,0 +1,24 @@
+"""Sweep of the long-walk hand-off threshold (B2PT_LONG_WALK) on the headline scene."""
+import sys, os, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from mygpuraytracer_b200 import api, abi, assets
+root = assets.prepare()
+assets.set_mesh(root, 250000)
+sc = api.Scene(assets.scene_file("cornellSpaceship", 1920, 1080, root=root))
+for lw in sys.argv[1:]:
+    os.environ["B2PT_LONG_WALK"] = lw
+    with api.Renderer(sc, abi.default_options()) as r:
+        r.render(1, 5, 1); r.sync()
+        t0 = time.time(); r.render(6, 30, 1); r.sync(); dt = (time.time() - t0) / 30 * 1e3
+        prof = r.profile_iteration(100)
+    K = 3
+    rs = [api.Renderer(sc, abi.default_options()) for _ in range(K)]
+    for k, r in enumerate(rs): r.render(k + 1, 4, K)
+    for r in rs: r.sync()
+    iters = 48
+    t0 = time.time()
+    for k, r in enumerate(rs): r.render(100 + k, iters // K, K)
+    for r in rs: r.sync()
+    dt3 = (time.time() - t0) / iters * 1e3
+    for r in rs: r.close()
+    print(f"long_walk={lw}: 1 stream {dt:.3f} ms/iter, 3 streams {dt3:.3f} ms/iter, prof={ {k: round(v,3) for k,v in prof.items()} }", flush=True)
