@@ -226,6 +226,28 @@ float b2pt_last_loop_ms(B2ptCtx* ctx);
  * variant).  rgba8_dev is device memory, W*H*4 bytes. */
 int b2pt_tonemap_rgba8(B2ptCtx* ctx, const float* src_dev, int32_t iter, uint8_t* rgba8_dev);
 
+/* ---- output hand-off (saveImage, CPUdenoise) ---------------------------------- */
+enum { B2PT_AOV_IMAGE = 0, B2PT_AOV_ALBEDO = 1 };
+
+/* The pixels saveImage() hands to image::savePNG (apps/src/main.cpp:115-135,
+ * apps/src/image.cpp:22-33), quantised on the device:
+ *     v = image / samples (B2PT_AOV_IMAGE)  or  albedo (B2PT_AOV_ALBEDO)
+ *     rgb8[(y*W + x')*3 + c] = (unsigned char)(clamp(v, 0, 1) * 255.f)
+ * with x' = W-1-x when mirror_x != 0 (saveImage mirrors, main.cpp:126).
+ * rgb8_host holds W*H*3 bytes.  Synchronous. */
+int b2pt_resolve_rgb8(B2ptCtx* ctx, int32_t aov, int32_t samples, int32_t mirror_x, uint8_t* rgb8_host);
+
+/* saveImage + image::savePNG: write the mirrored, quantised AOV as an 8-bit RGB
+ * PNG at `path` (the caller composes the "<FILE>.<time>.<n>samp.png" name). */
+int b2pt_save_png(B2ptCtx* ctx, int32_t aov, int32_t samples, const char* path);
+
+/* The denoiser's "color" input (CPUdenoise, apps/src/main.cpp:189-203):
+ * color = image / (float)iter as W*H Float3, written to color_dev (device
+ * memory, may be NULL) and/or color_host (may be NULL).  Together with
+ * b2pt_device_albedo() these are the two images oidn::Filter::setImage takes,
+ * so a device-side denoiser needs no host round trip. */
+int b2pt_resolve_color(B2ptCtx* ctx, int32_t iter, float* color_dev, float* color_host);
+
 /* ---- statistics and stage dumps (parity / measurement) --------------------- */
 
 /* Live path counts of the last rendered iteration: n_live[d] = number of

@@ -189,6 +189,22 @@ class Renderer:
         C.memmove(C.byref(cam), np.ascontiguousarray(camera).ctypes.data, C.sizeof(abi.Camera))
         _check(self.lib.b2pt_set_camera(self._h, C.byref(cam)))
 
+    # -- output hand-off (saveImage / CPUdenoise, apps/src/main.cpp:115-219) ---------------
+    def resolve_rgb8(self, aov: int = abi.AOV_IMAGE, samples: int = 1, mirror_x: bool = True) -> np.ndarray:
+        """The (H, W, 3) uint8 pixels ``saveImage`` hands to ``image::savePNG``."""
+        out = np.empty((self.pod.height, self.pod.width, 3), np.uint8)
+        _check(self.lib.b2pt_resolve_rgb8(self._h, aov, samples, 1 if mirror_x else 0, out.ctypes.data))
+        return out
+
+    def save_png(self, path: str, aov: int = abi.AOV_IMAGE, samples: int = 1) -> None:
+        _check(self.lib.b2pt_save_png(self._h, aov, samples, os.fsencode(path)))
+
+    def resolve_color(self, iteration: int, color_dev: int = 0) -> np.ndarray:
+        """``image / iteration`` as Float3: the denoiser's colour input (main.cpp:194-201)."""
+        out = np.empty((self.n_pixels, 3), np.float32)
+        _check(self.lib.b2pt_resolve_color(self._h, iteration, color_dev or None, out.ctypes.data))
+        return out
+
     def last_loop_ms(self) -> float:
         return float(self.lib.b2pt_last_loop_ms(self._h))
 

@@ -33,6 +33,7 @@
 #include "k_shade.cuh"
 #include "k_sort.cuh"
 #include "k_walk.cuh"
+#include "host/png_writer.h"
 #include "pt_device.cuh"
 
 using namespace b2pt;
@@ -143,6 +144,12 @@ struct B2ptCtx {
   unsigned long long* trav_stats = nullptr;  // [depth][24], B2PT_TRAVERSAL_STATS=1 only
   void* l2_window_ptr = nullptr;
   size_t l2_window_bytes = 0;
+  // first-bounce cache (pathtrace.cu:586-610, intended semantics): with AA and DOF off the camera rays are the
+  // same every iteration, so depth 0 keeps its own hit/key/live buffers, filled once and reused afterwards
+  bool fb_enabled = false, fb_valid = false;
+  HitBuf fb_hits{};
+  uint8_t *fb_key = nullptr, *fb_live = nullptr;
+  unsigned int* fb_hist = nullptr;  // [2][kMaxMaterials]: hist[0], hist_live[0] of the cached depth
   int walk_grid = 0, finish_grid = 0, long_grid = 0, long_walk = 32;
   int2* long_queue = nullptr;
   bool old_walk = false;
@@ -563,6 +570,14 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
   CK(cudaMemsetAsync(c->shade_status, 0, (size_t)c->shade_grid * 8, c->stream));
   CK(cudaMemsetAsync(c->image, 0, P * 12, c->stream));
   CK(cudaMemsetAsync(c->albedo, 0, P * 12, c->stream));
+  c->fb_enabled = opt.cache_first_bounce && !opt.antialiasing && !opt.depth_of_field;
+  if (c->fb_enabled) {
+    if ((rc = c->dalloc(&c->fb_hits.h0, P))) return rc;
+    if ((rc = c->dalloc(&c->fb_hits.h1, P))) return rc;
+    if ((rc = c->dalloc(&c->fb_key, P))) return rc;
+    if ((rc = c->dalloc(&c->fb_live, P))) return rc;
+    if ((rc = c->dalloc(&c->fb_hist, (size_t)2 * kMaxMaterials))) return rc;
+  }
   if (opt.record_stages) {
     if ((rc = c->dalloc(&c->rec_s0, P))) return rc;
     if ((rc = c->dalloc(&c->rec_s1, P))) return rc;
@@ -654,6 +669,21 @@ __global__ void k_set_iter(int* iter_state, int first, int stride) {
   iter_state[2] = stride;
 }
 
+// First-bounce cache: save / restore the depth-0 material histograms (the hit records themselves stay
+// in the depth-0 buffers and are simply not recomputed).
+__global__ void k_first_bounce_hist(Counters* ctr, unsigned int* saved, int n_paths, int restore) {
+  for (int i = threadIdx.x; i < kMaxMaterials; i += blockDim.x) {
+    if (restore) {
+      ctr->hist[0][i] = saved[i];
+      ctr->hist_live[0][i] = saved[kMaxMaterials + i];
+    } else {
+      saved[i] = ctr->hist[0][i];
+      saved[kMaxMaterials + i] = ctr->hist_live[0][i];
+    }
+  }
+  if (restore && threadIdx.x == 0) atomicAdd(&ctr->segments, (unsigned long long)n_paths);
+}
+
 template <int TRIG>
 static void launch_generate(B2ptCtx* c) {
   k_generate<TRIG><<<c->gen_grid, 256, 0, c->stream>>>(c->gen, c->iter_state, c->buf[0]);
@@ -711,12 +741,16 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
       CK(cudaMemcpy(R->in_s1.data(), in.s1, (size_t)n * 16, cudaMemcpyDeviceToHost));
       CK(cudaMemcpy(R->in_s2.data(), in.s2, (size_t)n * 16, cudaMemcpyDeviceToHost));
     }
+    const bool fb = c->fb_enabled && d == 0;
+    const HitBuf hits_d = fb ? c->fb_hits : c->hits;
+    uint8_t* const key_d = fb ? c->fb_key : c->key;
+    uint8_t* const live_d = fb ? c->fb_live : c->live;
     IsectParams ip;
     ip.scene = c->dscene;
     ip.in = in;
-    ip.out = c->hits;
-    ip.key = c->key;
-    ip.live = c->live;
+    ip.out = hits_d;
+    ip.key = key_d;
+    ip.live = live_d;
     ip.ctr = c->ctr;
     ip.depth = d;
     ip.stats = c->trav_stats ? c->trav_stats + 24 * d : nullptr;
@@ -724,6 +758,10 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
     ip.queue = c->mesh_queue;
     ip.long_queue = c->long_queue;
     ip.long_walk = c->long_walk;
+    if (fb && c->fb_valid) {
+      k_first_bounce_hist<<<1, 256, 0, s>>>(c->ctr, c->fb_hist, c->P, 1);
+      c->launches += 1;
+    } else {
     k_intersect_analytic<<<c->analytic_grid, 256, 0, s>>>(ip);
     c->launches += 1;
     if (c->dscene.n_meshes > 0) {
@@ -743,10 +781,15 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
         c->launches += 1;
       }
     }
+    if (fb) {
+      k_first_bounce_hist<<<1, 256, 0, s>>>(c->ctr, c->fb_hist, c->P, 0);
+      c->launches += 1;
+    }
+    }
     if (c->opt.sort_by_material) {
       MatSortParams mp;
-      mp.key = c->key;
-      mp.live = c->live;
+      mp.key = key_d;
+      mp.live = live_d;
       mp.perm = c->perm;
       mp.apos = c->apos;
       mp.ctr = c->ctr;
@@ -760,8 +803,8 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
     if (record) {
       CK(cudaStreamSynchronize(s));
       R->h0.resize(n); R->h1.resize(n); R->perm.resize(n);
-      CK(cudaMemcpy(R->h0.data(), c->hits.h0, (size_t)n * 16, cudaMemcpyDeviceToHost));
-      CK(cudaMemcpy(R->h1.data(), c->hits.h1, (size_t)n * 16, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(R->h0.data(), hits_d.h0, (size_t)n * 16, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(R->h1.data(), hits_d.h1, (size_t)n * 16, cudaMemcpyDeviceToHost));
       if (c->opt.sort_by_material) {
         CK(cudaMemcpy(R->perm.data(), c->perm, (size_t)n * 4, cudaMemcpyDeviceToHost));
       } else {
@@ -772,10 +815,10 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
     sp.scene = c->dscene;
     sp.in = in;
     sp.out = out;
-    sp.hits = c->hits;
+    sp.hits = hits_d;
     sp.perm = c->opt.sort_by_material ? c->perm : nullptr;
     sp.apos = c->opt.sort_by_material ? c->apos : nullptr;
-    sp.live = c->live;
+    sp.live = live_d;
     sp.ctr = c->ctr;
     sp.status = c->shade_status;
     sp.image = c->image_target;
@@ -810,6 +853,7 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
   if (time_loop) CK(cudaEventRecordWithFlags(c->ev_loop_b, s, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
   if (kt) kt->mark(-1);
   CK(cudaGetLastError());
+  if (c->fb_enabled && !capturing) c->fb_valid = true;
   if (record) {
     // the survival flags k_intersect predicted must be what the shade then did
     unsigned int mism = 0;
@@ -865,6 +909,15 @@ extern "C" int b2pt_render(B2ptCtx* c, int32_t iter_first, int32_t iter_count, i
     }
     c->loop_timed = true;
     return 0;
+  }
+  if (c->fb_enabled && !c->fb_valid) {
+    // the iteration that fills the first-bounce cache runs outside the graph; the graph replays the cached form
+    int rc = enqueue_iteration(c, false, iter_count == 1);
+    if (rc) return rc;
+    if (--iter_count == 0) {
+      c->loop_timed = true;
+      return 0;
+    }
   }
   if (!c->graph_exec) {
     const int64_t before = c->launches;
@@ -923,6 +976,7 @@ extern "C" int b2pt_set_camera(B2ptCtx* c, const B2ptCamera* cam) {
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->stream));
   c->gen.cam = to_dev_camera(*cam);
+  c->fb_valid = false;
   if (c->graph_exec) {  // the camera is baked into the captured kernel arguments
     cudaGraphExecDestroy(c->graph_exec);
     cudaGraphDestroy(c->graph);
@@ -1021,6 +1075,98 @@ extern "C" int b2pt_tonemap_rgba8(B2ptCtx* c, const float* src_dev, int32_t iter
   k_tonemap<<<(c->P + 255) / 256, 256, 0, c->stream>>>(src_dev ? src_dev : c->image_target, c->P, iter, (uchar4*)rgba8_dev);
   c->launches += 1;
   CK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------
+// output hand-off: saveImage / savePNG (main.cpp:115-165, image.cpp:22-39) and the
+// denoiser inputs (main.cpp:189-203)
+// ---------------------------------------------------------------------------------
+// image::savePNG quantisation: (unsigned char)(glm::clamp(v, 0, 1) * 255.f) per channel,
+// v = image / samples (saveImage, main.cpp:126) or the albedo as it is (:129);
+// saveImage mirrors x (setPixel(width - 1 - x, y, ...)).
+__device__ __forceinline__ unsigned char png_quant(float v) {
+  float c = (v < 0.0f) ? 0.0f : v;  // glm::max(x, 0): (x < 0) ? 0 : x
+  c = (1.0f < c) ? 1.0f : c;        // glm::min(x, 1): (1 < x) ? 1 : x
+  c = c * 255.f;
+  return c == c ? (unsigned char)c : (unsigned char)0;  // NaN: the reference's cast is undefined, 0 here
+}
+
+__global__ void k_resolve_rgb8(const float* __restrict__ src, int w, int h, float samples, int divide, int mirror_x,
+                               unsigned char* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= w * h) return;
+  const int x = i % w, y = i / w;
+  float r = src[3 * (size_t)i], g = src[3 * (size_t)i + 1], b = src[3 * (size_t)i + 2];
+  if (divide) {
+    r = r / samples;
+    g = g / samples;
+    b = b / samples;
+  }
+  const size_t o = 3 * ((size_t)y * w + (mirror_x ? w - 1 - x : x));
+  dst[o] = png_quant(r);
+  dst[o + 1] = png_quant(g);
+  dst[o + 2] = png_quant(b);
+}
+
+// inputColor[index] = image[index] / (float)iteration (main.cpp:194-199), Float3 as OIDN's setImage expects.
+__global__ void k_resolve_color(const float* __restrict__ src, size_t n3, float iter, float* __restrict__ dst) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n3; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = src[i] / iter;
+}
+
+static int resolve_rgb8_host(B2ptCtx* c, int32_t aov, int32_t samples, int32_t mirror_x, std::vector<uint8_t>* out) {
+  if (aov != B2PT_AOV_IMAGE && aov != B2PT_AOV_ALBEDO) return fail(B2PT_ERR_INVALID, "aov must be B2PT_AOV_IMAGE or B2PT_AOV_ALBEDO");
+  if (aov == B2PT_AOV_IMAGE && samples <= 0) return fail(B2PT_ERR_INVALID, "samples must be > 0");
+  CK(cudaSetDevice(c->device));
+  unsigned char* d = nullptr;
+  CK(cudaMalloc(&d, (size_t)c->P * 3));
+  const float* src = aov == B2PT_AOV_IMAGE ? c->image_target : c->albedo;
+  k_resolve_rgb8<<<(c->P + 255) / 256, 256, 0, c->stream>>>(src, c->W, c->H, (float)samples, aov == B2PT_AOV_IMAGE, mirror_x, d);
+  c->launches += 1;
+  out->resize((size_t)c->P * 3);
+  cudaError_t e = cudaMemcpyAsync(out->data(), d, out->size(), cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(B2PT_ERR_CUDA, cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int b2pt_resolve_rgb8(B2ptCtx* c, int32_t aov, int32_t samples, int32_t mirror_x, uint8_t* rgb8_host) {
+  if (!c || !rgb8_host) return fail(B2PT_ERR_INVALID, "ctx and rgb8_host must not be NULL");
+  std::vector<uint8_t> v;
+  int rc = resolve_rgb8_host(c, aov, samples, mirror_x, &v);
+  if (rc) return rc;
+  memcpy(rgb8_host, v.data(), v.size());
+  return 0;
+}
+
+extern "C" int b2pt_save_png(B2ptCtx* c, int32_t aov, int32_t samples, const char* path) {
+  if (!c || !path) return fail(B2PT_ERR_INVALID, "ctx and path must not be NULL");
+  std::vector<uint8_t> v;
+  int rc = resolve_rgb8_host(c, aov, samples, 1, &v);
+  if (rc) return rc;
+  const std::string err = b2pt_host::write_png_rgb8(path, c->W, c->H, v.data());
+  if (!err.empty()) return fail(B2PT_ERR_IO, err);
+  return 0;
+}
+
+extern "C" int b2pt_resolve_color(B2ptCtx* c, int32_t iter, float* color_dev, float* color_host) {
+  if (!c) return fail(B2PT_ERR_INVALID, "ctx is NULL");
+  if (iter <= 0) return fail(B2PT_ERR_INVALID, "iter must be > 0");
+  if (!color_dev && !color_host) return fail(B2PT_ERR_INVALID, "color_dev and color_host are both NULL");
+  CK(cudaSetDevice(c->device));
+  float* d = color_dev;
+  if (!d) CK(cudaMalloc(&d, (size_t)c->P * 12));
+  k_resolve_color<<<c->sm_count * 4, 256, 0, c->stream>>>(c->image_target, (size_t)c->P * 3, (float)iter, d);
+  c->launches += 1;
+  cudaError_t e = cudaSuccess;
+  if (color_host) {
+    e = cudaMemcpyAsync(color_host, d, (size_t)c->P * 12, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  }
+  if (!color_dev) cudaFree(d);
+  if (e != cudaSuccess) return fail(B2PT_ERR_CUDA, cudaGetErrorString(e));
   return 0;
 }
 

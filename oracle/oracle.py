@@ -301,3 +301,26 @@ def num_threads() -> int:
 
 def set_num_threads(n: int) -> None:
     lib().oracle_set_num_threads(n)
+
+
+# ---- output hand-off (TEST INFRASTRUCTURE like everything in this package) -----------
+def save_image_rgb8(image: np.ndarray, width: int, height: int, samples: float = 1.0, divide: bool = True,
+                    mirror_x: bool = True) -> np.ndarray:
+    """saveImage + image::savePNG quantisation (apps/src/main.cpp:115-135,
+    apps/src/image.cpp:22-33): ``img.setPixel(width-1-x, y, pix / samples)``,
+    then ``(unsigned char)(glm::clamp(pix, 0, 1) * 255.f)`` per channel.
+    Returns (H, W, 3) uint8."""
+    v = np.asarray(image, np.float32).reshape(height, width, 3)
+    if divide:
+        v = (v / np.float32(samples)).astype(np.float32)
+    c = np.where(v < np.float32(0), np.float32(0), v)          # glm::max(x, 0) = (x < 0) ? 0 : x
+    c = np.where(np.float32(1) < c, np.float32(1), c)          # glm::min(x, 1) = (1 < x) ? 1 : x
+    c = (c * np.float32(255.0)).astype(np.float32)
+    c = np.where(np.isnan(c), np.float32(0), c)                # the reference's cast of NaN is undefined
+    out = c.astype(np.uint8)                                   # truncation, values already in [0, 255]
+    return out[:, ::-1, :].copy() if mirror_x else out
+
+
+def denoise_color(image: np.ndarray, iteration: int) -> np.ndarray:
+    """inputColor[index] = image[index] / (float)iteration (CPUdenoise, apps/src/main.cpp:194-199)."""
+    return (np.asarray(image, np.float32) / np.float32(iteration)).astype(np.float32)

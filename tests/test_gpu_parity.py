@@ -141,6 +141,49 @@ def test_multi_iteration_image_and_graph_replay(tmp_path):
             assert r.last_loop_ms() > 0.0
 
 
+@pytest.mark.parametrize("scene_kind", ["cornellGlass", "mesh"])
+def test_first_bounce_cache_changes_nothing(tmp_path, scene_kind):
+    """a18 (pathtrace.cu:586-610, intended semantics): with AA and DOF off the
+    depth-0 hits are computed once and reused; images, albedo, live counts and the
+    per-depth stage dumps stay bit-identical to the uncached run and to the
+    oracle, with and without the CUDA graph, and across a camera change."""
+    if scene_kind == "mesh":
+        pod = _mesh_scene(tmp_path, "cornellSpaceship", 96, 54, 1000)
+    else:
+        pod = api.Scene(scenes.write_scene("cornellGlass", str(tmp_path / "s.txt"), width=64, height=48)).pod
+    base = dict(trig_mode=abi.TRIG_PORTABLE, antialiasing=0)
+    ref, ref_alb, nlive, _ = oracle.render(pod, abi.default_options(**base), 1, 6, 1)
+    for graph in (1, 0):
+        with api.Renderer(pod, abi.default_options(cache_first_bounce=1, use_graph=graph, **base)) as r:
+            r.render(1, 1, 1)
+            launches_fill = r.launch_count()
+            r.render(2, 2, 1)
+            r.render(4, 3, 1)
+            img, alb = r.read()
+            assert_same_bits(img, ref, f"cached image (graph={graph})")
+            assert_same_bits(alb, ref_alb, "cached albedo")
+            assert list(r.live_counts()[: len(nlive)]) == list(nlive)
+            # iterations after the first skip the depth-0 intersect kernels
+            per_iter_cached = (r.launch_count() - launches_fill - 2) / 5.0
+            assert per_iter_cached < launches_fill - 1
+    # stage dumps of a cached iteration == oracle stages of that iteration
+    opt = abi.default_options(cache_first_bounce=1, record_stages=1, **base)
+    oimg = np.zeros((pod.n_pixels, 3), np.float32)
+    with api.Renderer(pod, opt) as r:
+        for it in (1, 2, 3):
+            r.render(it, 1, 1)
+            got = r.stages()
+            want = oracle.iteration_with_stages(pod, opt, it, oimg, None)
+            for d, (g, o) in enumerate(zip(got, want)):
+                for name in STAGES_TO_COMPARE:
+                    assert_same_bits(g[name], o[name], f"cached iter {it} depth {d} {name}")
+    # AA on: the option must be ignored (the reference compiles the cache out, pathtrace.cu:586)
+    ref_aa, *_ = oracle.render(pod, abi.default_options(trig_mode=abi.TRIG_PORTABLE), 1, 3, 1)
+    with api.Renderer(pod, abi.default_options(trig_mode=abi.TRIG_PORTABLE, cache_first_bounce=1)) as r:
+        r.render(1, 3, 1)
+        assert_same_bits(r.read()[0], ref_aa, "cache ignored with AA on")
+
+
 def test_strided_iterations_sum_to_the_sequential_image(tmp_path):
     """spp sharding: ranks rendering {1,3,5,..} and {2,4,6,..} add up to the
     sequential image within float summation order (1e-5 relative)."""
