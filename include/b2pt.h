@@ -195,7 +195,11 @@ int b2pt_sync(B2ptCtx* ctx);
 int b2pt_read_accum(B2ptCtx* ctx, float* image_host, float* albedo_host);
 
 /* Exactly one reference pathtrace(pbo, frame, iter) call: render `iter`, then
- * copy image and albedo to the host buffers (scene->state.image / .albedo). */
+ * copy image and albedo to the host buffers (scene->state.image / .albedo).
+ * The albedo AOV only changes on iteration 1 and on a reset, so the copy into
+ * `albedo_host` is skipped when the previous b2pt_pathtrace call already wrote
+ * the current albedo to the SAME pointer (the reference's state.albedo is one
+ * persistent vector); b2pt_read_accum always copies. */
 int b2pt_pathtrace(B2ptCtx* ctx, int32_t iter, float* image_host, float* albedo_host);
 
 /* Device pointers of the accumulators (W*H*3 floats), for zero-copy hand-off
@@ -255,11 +259,32 @@ int b2pt_resolve_color(B2ptCtx* ctx, int32_t iter, float* color_dev, float* colo
  * written (<= cap).  Synchronises. */
 int b2pt_live_counts(B2ptCtx* ctx, int32_t* n_live, int32_t cap);
 
+/* Mesh-walk queue lengths of the last rendered iteration: walks[d] = rays of
+ * depth d that had to walk a mesh BVH, long_walks[d] = (ray, mesh) walks handed
+ * to the warp-cooperative kernel (may be NULL).  Returns the depths written. */
+int b2pt_walk_counts(B2ptCtx* ctx, int32_t* walks, int32_t* long_walks, int32_t cap);
+
 /* Per-kernel device time of ONE iteration, measured with CUDA events around
  * every launch (no graph): ms[0] generate, ms[1] intersect (sum over depths),
  * ms[2] material sort, ms[3] shade+compact+gather, ms[4] whole iteration.
  * The iteration is rendered and accumulated like any other.  Synchronous. */
 int b2pt_profile_iteration(B2ptCtx* ctx, int32_t iter, float ms[5]);
+
+/* The same measurement per kernel: the intersect stage is four kernels
+ * (analytic geoms; per-lane BVH walk; warp-cooperative long walks; record
+ * finishing).  Sums over the depths of one iteration, milliseconds. */
+enum {
+  B2PT_PROF_GENERATE = 0,  /* k_generate                                      */
+  B2PT_PROF_ANALYTIC = 1,  /* k_intersect_analytic                            */
+  B2PT_PROF_WALK = 2,      /* k_mesh_walk                                     */
+  B2PT_PROF_WALK_LONG = 3, /* k_mesh_walk_long                                */
+  B2PT_PROF_FINISH = 4,    /* k_mesh_finish                                   */
+  B2PT_PROF_SORT = 5,      /* k_sort_material                                 */
+  B2PT_PROF_SHADE = 6,     /* k_shade_compact                                 */
+  B2PT_PROF_ITERATION = 7, /* the whole iteration                             */
+  B2PT_PROF_COUNT = 8
+};
+int b2pt_profile_kernels(B2ptCtx* ctx, int32_t iter, float ms[B2PT_PROF_COUNT]);
 
 /* Kernel launches issued by this context since creation. */
 int64_t b2pt_launch_count(B2ptCtx* ctx);

@@ -191,12 +191,14 @@ SYMBOLS = {
     "b2pt_stream": (_vp, [_vp]),
     "b2pt_set_stream": (C.c_int, [_vp, _vp]),
     "b2pt_profile_iteration": (C.c_int, [_vp, _i32, _f32p]),
+    "b2pt_profile_kernels": (C.c_int, [_vp, _i32, _f32p]),
     "b2pt_last_loop_ms": (C.c_float, [_vp]),
     "b2pt_tonemap_rgba8": (C.c_int, [_vp, _vp, _i32, _vp]),
     "b2pt_resolve_rgb8": (C.c_int, [_vp, _i32, _i32, _i32, _vp]),
     "b2pt_save_png": (C.c_int, [_vp, _i32, _i32, C.c_char_p]),
     "b2pt_resolve_color": (C.c_int, [_vp, _i32, _vp, _vp]),
     "b2pt_live_counts": (C.c_int, [_vp, _i32p, _i32]),
+    "b2pt_walk_counts": (C.c_int, [_vp, _i32p, _i32p, _i32]),
     "b2pt_launch_count": (_i64, [_vp]),
     "b2pt_stage_read": (_i64, [_vp, _i32, _i32, _vp, _i64]),
     "b2pt_bvh_info": (C.c_int, [_vp, _i32, C.POINTER(BvhInfo)]),

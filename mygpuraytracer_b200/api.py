@@ -213,6 +213,13 @@ class Renderer:
         k = _check(self.lib.b2pt_live_counts(self._h, buf.ctypes.data_as(C.POINTER(C.c_int32)), 64))
         return buf[:k].copy()
 
+    def walk_counts(self, long_walks: bool = False) -> np.ndarray:
+        """Per-depth mesh-walk queue lengths of the last iteration (or the long-walk hand-offs)."""
+        a, b = np.zeros(64, np.int32), np.zeros(64, np.int32)
+        k = _check(self.lib.b2pt_walk_counts(self._h, a.ctypes.data_as(C.POINTER(C.c_int32)),
+                                             b.ctypes.data_as(C.POINTER(C.c_int32)), 64))
+        return (b if long_walks else a)[:k].copy()
+
     def launch_count(self) -> int:
         return int(self.lib.b2pt_launch_count(self._h))
 
@@ -233,6 +240,13 @@ class Renderer:
         ms = (C.c_float * 5)()
         _check(self.lib.b2pt_profile_iteration(self._h, iteration, ms))
         return dict(zip(["generate", "intersect", "sort", "shade", "iteration"], [float(x) for x in ms]))
+
+    def profile_kernels(self, iteration: int) -> Dict[str, float]:
+        """Per-kernel device time of one iteration (b2pt_profile_kernels), ms."""
+        ms = (C.c_float * 8)()
+        _check(self.lib.b2pt_profile_kernels(self._h, iteration, ms))
+        names = ["generate", "analytic", "walk", "walk_long", "finish", "sort", "shade", "iteration"]
+        return dict(zip(names, [float(x) for x in ms]))
 
     def stream_ptr(self) -> int:
         return int(self.lib.b2pt_stream(self._h) or 0)

@@ -146,6 +146,10 @@ struct B2ptCtx {
   size_t l2_window_bytes = 0;
   // first-bounce cache (pathtrace.cu:586-610, intended semantics): with AA and DOF off the camera rays are the
   // same every iteration, so depth 0 keeps its own hit/key/live buffers, filled once and reused afterwards
+  // the albedo AOV only changes on iteration 1 (pathtrace.cu:412) and on a reset: b2pt_pathtrace skips the
+  // D2H copy into a host buffer that already holds the current version
+  uint64_t albedo_version = 1, albedo_host_version = 0;
+  const float* albedo_host_last = nullptr;
   bool fb_enabled = false, fb_valid = false;
   HitBuf fb_hits{};
   uint8_t *fb_key = nullptr, *fb_live = nullptr;
@@ -766,11 +770,14 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
     c->launches += 1;
     if (c->dscene.n_meshes > 0) {
       if (c->opt.use_bvh && !c->old_walk) {
+        if (kt) kt->mark(4);
         if (c->trav_stats)
           k_mesh_walk<true><<<c->walk_grid, kWalkThreads, 0, s>>>(ip);
         else
           k_mesh_walk<false><<<c->walk_grid, kWalkThreads, 0, s>>>(ip);
+        if (kt) kt->mark(5);
         k_mesh_walk_long<<<c->long_grid, kCoopThreads, 0, s>>>(ip);
+        if (kt) kt->mark(6);
         k_mesh_finish<<<c->finish_grid, 256, 0, s>>>(ip);
         c->launches += 3;
       } else {
@@ -864,9 +871,9 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
   return 0;
 }
 
-extern "C" int b2pt_profile_iteration(B2ptCtx* c, int32_t iter, float ms[5]) {
-  if (!c || !ms) return fail(B2PT_ERR_INVALID, "ctx and ms must not be NULL");
+static int profile_impl(B2ptCtx* c, int32_t iter, float* kinds, int n_kinds, float* total) {
   CK(cudaSetDevice(c->device));
+  if (iter <= 1) c->albedo_version += 1;
   k_set_iter<<<1, 1, 0, c->stream>>>(c->iter_state, iter, 1);
   c->launches += 1;
   KernelTimes kt;
@@ -879,18 +886,46 @@ extern "C" int b2pt_profile_iteration(B2ptCtx* c, int32_t iter, float ms[5]) {
     cudaError_t e = cudaStreamSynchronize(c->stream);
     if (e != cudaSuccess) rc = fail(B2PT_ERR_CUDA, cudaGetErrorString(e));
   }
-  for (int k = 0; k < 5; ++k) ms[k] = 0.0f;
+  for (int k = 0; k < n_kinds; ++k) kinds[k] = 0.0f;
+  *total = 0.0f;
   if (rc == 0) {
     for (size_t i = 0; i + 1 < kt.ev.size(); ++i) {
       float t = 0.0f;
       cudaEventElapsedTime(&t, kt.ev[i], kt.ev[i + 1]);
-      if (kt.kind[i] >= 0 && kt.kind[i] < 4) ms[kt.kind[i]] += t;
+      if (kt.kind[i] >= 0 && kt.kind[i] < n_kinds) kinds[kt.kind[i]] += t;
     }
-    cudaEventElapsedTime(&ms[4], e0, kt.ev.back());
+    cudaEventElapsedTime(total, e0, kt.ev.back());
   }
   for (cudaEvent_t e : kt.ev) cudaEventDestroy(e);
   cudaEventDestroy(e0);
   c->loop_timed = true;
+  return rc;
+}
+
+extern "C" int b2pt_profile_iteration(B2ptCtx* c, int32_t iter, float ms[5]) {
+  if (!c || !ms) return fail(B2PT_ERR_INVALID, "ctx and ms must not be NULL");
+  float k[7], total;
+  int rc = profile_impl(c, iter, k, 7, &total);
+  ms[0] = k[0];
+  ms[1] = k[1] + k[4] + k[5] + k[6];
+  ms[2] = k[2];
+  ms[3] = k[3];
+  ms[4] = total;
+  return rc;
+}
+
+extern "C" int b2pt_profile_kernels(B2ptCtx* c, int32_t iter, float ms[B2PT_PROF_COUNT]) {
+  if (!c || !ms) return fail(B2PT_ERR_INVALID, "ctx and ms must not be NULL");
+  float k[7], total;
+  int rc = profile_impl(c, iter, k, 7, &total);
+  ms[B2PT_PROF_GENERATE] = k[0];
+  ms[B2PT_PROF_ANALYTIC] = k[1];
+  ms[B2PT_PROF_WALK] = k[4];
+  ms[B2PT_PROF_WALK_LONG] = k[5];
+  ms[B2PT_PROF_FINISH] = k[6];
+  ms[B2PT_PROF_SORT] = k[2];
+  ms[B2PT_PROF_SHADE] = k[3];
+  ms[B2PT_PROF_ITERATION] = total;
   return rc;
 }
 
@@ -899,6 +934,7 @@ extern "C" int b2pt_render(B2ptCtx* c, int32_t iter_first, int32_t iter_count, i
   if (iter_count < 0 || iter_stride <= 0) return fail(B2PT_ERR_INVALID, "iter_count >= 0 and iter_stride > 0 required");
   if (iter_count == 0) return 0;
   CK(cudaSetDevice(c->device));
+  if (iter_first <= 1) c->albedo_version += 1;  // iteration 1 writes the albedo AOV
   k_set_iter<<<1, 1, 0, c->stream>>>(c->iter_state, iter_first, iter_stride);
   c->launches += 1;
   const bool record = c->opt.record_stages != 0;
@@ -958,7 +994,13 @@ extern "C" int b2pt_read_accum(B2ptCtx* c, float* image_host, float* albedo_host
 extern "C" int b2pt_pathtrace(B2ptCtx* c, int32_t iter, float* image_host, float* albedo_host) {
   int rc = b2pt_render(c, iter, 1, 1);
   if (rc) return rc;
-  return b2pt_read_accum(c, image_host, albedo_host);
+  const bool albedo_current = albedo_host && albedo_host == c->albedo_host_last && c->albedo_host_version == c->albedo_version;
+  rc = b2pt_read_accum(c, image_host, albedo_current ? nullptr : albedo_host);
+  if (rc == 0 && albedo_host) {
+    c->albedo_host_last = albedo_host;
+    c->albedo_host_version = c->albedo_version;
+  }
+  return rc;
 }
 
 extern "C" int b2pt_reset_accum(B2ptCtx* c) {
@@ -966,6 +1008,7 @@ extern "C" int b2pt_reset_accum(B2ptCtx* c) {
   CK(cudaSetDevice(c->device));
   CK(cudaMemsetAsync(c->image_target, 0, (size_t)c->P * 12, c->stream));
   CK(cudaMemsetAsync(c->albedo, 0, (size_t)c->P * 12, c->stream));
+  c->albedo_version += 1;
   return 0;
 }
 
@@ -1039,6 +1082,24 @@ extern "C" int b2pt_live_counts(B2ptCtx* c, int32_t* n_live, int32_t cap) {
   int k = 0;
   if (e == cudaSuccess)
     for (; k < cap && k <= c->loop_depth; ++k) n_live[k] = h->n_live[k];
+  free(h);
+  if (e != cudaSuccess) return fail(B2PT_ERR_CUDA, cudaGetErrorString(e));
+  return k;
+}
+
+extern "C" int b2pt_walk_counts(B2ptCtx* c, int32_t* walks, int32_t* long_walks, int32_t cap) {
+  if (!c || !walks) return fail(B2PT_ERR_INVALID, "ctx and walks must not be NULL");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  Counters* h = (Counters*)malloc(sizeof(Counters));
+  if (!h) return fail(B2PT_ERR_NOMEM, "out of host memory");
+  cudaError_t e = cudaMemcpy(h, c->ctr, sizeof(Counters), cudaMemcpyDeviceToHost);
+  int k = 0;
+  if (e == cudaSuccess)
+    for (; k < cap && k < c->loop_depth; ++k) {
+      walks[k] = (int32_t)h->mesh_count[k];
+      if (long_walks) long_walks[k] = (int32_t)h->long_count[k];
+    }
   free(h);
   if (e != cudaSuccess) return fail(B2PT_ERR_CUDA, cudaGetErrorString(e));
   return k;
