@@ -114,6 +114,7 @@ struct B2ptCtx {
   int W = 0, H = 0, P = 0, depth = 0, loop_depth = 0;
   int n_geoms = 0, n_materials = 0;
   int sm_count = 0;
+  float origin_world = 0.0f;  // rays start inside [-origin_world, origin_world]^3 (BVH padding, set_camera check)
 
   std::vector<void*> allocs;  // every cudaMalloc, freed in b2pt_destroy
   std::vector<MeshBuild> meshes;
@@ -141,7 +142,7 @@ struct B2ptCtx {
   int *rec_live = nullptr, *rec_dead = nullptr;
   std::vector<StageRecord> records;
 
-  unsigned long long* trav_stats = nullptr;  // [depth][24], B2PT_TRAVERSAL_STATS=1 only
+  unsigned long long* trav_stats = nullptr;  // [depth][32], B2PT_TRAVERSAL_STATS=1 only
   void* l2_window_ptr = nullptr;
   size_t l2_window_bytes = 0;
   // first-bounce cache (pathtrace.cu:586-610, intended semantics): with AA and DOF off the camera rays are the
@@ -154,9 +155,12 @@ struct B2ptCtx {
   HitBuf fb_hits{};
   uint8_t *fb_key = nullptr, *fb_live = nullptr;
   unsigned int* fb_hist = nullptr;  // [2][kMaxMaterials]: hist[0], hist_live[0] of the cached depth
-  int walk_grid = 0, finish_grid = 0, long_grid = 0, long_walk = 32;
+  int walk_grid = 0, finish_grid = 0, long_grid = 0, long_walk = 24;
   int2* long_queue = nullptr;
-  bool old_walk = false;
+  float4* long_best = nullptr;
+  int2* long_stack = nullptr;
+  int* long_n = nullptr;
+  int long_cap = 0;
   int isect_grid = 0, analytic_grid = 0, sort_grid = 0, shade_grid = 0, gen_grid = 0;
   int* mesh_queue = nullptr;
   cudaEvent_t ev_loop_a = nullptr, ev_loop_b = nullptr;
@@ -305,7 +309,7 @@ static int radix_sort_pairs_dev(uint32_t* key, uint32_t* val, int n, cudaStream_
 // ---------------------------------------------------------------------------------
 // LBVH build for one mesh
 // ---------------------------------------------------------------------------------
-static int build_mesh(B2ptCtx* c, const float* pos_host, const float* uv_host, int n, MeshBuild* out) {
+static int build_mesh(B2ptCtx* c, const float* pos_host, const float* uv_host, int n, float origin_radius, MeshBuild* out) {
   cudaStream_t s = c->stream;
   int rc;
   if ((rc = c->dalloc(&out->face_pos, (size_t)n * 9))) return rc;
@@ -330,7 +334,9 @@ static int build_mesh(B2ptCtx* c, const float* pos_host, const float* uv_host, i
     }
   float ext = 0.0f;
   for (int k = 0; k < 3; ++k) ext = std::max(ext, std::max(std::fabs(lo[k]), std::fabs(hi[k])));
-  const float pad = 4e-6f * std::max(ext, 1.0f);
+  // second term: the FMA slab test of k_walk.cuh displaces a plane by up to ~2^-23 * (largest coordinate of a
+  // ray origin in this mesh's object space); origin_radius bounds that coordinate
+  const float pad = 4e-6f * std::max(ext, 1.0f) + 9.5367431640625e-7f * origin_radius;
 
   TriBounds* bounds = nullptr;
   uint32_t *code = nullptr, *val = nullptr;
@@ -385,7 +391,7 @@ static int build_mesh(B2ptCtx* c, const float* pos_host, const float* uv_host, i
   cudaFree(children);
   cudaFree(parent);
   cudaFree(visit);
-  if (out->info.max_depth > kShortStack + kLocalStack)
+  if (out->info.max_depth > 2 * (kWalkShort + kWalkSpill) / 3)
     return fail(B2PT_ERR_RANGE, "LBVH deeper than the traversal stack");
   return 0;
 }
@@ -454,6 +460,29 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
   CK(cudaEventCreate(&c->ev_loop_b));
 
   int rc;
+  // ---- where rays can start: every geom's world box and the camera, with a 4x margin for camera moves ----
+  float origin_world = 0.0f;
+  for (int k = 0; k < 3; ++k) origin_world = std::max(origin_world, std::fabs(sc->camera.position[k]));
+  for (int g = 0; g < sc->n_geoms; ++g) {
+    const B2ptGeom& G = sc->geoms[g];
+    float lo[3] = {-0.5f, -0.5f, -0.5f}, hi[3] = {0.5f, 0.5f, 0.5f};
+    if (G.type == B2PT_OBJ && G.face_count > 0 && sc->face_pos && G.face_begin >= 0 &&
+        (long long)G.face_begin + G.face_count <= sc->n_faces) {
+      for (int k = 0; k < 3; ++k) { lo[k] = FLT_MAX; hi[k] = -FLT_MAX; }
+      const float* fp = sc->face_pos + (size_t)G.face_begin * 9;
+      for (size_t v = 0; v < (size_t)G.face_count * 3; ++v)
+        for (int k = 0; k < 3; ++k) {
+          lo[k] = std::min(lo[k], fp[v * 3 + k]);
+          hi[k] = std::max(hi[k], fp[v * 3 + k]);
+        }
+    }
+    DevGeom tmp;
+    world_box(G.transform, lo, hi, &tmp);
+    origin_world = std::max(origin_world, std::max({std::fabs(tmp.wmin.x), std::fabs(tmp.wmin.y), std::fabs(tmp.wmin.z),
+                                                     std::fabs(tmp.wmax.x), std::fabs(tmp.wmax.y), std::fabs(tmp.wmax.z)}));
+  }
+  origin_world *= 4.0f;
+  c->origin_world = origin_world;
   // ---- geoms, meshes, textures -----------------------------------------------------
   std::vector<DevGeom> hg(sc->n_geoms);
   std::vector<DevMesh> hm;
@@ -478,8 +507,16 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
       if (G.face_begin < 0 || (long long)G.face_begin + G.face_count > sc->n_faces || !sc->face_pos || !sc->face_uv)
         return fail(B2PT_ERR_INVALID, "geom face range out of bounds");
       MeshBuild mb;
+      float origin_radius = 0.0f;  // the cube [-origin_world, origin_world]^3 seen from object space
+      for (int cn = 0; cn < 8; ++cn) {
+        const float p[3] = {(cn & 1) ? origin_world : -origin_world, (cn & 2) ? origin_world : -origin_world,
+                            (cn & 4) ? origin_world : -origin_world};
+        const float* m = G.inverse_transform;
+        for (int r = 0; r < 3; ++r)
+          origin_radius = std::max(origin_radius, std::fabs(m[r] * p[0] + m[4 + r] * p[1] + m[8 + r] * p[2] + m[12 + r]));
+      }
       if ((rc = build_mesh(c, sc->face_pos + (size_t)G.face_begin * 9, sc->face_uv + (size_t)G.face_begin * 6,
-                           G.face_count, &mb)))
+                           G.face_count, origin_radius, &mb)))
         return rc;
       {
         float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
@@ -555,7 +592,11 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
   if ((rc = c->dalloc(&c->live, P))) return rc;
   if ((rc = c->dalloc(&c->apos, P))) return rc;
   if ((rc = c->dalloc(&c->mesh_queue, P))) return rc;
-  if ((rc = c->dalloc(&c->long_queue, P * (size_t)std::max(1, (int)hm.size())))) return rc;
+  c->long_cap = (int)std::max<size_t>(P / 4, 4096);
+  if ((rc = c->dalloc(&c->long_queue, (size_t)c->long_cap))) return rc;
+  if ((rc = c->dalloc(&c->long_best, (size_t)c->long_cap))) return rc;
+  if ((rc = c->dalloc(&c->long_stack, (size_t)c->long_cap * kLongCarry))) return rc;
+  if ((rc = c->dalloc(&c->long_n, (size_t)c->long_cap))) return rc;
   if ((rc = c->dalloc(&c->ctr, 1))) return rc;
   if ((rc = c->dalloc(&c->iter_state, 4))) return rc;
   c->sort_grid = (int)((P + kSortTile - 1) / kSortTile);
@@ -591,22 +632,19 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
   }
 
   if (getenv("B2PT_TRAVERSAL_STATS")) {
-    if ((rc = c->dalloc(&c->trav_stats, (size_t)24 * (kMaxDepth + 1)))) return rc;
-    CK(cudaMemsetAsync(c->trav_stats, 0, sizeof(unsigned long long) * 24 * (kMaxDepth + 1), c->stream));
+    if ((rc = c->dalloc(&c->trav_stats, (size_t)32 * (kMaxDepth + 1)))) return rc;
+    CK(cudaMemsetAsync(c->trav_stats, 0, sizeof(unsigned long long) * 32 * (kMaxDepth + 1), c->stream));
   }
   // persistent grid of the intersect kernel: SMs x resident CTAs
   int occ = 0;
-  if (opt.use_bvh)
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_intersect_mesh<true>, kIsectThreads, 0));
-  else
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_intersect_mesh<false>, kIsectThreads, 0));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_intersect_mesh_brute, kIsectThreads, 0));
   c->isect_grid = c->sm_count * std::max(occ, 1);
-  c->old_walk = getenv("B2PT_OLD_WALK") != nullptr;
   if (c->trav_stats)
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mesh_walk<true>, kWalkThreads, 0));
   else
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mesh_walk<false>, kWalkThreads, 0));
   c->walk_grid = c->sm_count * std::max(occ, 1);
+  if (const char* e = getenv("B2PT_WALK_CTAS")) c->walk_grid = c->sm_count * std::max(1, std::min(atoi(e), std::max(occ, 1)));
   c->finish_grid = c->sm_count * 8;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mesh_walk_long, kCoopThreads, 0));
   c->long_grid = c->sm_count * std::max(occ, 1);
@@ -629,15 +667,20 @@ extern "C" void b2pt_destroy(B2ptCtx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   if (c->trav_stats) {
-    std::vector<unsigned long long> h((size_t)24 * (kMaxDepth + 1));
+    std::vector<unsigned long long> h((size_t)32 * (kMaxDepth + 1));
     cudaMemcpy(h.data(), c->trav_stats, h.size() * 8, cudaMemcpyDeviceToHost);
     for (int d = 0; d < c->loop_depth; ++d) {
-      const unsigned long long* s = &h[(size_t)24 * d];
+      const unsigned long long* s = &h[(size_t)32 * d];
       if (!s[0]) continue;
       fprintf(stderr, "[b2pt traversal] depth %d: %llu walks, nodes/walk %.1f (max %llu), tris/walk %.1f (max %llu), log2 hist:",
               d, s[0], (double)s[1] / s[0], s[3], (double)s[2] / s[0], s[4]);
       for (int k = 0; k < 16; ++k) fprintf(stderr, " %llu", s[5 + k]);
       fprintf(stderr, "\n");
+      if (s[21])
+        fprintf(stderr, "[b2pt traversal]   per warp: %llu warps, loop iterations avg %.1f max %llu, cycles avg %.0f max %llu, "
+                        "refills avg %.1f (%.0f cycles each), prologue %.0f cycles, lanes per node step %.1f\n",
+                s[21], (double)s[22] / s[21], s[23], (double)s[24] / s[21], s[25], (double)s[26] / s[21],
+                s[26] ? (double)s[27] / s[26] : 0.0, (double)s[28] / s[21], s[30] ? (double)s[29] / s[30] : 0.0);
     }
   }
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
@@ -757,11 +800,15 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
     ip.live = live_d;
     ip.ctr = c->ctr;
     ip.depth = d;
-    ip.stats = c->trav_stats ? c->trav_stats + 24 * d : nullptr;
+    ip.stats = c->trav_stats ? c->trav_stats + 32 * d : nullptr;
     if (kt) kt->mark(1);
     ip.queue = c->mesh_queue;
     ip.long_queue = c->long_queue;
     ip.long_walk = c->long_walk;
+    ip.long_cap = c->long_cap;
+    ip.long_best = c->long_best;
+    ip.long_stack = c->long_stack;
+    ip.long_n = c->long_n;
     if (fb && c->fb_valid) {
       k_first_bounce_hist<<<1, 256, 0, s>>>(c->ctr, c->fb_hist, c->P, 1);
       c->launches += 1;
@@ -769,7 +816,7 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
     k_intersect_analytic<<<c->analytic_grid, 256, 0, s>>>(ip);
     c->launches += 1;
     if (c->dscene.n_meshes > 0) {
-      if (c->opt.use_bvh && !c->old_walk) {
+      if (c->opt.use_bvh) {
         if (kt) kt->mark(4);
         if (c->trav_stats)
           k_mesh_walk<true><<<c->walk_grid, kWalkThreads, 0, s>>>(ip);
@@ -781,10 +828,7 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
         k_mesh_finish<<<c->finish_grid, 256, 0, s>>>(ip);
         c->launches += 3;
       } else {
-        if (c->opt.use_bvh)
-          k_intersect_mesh<true><<<c->isect_grid, kIsectThreads, 0, s>>>(ip);
-        else
-          k_intersect_mesh<false><<<c->isect_grid, kIsectThreads, 0, s>>>(ip);
+        k_intersect_mesh_brute<<<c->isect_grid, kIsectThreads, 0, s>>>(ip);
         c->launches += 1;
       }
     }
@@ -1016,6 +1060,9 @@ extern "C" int b2pt_set_camera(B2ptCtx* c, const B2ptCamera* cam) {
   if (!c || !cam) return fail(B2PT_ERR_INVALID, "ctx and cam must not be NULL");
   if (cam->resolution[0] != c->W || cam->resolution[1] != c->H)
     return fail(B2PT_ERR_INVALID, "the resolution of a context cannot change");
+  for (int k = 0; k < 3; ++k)
+    if (!(std::fabs(cam->position[k]) <= c->origin_world))
+      return fail(B2PT_ERR_RANGE, "camera position is outside the region the BVH boxes were padded for; create a new context");
   CK(cudaSetDevice(c->device));
   CK(cudaStreamSynchronize(c->stream));
   c->gen.cam = to_dev_camera(*cam);

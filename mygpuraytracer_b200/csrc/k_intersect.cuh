@@ -28,8 +28,6 @@
 namespace b2pt {
 
 constexpr int kIsectThreads = 256;
-constexpr int kShortStack = 12;   // entries per thread in shared memory
-constexpr int kLocalStack = 52;   // spill entries per thread (LBVH depth <= 64)
 
 struct IsectParams {
   DevScene scene;
@@ -42,21 +40,11 @@ struct IsectParams {
   int* queue;                 // rays that must walk a mesh (filled by k_intersect_analytic)
   int2* long_queue;           // (ray, geom) walks that outgrew one lane (filled by k_mesh_walk)
   int long_walk;              // steps after which k_mesh_walk hands a walk to k_mesh_walk_long
+  int long_cap;               // capacity of the hand-off queue
+  float4* long_best;          // [long_cap] (t, bu, bv, face) of the closest triangle found so far
+  int2* long_stack;           // [long_cap][kLongCarry] carried traversal stack
+  int* long_n;                // [long_cap] carried entries, -1: restart at the root
   unsigned long long* stats;  // optional traversal statistics (B2PT_TRAVERSAL_STATS=1), else NULL
-};
-
-struct StackRef {
-  int* sm;     // shared-memory base for this thread (stride = blockDim)
-  int* local;  // local-memory spill
-  int sp;
-  __device__ __forceinline__ void push(int v) {
-    if (sp < kShortStack) sm[sp * kIsectThreads] = v; else local[sp - kShortStack] = v;
-    ++sp;
-  }
-  __device__ __forceinline__ int pop() {
-    --sp;
-    return sp < kShortStack ? sm[sp * kIsectThreads] : local[sp - kShortStack];
-  }
 };
 
 // Conservative ray/box slab test; NaNs (0 * inf) are dropped by fminf/fmaxf.
@@ -92,90 +80,6 @@ __device__ __forceinline__ float tri_exact(V3 qo, V3 qd, V3 v0, V3 v1, V3 v2, fl
   *bu = u;
   *bv = v;
   return length(qo - pt);
-}
-
-// Walk the 4-wide LBVH of one mesh (k_emit_wide4).  t_limit bounds the search
-// (FLT_MAX, or the closest analytic hit so far when the geom is rigid).
-// Returns the object-space distance of the closest triangle, or -1.
-__device__ __forceinline__ float mesh_traverse(const DevMesh& m, V3 qo, V3 qd, float t_limit, int* face, float* bu,
-                                               float* bv, StackRef st, unsigned long long* stats = nullptr) {
-  unsigned int n_nodes = 0, n_tris = 0;
-  const V3 id = mk(1.0f / qd.x, 1.0f / qd.y, 1.0f / qd.z);
-  float tbest = t_limit;
-  float lim = t_limit >= FLT_MAX ? FLT_MAX : t_limit * 1.00001f + 1e-6f;
-  int best = -1;
-  int node = m.root;
-  st.sp = 0;
-  while (true) {
-    if (node >= 0) {
-      ++n_nodes;
-      const float4* n = m.nodes + 8 * (size_t)node;
-      const float4 lx = __ldg(n), ly = __ldg(n + 1), lz = __ldg(n + 2);
-      const float4 hx = __ldg(n + 3), hy = __ldg(n + 4), hz = __ldg(n + 5);
-      const float4 cf = __ldg(n + 6);
-      float tn[4];
-      int ch[4] = {__float_as_int(cf.x), __float_as_int(cf.y), __float_as_int(cf.z), __float_as_int(cf.w)};
-      {
-        float tf;
-        slab(lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, qo, id, &tn[0], &tf);
-        if (!(tn[0] <= tf && tf >= 0.0f && tn[0] <= lim)) ch[0] = kEmptyChild;
-        slab(lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, qo, id, &tn[1], &tf);
-        if (!(tn[1] <= tf && tf >= 0.0f && tn[1] <= lim)) ch[1] = kEmptyChild;
-        slab(lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, qo, id, &tn[2], &tf);
-        if (!(tn[2] <= tf && tf >= 0.0f && tn[2] <= lim)) ch[2] = kEmptyChild;
-        slab(lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, qo, id, &tn[3], &tf);
-        if (!(tn[3] <= tf && tf >= 0.0f && tn[3] <= lim)) ch[3] = kEmptyChild;
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (ch[k] == kEmptyChild) tn[k] = FLT_MAX;
-      // sort the (up to four) hits by entry distance: 5-comparator network
-#define B2PT_CSWAP(a, b)                                   \
-  if (tn[b] < tn[a]) {                                     \
-    const float tt = tn[a]; tn[a] = tn[b]; tn[b] = tt;     \
-    const int cc = ch[a]; ch[a] = ch[b]; ch[b] = cc;       \
-  }
-      B2PT_CSWAP(0, 1) B2PT_CSWAP(2, 3) B2PT_CSWAP(0, 2) B2PT_CSWAP(1, 3) B2PT_CSWAP(1, 2)
-#undef B2PT_CSWAP
-      if (ch[0] != kEmptyChild) {
-        // nearest first; the others go on the stack farthest first
-        if (ch[3] != kEmptyChild) st.push(ch[3]);
-        if (ch[2] != kEmptyChild) st.push(ch[2]);
-        if (ch[1] != kEmptyChild) st.push(ch[1]);
-        node = ch[0];
-        continue;
-      }
-    } else {
-      ++n_tris;
-      const int slot = ~node;
-      const float4* tp = m.tris + 3 * (size_t)slot;
-      const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-      float u, v;
-      const float t = tri_exact(qo, qd, mk(a.x, a.y, a.z), mk(b.x, b.y, b.z), mk(c.x, c.y, c.z), &u, &v);
-      if (t >= 0.0f) {
-        const int fid = __float_as_int(a.w);
-        if (t < tbest || (t == tbest && fid < best)) {
-          tbest = t;
-          best = fid;
-          *bu = u;
-          *bv = v;
-          lim = t * 1.00001f + 1e-6f;
-        }
-      }
-    }
-    if (st.sp == 0) break;
-    node = st.pop();
-  }
-  if (stats) {
-    atomicAdd(&stats[0], 1ull);
-    atomicAdd(&stats[1], (unsigned long long)n_nodes);
-    atomicAdd(&stats[2], (unsigned long long)n_tris);
-    atomicMax(&stats[3], (unsigned long long)n_nodes);
-    atomicMax(&stats[4], (unsigned long long)n_tris);
-    atomicAdd(&stats[5 + min(15u, 31u - __clz(n_nodes | 1u))], 1ull);  // log2 histogram of node visits
-  }
-  *face = best;
-  return best >= 0 ? tbest : -1.0f;
 }
 
 // The reference's loop over every face, in face order (intersections.h:216-230).
@@ -449,17 +353,13 @@ __global__ void __launch_bounds__(256) k_intersect_analytic(IsectParams p) {
   if (blockIdx.x == 0 && tid == 0) atomicAdd(&p.ctr->segments, (unsigned long long)n);
 }
 
-// Persistent warps take 32 queued rays at a time; every lane walks the 4-wide
-// LBVH for its own ray in one tight loop.  (A variant that refilled finished
-// lanes from the queue and finished long walks cooperatively kept more lanes
-// busy but executed so many more instructions per step that it was 20 % slower;
-// see profiles/r01_notes.md.)
-template <bool USE_BVH>
-__global__ void __launch_bounds__(kIsectThreads, 3) k_intersect_mesh(IsectParams p) {
+// Validation path (use_bvh = 0): the reference's brute-force loop over every face
+// (intersections.h:216-230) for the queued rays, 32 at a time per persistent warp.
+// The product path is k_walk.cuh.
+__global__ void __launch_bounds__(kIsectThreads, 3) k_intersect_mesh_brute(IsectParams p) {
   __shared__ DevGeom sgeom[kMaxGeoms];
   __shared__ int shist[kMaxMaterials];
   __shared__ int slive[kMaxMaterials];
-  __shared__ int sstack[USE_BVH ? kShortStack * kIsectThreads : 1];
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int n_geoms = p.scene.n_geoms;
@@ -477,7 +377,6 @@ __global__ void __launch_bounds__(kIsectThreads, 3) k_intersect_mesh(IsectParams
   }
   __syncthreads();
   unsigned int* head = &p.ctr->ray_ticket[p.depth];
-  int local_stack[USE_BVH ? kLocalStack : 1];
   while (true) {
     unsigned int qb = 0;
     if (lane == 0) qb = atomicAdd(head, 32u);
@@ -505,16 +404,7 @@ __global__ void __launch_bounds__(kIsectThreads, 3) k_intersect_mesh(IsectParams
         const V3 qd = normalize(xform(G.inv, d, 0.0f));
         float bu = 0, bv = 0, t;
         int tface = -1;
-        if (USE_BVH) {
-          StackRef st;
-          st.sm = sstack + tid;
-          st.local = local_stack;
-          st.sp = 0;
-          const float lim = (G.rigid && t_min < FLT_MAX) ? t_min * 1.0001f + 1e-5f : FLT_MAX;
-          t = mesh_traverse(M, qo, qd, lim, &tface, &bu, &bv, st, p.stats);
-        } else {
-          t = mesh_brute(M, qo, qd, &tface, &bu, &bv);
-        }
+        t = mesh_brute(M, qo, qd, &tface, &bu, &bv);
         if (t > 0.0f && (t < t_min || (t == t_min && g < hit))) {
           t_min = t; hit = g; mhit = g; mface = tface; mbu = bu; mbv = bv;
         }

@@ -216,8 +216,10 @@ __global__ void __launch_bounds__(256) k_node_depth(int n, const int* __restrict
 // whose children are its grandchildren (or a child that is a leaf), so a walk
 // makes half as many dependent memory round trips.  One wide node is exactly
 // one 128-byte line, boxes stored per axis for the four slots:
-//   f0 = min.x[0..3]  f1 = min.y  f2 = min.z  f3 = max.x  f4 = max.y  f5 = max.z
+//   f0 = min.x[0..3]  f1 = max.x   f2 = min.y  f3 = max.y   f4 = min.z  f5 = max.z
 //   f6 = child ids as int bits (>= 0: wide node, < 0: ~leaf slot, kEmptyChild: unused)   f7 = pad
+// (both planes of an axis sit in one aligned 32-byte half-sector: the walk picks the plane a ray enters
+// through with a 16-byte address offset, or fetches the pair with one 256-bit load)
 // Wide nodes keep the index of the binary node they come from.
 constexpr int kEmptyChild = 0x40000000;
 
@@ -253,8 +255,8 @@ __global__ void __launch_bounds__(256) k_emit_wide4(int n, const int2* __restric
   }
   float4* o = nodes + 8 * (size_t)i;
   for (int a = 0; a < 3; ++a) {
-    o[a] = make_float4(lo[a][0], lo[a][1], lo[a][2], lo[a][3]);
-    o[3 + a] = make_float4(hi[a][0], hi[a][1], hi[a][2], hi[a][3]);
+    o[2 * a] = make_float4(lo[a][0], lo[a][1], lo[a][2], lo[a][3]);
+    o[2 * a + 1] = make_float4(hi[a][0], hi[a][1], hi[a][2], hi[a][3]);
   }
   o[6] = make_float4(__int_as_float(id[0]), __int_as_float(id[1]), __int_as_float(id[2]), __int_as_float(id[3]));
   o[7] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);

@@ -44,7 +44,7 @@ struct MaterialSortPolicy {
     return ctr->serial * (unsigned int)(kMaxDepth + 1) + (unsigned int)depth + 1u;
   }
   // ascending digit == descending material
-  __device__ __forceinline__ unsigned int digit(int idx) const { return 255u - (unsigned int)key[idx]; }
+  __device__ __forceinline__ unsigned int digit(int idx) const { return 255u - (unsigned int)__ldg(key + idx); }
   __device__ __forceinline__ unsigned int bin_total(int bin) const { return ctr->hist[depth][255 - bin]; }
   __device__ __forceinline__ void scatter(int idx, unsigned int pos) const { perm[pos] = idx; }
   static constexpr bool kFewBins = true;  // a handful of materials: one warp looks back per bin
@@ -66,7 +66,7 @@ struct RadixPassPolicy {
   __device__ __forceinline__ unsigned int* ticket() const { return ticket_; }
   __device__ __forceinline__ unsigned long long* status() const { return status_; }
   __device__ __forceinline__ unsigned int epoch() const { return epoch_; }
-  __device__ __forceinline__ unsigned int digit(int idx) const { return (key_in[idx] >> shift) & 255u; }
+  __device__ __forceinline__ unsigned int digit(int idx) const { return (__ldg(key_in + idx) >> shift) & 255u; }
   __device__ __forceinline__ unsigned int bin_total(int bin) const { return hist[bin]; }
   __device__ __forceinline__ void scatter(int idx, unsigned int pos) const {
     key_out[pos] = key_in[idx];
@@ -96,11 +96,18 @@ __global__ void __launch_bounds__(kSortThreads) k_onesweep_pass(Policy p) {
   const int wbase = (int)tile * kSortTile + warp * (kSortRows * 32);
   unsigned short lrank[kSortRows];
   unsigned short ldig[kSortRows];
+  // every key of the tile is loaded before the ranking chain starts (see k_sort_material)
+  unsigned short draw[kSortRows];
+#pragma unroll
+  for (int r = 0; r < kSortRows; ++r) {
+    const int idx = wbase + r * 32 + lane;
+    draw[r] = idx < n ? (unsigned short)p.digit(idx) : (unsigned short)0;
+  }
 #pragma unroll
   for (int r = 0; r < kSortRows; ++r) {
     const int idx = wbase + r * 32 + lane;
     const bool valid = idx < n;
-    const unsigned int dig = valid ? p.digit(idx) : 256u + (unsigned int)lane;  // invalid lanes match nobody
+    const unsigned int dig = valid ? (unsigned int)draw[r] : 256u + (unsigned int)lane;  // invalid lanes match nobody
     const unsigned int peers = __match_any_sync(0xffffffffu, dig);
     unsigned int before = 0;
     if (valid) before = wcnt[warp][dig];
@@ -244,12 +251,21 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_material(MatSortParams p)
 
   const int wbase = (int)tile * kSortTile + warp * (kSortRows * 32);
   unsigned short lrank[kSortRows], larank[kSortRows], ldig[kSortRows];
+  // all 2 x 16 loads of the tile are issued before the first rank is computed: the ranking loop below is a chain
+  // of warp barriers, and a load inside it would add one memory round trip per row
+  unsigned char kraw[kSortRows], lraw[kSortRows];
+#pragma unroll
+  for (int r = 0; r < kSortRows; ++r) {
+    const int idx = wbase + r * 32 + lane;
+    kraw[r] = idx < n ? __ldg(p.key + idx) : (unsigned char)0;
+    lraw[r] = idx < n ? __ldg(p.live + idx) : (unsigned char)0;
+  }
 #pragma unroll
   for (int r = 0; r < kSortRows; ++r) {
     const int idx = wbase + r * 32 + lane;
     const bool valid = idx < n;
-    const unsigned int dig = valid ? 255u - (unsigned int)p.key[idx] : 256u + (unsigned int)lane;
-    const bool alive = valid && p.live[idx] != 0;
+    const unsigned int dig = valid ? 255u - (unsigned int)kraw[r] : 256u + (unsigned int)lane;
+    const bool alive = valid && lraw[r] != 0;
     const unsigned int peers = __match_any_sync(0xffffffffu, dig);
     const unsigned int lpeers = peers & __ballot_sync(0xffffffffu, alive);
     unsigned int before = 0, lbefore = 0;

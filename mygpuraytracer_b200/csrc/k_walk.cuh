@@ -45,8 +45,87 @@ constexpr int kWalkThreads = B2PT_WALK_THREADS;
 constexpr int kWalkShort = 8;    // (node, tn) entries per lane in shared memory
 constexpr int kWalkSpill = 88;   // spill entries per lane: 96 in all = 3 per level of a 32-level wide tree
 constexpr int kRefillMin = B2PT_REFILL_MIN;    // idle lanes that trigger a refill
+constexpr int kLongCarry = 32;  // stack entries a long walk carries over to k_mesh_walk_long
 constexpr int kWalkDone = 0x7fffffff;
 constexpr int kNoGeom = 0x7fffffff;
+
+
+#ifndef B2PT_NODE_LOAD256
+#define B2PT_NODE_LOAD256 0
+#endif
+
+// Box test of the four children of a wide node with one FMA per plane.
+// The ray keeps id = 1/d and noid = -(o * id).  A node stores, per axis, the four
+// children's min planes and max planes in one aligned 32-byte pair (k_lbvh.cuh).
+// Per axis the plane the ray enters through ("near") is the min plane when
+// d >= 0 and the max plane otherwise, so the walk fetches near and far planes
+// through three per-ray byte offsets (offx/offy/offz: near; far = off ^ 16) and
+// needs no min/max between the two planes of an axis:
+//     tn = max(near.x*id.x + noid.x, near.y*.., near.z*.., 0)
+//     tf = min(far.x*id.x + noid.x,  far.y*..,  far.z*..,  lim)
+// (B2PT_NODE_LOAD256: three 256-bit loads fetch the pairs and min/max orders them.)
+// Rounding: o*id is rounded once and the FMA once, which displaces each plane by
+// at most ~2^-23 * max(|o|, |plane|) in position space whatever the size of id;
+// the build pads every box by 2^-20 * (largest coordinate a ray origin can have
+// in object space) on top of the extent term, so the test stays conservative.
+// NaNs (0 * inf, inf - inf for rays parallel to an axis) are dropped by
+// fminf / fmaxf: that axis then does not constrain the box.
+struct WideHit {
+  float tn[4];
+  bool ok[4];
+};
+__device__ __forceinline__ void ldg256(const void* p, float4* a, float4* b) {
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(a->x), "=f"(a->y), "=f"(a->z), "=f"(a->w), "=f"(b->x), "=f"(b->y), "=f"(b->z), "=f"(b->w)
+               : "l"(p));
+}
+__device__ __forceinline__ void wide_slab_fma(const float4* node, int offx, int offy, int offz, V3 id, V3 noid, float lim,
+                                              WideHit* h, float4* cf) {
+#if B2PT_NODE_LOAD256
+  float4 ax, bx, ay, by, az, bz;
+  ldg256(node, &ax, &bx);
+  ldg256(node + 2, &ay, &by);
+  ldg256(node + 4, &az, &bz);
+  *cf = __ldg(node + 6);
+#define B2PT_ONE(k, c)                                                                                         \
+  {                                                                                                            \
+    const float x0 = fmaf(ax.c, id.x, noid.x), x1 = fmaf(bx.c, id.x, noid.x);                                  \
+    const float y0 = fmaf(ay.c, id.y, noid.y), y1 = fmaf(by.c, id.y, noid.y);                                  \
+    const float z0 = fmaf(az.c, id.z, noid.z), z1 = fmaf(bz.c, id.z, noid.z);                                  \
+    const float a = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));                    \
+    const float b = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), lim));                     \
+    h->tn[k] = a;                                                                                              \
+    h->ok[k] = a <= b;                                                                                         \
+  }
+  B2PT_ONE(0, x) B2PT_ONE(1, y) B2PT_ONE(2, z) B2PT_ONE(3, w)
+#undef B2PT_ONE
+#else
+  const char* nb = reinterpret_cast<const char*>(node);
+  const float4 nx = __ldg(reinterpret_cast<const float4*>(nb + offx));
+  const float4 fx = __ldg(reinterpret_cast<const float4*>(nb + (offx ^ 16)));
+  const float4 ny = __ldg(reinterpret_cast<const float4*>(nb + offy));
+  const float4 fy = __ldg(reinterpret_cast<const float4*>(nb + (offy ^ 16)));
+  const float4 nz = __ldg(reinterpret_cast<const float4*>(nb + offz));
+  const float4 fz = __ldg(reinterpret_cast<const float4*>(nb + (offz ^ 16)));
+  *cf = __ldg(node + 6);
+#define B2PT_ONE(k, c)                                                                                         \
+  {                                                                                                            \
+    const float a = fmaxf(fmaxf(fmaf(nx.c, id.x, noid.x), fmaf(ny.c, id.y, noid.y)),                           \
+                          fmaxf(fmaf(nz.c, id.z, noid.z), 0.0f));                                              \
+    const float b = fminf(fminf(fmaf(fx.c, id.x, noid.x), fmaf(fy.c, id.y, noid.y)),                           \
+                          fminf(fmaf(fz.c, id.z, noid.z), lim));                                               \
+    h->tn[k] = a;                                                                                              \
+    h->ok[k] = a <= b;                                                                                         \
+  }
+  B2PT_ONE(0, x) B2PT_ONE(1, y) B2PT_ONE(2, z) B2PT_ONE(3, w)
+#undef B2PT_ONE
+#endif
+}
+__device__ __forceinline__ void slab_offsets(V3 id, int* offx, int* offy, int* offz) {
+  *offx = id.x >= 0.0f ? 0 : 16;
+  *offy = id.y >= 0.0f ? 32 : 48;
+  *offz = id.z >= 0.0f ? 64 : 80;
+}
 
 __device__ __forceinline__ bool walk_is_inner(int node) { return (unsigned int)node < 0x40000000u; }
 
@@ -61,6 +140,12 @@ __global__ void __launch_bounds__(kWalkThreads, B2PT_WALK_MINBLOCKS) k_mesh_walk
   const int n_geoms = p.scene.n_geoms;
   const unsigned int total = p.ctr->mesh_count[p.depth];
   if (total == 0) return;
+  const long long clk_start = STATS ? clock64() : 0;
+  long long clk_loop = 0, clk_refill = 0;
+  unsigned int w_iters = 0, w_refills = 0, w_node_iters = 0, w_node_lanes = 0;
+  unsigned int a_walks = 0, a_nodes = 0, a_tris = 0, a_maxn = 0, a_maxt = 0;
+  __shared__ unsigned long long sstat[32];  // per-CTA copy of p.stats, flushed once
+  if (STATS && tid < 32) sstat[tid] = 0ull;
   {
     const float4* src = reinterpret_cast<const float4*>(p.scene.geoms);
     float4* dst = reinterpret_cast<float4*>(sgeom);
@@ -84,6 +169,8 @@ __global__ void __launch_bounds__(kWalkThreads, B2PT_WALK_MINBLOCKS) k_mesh_walk
   const float4* nodes = nullptr;
   const float4* tris = nullptr;
   V3 qo = mk(0, 0, 0), qd = mk(0, 0, 1), id = mk(0, 0, 1);
+  V3 noid = mk(0, 0, 0);
+  int offx = 0, offy = 32, offz = 64;
   float tbest = 0.0f, lim = 0.0f, bu = 0.0f, bv = 0.0f;
   int best = -1;
   float t_min = FLT_MAX;  // closest hit so far over all geoms (analytic + meshes already walked)
@@ -91,6 +178,8 @@ __global__ void __launch_bounds__(kWalkThreads, B2PT_WALK_MINBLOCKS) k_mesh_walk
   unsigned int n_nodes = 0, n_tris = 0;
   int steps = 0;
   bool exhausted = false;
+  bool first_fetch = true;
+  const unsigned int static_part = gridDim.x * (kWalkThreads / 32) * 32u;
   const int long_walk = p.long_walk;
 
 #define B2PT_WALK_PUSH(c, t)                                                            \
@@ -100,13 +189,7 @@ __global__ void __launch_bounds__(kWalkThreads, B2PT_WALK_MINBLOCKS) k_mesh_walk
     else if (sp < kWalkShort + kWalkSpill) spill[sp - kWalkShort] = e;                  \
     ++sp;                                                                               \
   }
-// A walk that outgrew its lane is handed, whole, to k_mesh_walk_long (one warp per ray).
-#define B2PT_WALK_STEP_DONE()                                                           \
-  if (++steps > long_walk && node != kWalkDone) {                                       \
-    p.long_queue[atomicAdd(&p.ctr->long_count[p.depth], 1u)] = make_int2(ray, g);       \
-    node = kWalkDone;                                                                   \
-    best = -1;                                                                          \
-  }
+// Next thing to do: entries that fell behind the closest hit are dropped without touching memory.
 #define B2PT_WALK_POP_NEXT()                                                            \
   {                                                                                     \
     node = kWalkDone;                                                                   \
@@ -134,35 +217,46 @@ __global__ void __launch_bounds__(kWalkThreads, B2PT_WALK_MINBLOCKS) k_mesh_walk
       qo = xform(G.inv, o, 1.0f);
       qd = normalize(xform(G.inv, d, 0.0f));
       id = mk(1.0f / qd.x, 1.0f / qd.y, 1.0f / qd.z);
+      noid = mk(-(qo.x * id.x), -(qo.y * id.y), -(qo.z * id.z));
+      slab_offsets(id, &offx, &offy, &offz);
       const float t_limit = (G.rigid && t_min < FLT_MAX) ? t_min * 1.0001f + 1e-5f : FLT_MAX;
       tbest = t_limit;
       lim = t_limit >= FLT_MAX ? FLT_MAX : t_limit * 1.00001f + 1e-6f;
       best = -1;
       sp = 0;
       steps = 0;
-      node = M.root;
+      node = M.root;  // < 0: a mesh of one triangle
       g = gg;
       return true;
     }
     return false;
   };
 
+  if (STATS) clk_loop = clock64();
   while (true) {
-    const bool is_node = walk_is_inner(node);
-    const bool is_leaf = node < 0;
-    const unsigned int nm = __ballot_sync(0xffffffffu, is_node);
-    const unsigned int lm = __ballot_sync(0xffffffffu, is_leaf);
+    const bool can_node = walk_is_inner(node);
+    const bool has_leaf = node < 0;
+    const unsigned int nm = __ballot_sync(0xffffffffu, can_node);
+    const unsigned int lm = __ballot_sync(0xffffffffu, has_leaf);
     const unsigned int busy = nm | lm;
+    if (STATS) {
+      ++w_iters;
+      if (nm) {
+        ++w_node_iters;
+        w_node_lanes += __popc(nm);
+      }
+    }
     if (busy == 0u || (!exhausted && __popc(~busy) >= kRefillMin)) {
+      const long long clk_r = STATS ? clock64() : 0;
       // ---- refill: idle lanes fold their result, move on to the ray's next mesh or fetch a new ray ----
-      if (!is_node && !is_leaf && ray >= 0) {
-        if (STATS) {
-          atomicAdd(&p.stats[0], 1ull);
-          atomicAdd(&p.stats[1], (unsigned long long)n_nodes);
-          atomicAdd(&p.stats[2], (unsigned long long)n_tris);
-          atomicMax(&p.stats[3], (unsigned long long)n_nodes);
-          atomicMax(&p.stats[4], (unsigned long long)n_tris);
-          atomicAdd(&p.stats[5 + min(15u, 31u - __clz((n_nodes + n_tris) | 1u))], 1ull);  // log2 histogram of steps
+      if (!can_node && !has_leaf && ray >= 0) {
+        if (STATS) {  // lane-local, flushed once at the end
+          ++a_walks;
+          a_nodes += n_nodes;
+          a_tris += n_tris;
+          a_maxn = max(a_maxn, n_nodes);
+          a_maxt = max(a_maxt, n_tris);
+          atomicAdd(&sstat[5 + min(15u, 31u - __clz((n_nodes + n_tris) | 1u))], 1ull);  // log2 histogram of steps
         }
         if (best >= 0 && tbest > 0.0f && (tbest < t_min || (tbest == t_min && g < hit))) {
           // the mesh is the closest geom so far: (t, barycentrics, face) into the record, k_mesh_finish does the rest
@@ -195,8 +289,15 @@ __global__ void __launch_bounds__(kWalkThreads, B2PT_WALK_MINBLOCKS) k_mesh_walk
       if (need_m != 0u && !exhausted) {
         const int cnt = __popc(need_m);
         unsigned int qb = 0;
-        if (lane == 0) qb = atomicAdd(head, (unsigned int)cnt);
-        qb = __shfl_sync(0xffffffffu, qb, 0);
+        if (first_fetch) {
+          // every warp's first 32 rays are assigned statically: 3552 warps hitting one ticket word at kernel
+          // start is a queue of same-address atomics; the ticket hands out what lies behind the static part
+          qb = (unsigned int)(blockIdx.x * (kWalkThreads / 32) + (tid >> 5)) * 32u;
+          first_fetch = false;
+        } else {
+          if (lane == 0) qb = static_part + atomicAdd(head, (unsigned int)cnt);
+          qb = __shfl_sync(0xffffffffu, qb, 0);
+        }
         if (qb + (unsigned int)cnt >= total) exhausted = true;
         const unsigned int q = qb + (unsigned int)__popc(need_m & ((1u << lane) - 1u));
         if (need && q < total) {
@@ -211,30 +312,25 @@ __global__ void __launch_bounds__(kWalkThreads, B2PT_WALK_MINBLOCKS) k_mesh_walk
           if (!setup(mk(a.x, a.y, a.z), mk(b.x, b.y, b.z), 0)) ray = -1;
         }
       }
+      if (STATS) {
+        ++w_refills;
+        clk_refill += clock64() - clk_r;
+      }
       if (__ballot_sync(0xffffffffu, node != kWalkDone) == 0u && exhausted) break;
       continue;
     }
+    // One kind of step per iteration, whichever has more lanes waiting: a NODE step (the four child boxes of
+    // every lane's inner node) or a LEAF step (the exact triangle test), so the two code paths never
+    // serialise inside one iteration.
     if (__popc(nm) >= __popc(lm)) {
-      // ---- node step ----
-      if (is_node) {
+      if (can_node) {
         if (STATS) ++n_nodes;
-        const float4* n = nodes + 8 * (size_t)node;
-        const float4 lx = __ldg(n), ly = __ldg(n + 1), lz = __ldg(n + 2);
-        const float4 hx = __ldg(n + 3), hy = __ldg(n + 4), hz = __ldg(n + 5);
-        const float4 cf = __ldg(n + 6);
-        float tn[4];
-        int ch[4] = {__float_as_int(cf.x), __float_as_int(cf.y), __float_as_int(cf.z), __float_as_int(cf.w)};
-        {
-          float tf;
-          slab(lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, qo, id, &tn[0], &tf);
-          if (!(tn[0] <= tf && tf >= 0.0f && tn[0] <= lim)) ch[0] = kEmptyChild;
-          slab(lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, qo, id, &tn[1], &tf);
-          if (!(tn[1] <= tf && tf >= 0.0f && tn[1] <= lim)) ch[1] = kEmptyChild;
-          slab(lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, qo, id, &tn[2], &tf);
-          if (!(tn[2] <= tf && tf >= 0.0f && tn[2] <= lim)) ch[2] = kEmptyChild;
-          slab(lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, qo, id, &tn[3], &tf);
-          if (!(tn[3] <= tf && tf >= 0.0f && tn[3] <= lim)) ch[3] = kEmptyChild;
-        }
+        WideHit wh;
+        float4 cf;
+        wide_slab_fma(nodes + 8 * (size_t)node, offx, offy, offz, id, noid, lim, &wh, &cf);
+        float tn[4] = {wh.tn[0], wh.tn[1], wh.tn[2], wh.tn[3]};
+        int ch[4] = {wh.ok[0] ? __float_as_int(cf.x) : kEmptyChild, wh.ok[1] ? __float_as_int(cf.y) : kEmptyChild,
+                     wh.ok[2] ? __float_as_int(cf.z) : kEmptyChild, wh.ok[3] ? __float_as_int(cf.w) : kEmptyChild};
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           if (ch[k] == kEmptyChild) tn[k] = FLT_MAX;
@@ -249,30 +345,22 @@ __global__ void __launch_bounds__(kWalkThreads, B2PT_WALK_MINBLOCKS) k_mesh_walk
           // nearest first; the others go on the stack farthest first
           if (ch[3] != kEmptyChild) B2PT_WALK_PUSH(ch[3], tn[3])
           if (ch[2] != kEmptyChild) B2PT_WALK_PUSH(ch[2], tn[2])
-          if (ch[1] != kEmptyChild) {
-            B2PT_WALK_PUSH(ch[1], tn[1])
-#if B2PT_WALK_PREFETCH
-            // the entry on top of the stack is the likeliest next visit: have it in L1 by then
-            const void* pf = ch[1] >= 0 ? (const void*)(nodes + 8 * (size_t)ch[1]) : (const void*)(tris + 3 * (size_t)(~ch[1]));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
-#endif
-          }
+          if (ch[1] != kEmptyChild) B2PT_WALK_PUSH(ch[1], tn[1])
           node = ch[0];
         } else {
           B2PT_WALK_POP_NEXT()
         }
-        B2PT_WALK_STEP_DONE()
+        ++steps;
       }
     } else {
-      // ---- leaf step ----
-      if (is_leaf) {
+      if (has_leaf) {
         if (STATS) ++n_tris;
         const float4* tp = tris + 3 * (size_t)(~node);
-        const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+        const float4 ta = __ldg(tp), tb = __ldg(tp + 1), tc = __ldg(tp + 2);
         float u, v;
-        const float t = tri_exact(qo, qd, mk(a.x, a.y, a.z), mk(b.x, b.y, b.z), mk(c.x, c.y, c.z), &u, &v);
+        const float t = tri_exact(qo, qd, mk(ta.x, ta.y, ta.z), mk(tb.x, tb.y, tb.z), mk(tc.x, tc.y, tc.z), &u, &v);
         if (t >= 0.0f) {
-          const int fid = __float_as_int(a.w);
+          const int fid = __float_as_int(ta.w);
           if (t < tbest || (t == tbest && fid < best)) {
             tbest = t;
             best = fid;
@@ -282,14 +370,66 @@ __global__ void __launch_bounds__(kWalkThreads, B2PT_WALK_MINBLOCKS) k_mesh_walk
           }
         }
         B2PT_WALK_POP_NEXT()
-        B2PT_WALK_STEP_DONE()
+        ++steps;
+      }
+    }
+    // A walk that outgrew its lane is handed to k_mesh_walk_long together with its state: the closest hit so
+    // far and the traversal stack plus what the lane was about to do (up to kLongCarry entries; more restarts
+    // at the root, still pruned by the carried hit).  One atomic per warp; if the hand-off queue is full the
+    // lane simply keeps walking.
+    const bool hand = steps > long_walk && node != kWalkDone;
+    const unsigned int hm = __ballot_sync(0xffffffffu, hand);
+    if (hm != 0u) {
+      unsigned int lb = 0;
+      if (lane == __ffs(hm) - 1) lb = atomicAdd(&p.ctr->long_count[p.depth], (unsigned int)__popc(hm));
+      lb = __shfl_sync(0xffffffffu, lb, __ffs(hm) - 1);
+      if (hand) {
+        const unsigned int lq = lb + (unsigned int)__popc(hm & ((1u << lane) - 1u));
+        if (lq < (unsigned int)p.long_cap) {
+          p.long_queue[lq] = make_int2(ray, g);
+          p.long_best[lq] = make_float4(tbest, bu, bv, __int_as_float(best));
+          int2* ent = p.long_stack + (size_t)lq * kLongCarry;
+          int ne = -1;
+          if (sp + 1 <= kLongCarry) {
+            for (int k = 0; k < sp; ++k) ent[k] = k < kWalkShort ? sst[k * kWalkThreads] : spill[k - kWalkShort];
+            ent[sp] = make_int2(node, __float_as_int(0.0f));
+            ne = sp + 1;
+          }
+          p.long_n[lq] = ne;
+          node = kWalkDone;
+          best = -1;
+        } else {
+          steps = -0x40000000;
+        }
       }
     }
   }
 #undef B2PT_WALK_PUSH
-#undef B2PT_WALK_STEP_DONE
 #undef B2PT_WALK_POP_NEXT
+  if (STATS) {
+    atomicAdd(&sstat[0], (unsigned long long)a_walks);
+    atomicAdd(&sstat[1], (unsigned long long)a_nodes);
+    atomicAdd(&sstat[2], (unsigned long long)a_tris);
+    atomicMax(&sstat[3], (unsigned long long)a_maxn);
+    atomicMax(&sstat[4], (unsigned long long)a_maxt);
+    if (lane == 0) {
+      const long long now = clock64();
+      atomicAdd(&sstat[21], 1ull);
+      atomicAdd(&sstat[22], (unsigned long long)w_iters);
+      atomicMax(&sstat[23], (unsigned long long)w_iters);
+      atomicAdd(&sstat[24], (unsigned long long)(now - clk_start));
+      atomicMax(&sstat[25], (unsigned long long)(now - clk_start));
+      atomicAdd(&sstat[26], (unsigned long long)w_refills);
+      atomicAdd(&sstat[27], (unsigned long long)clk_refill);
+      atomicAdd(&sstat[28], (unsigned long long)(clk_loop - clk_start));
+      atomicAdd(&sstat[29], (unsigned long long)w_node_lanes);
+      atomicAdd(&sstat[30], (unsigned long long)w_node_iters);
+    }
+  }
   __syncthreads();
+  if (STATS && tid < 32 && sstat[tid]) {
+    if (tid == 3 || tid == 4 || tid == 23 || tid == 25) atomicMax(&p.stats[tid], sstat[tid]); else atomicAdd(&p.stats[tid], sstat[tid]);
+  }
   for (int i = tid; i < kMaxMaterials; i += kWalkThreads) {
     const int c = shist[i];
     if (c) atomicAdd(&p.ctr->hist[p.depth][i], (unsigned int)c);
@@ -298,143 +438,183 @@ __global__ void __launch_bounds__(kWalkThreads, B2PT_WALK_MINBLOCKS) k_mesh_walk
   }
 }
 
-// One warp per long walk.  The warp shares one stack of (node, entry distance)
-// pairs in shared memory; each round the 32 lanes take the top 32 entries, inner
-// nodes test their four child boxes, leaves run the exact triangle test, the
-// closest (t, face) of the round is reduced across the warp and the surviving
-// children are appended with a warp scan.  The visiting order is no longer
+// Long walks, kCoopGroup lanes per ray (four rays per warp).  A group shares one
+// stack of (node, entry distance) pairs in shared memory, seeded with the state
+// k_mesh_walk handed over; each round its lanes take the top entries, inner nodes
+// test their four child boxes, leaves run the exact triangle test, the closest
+// (t, face) of the round is reduced across the group and the surviving children
+// are appended with a segmented scan.  The visiting order is no longer
 // nearest-first, which is harmless: the winner is the lexicographic minimum of
 // (t, face id) whatever the order, and entries behind it are dropped.  Close to
-// the capacity of the stack the warp falls back to one entry per round
-// (depth-first, growth <= 3 per level).
+// the capacity of the stack a group falls back to one entry per round
+// (depth-first, growth <= 3 per level).  The loop is warp-uniform: the four
+// groups of a warp run their rounds in lockstep and refill independently.
 constexpr int kCoopThreads = 128;
-constexpr int kCoopCap = 1024;
+#ifndef B2PT_COOP_GROUP
+#define B2PT_COOP_GROUP 16
+#endif
+constexpr int kCoopGroup = B2PT_COOP_GROUP;
+constexpr int kCoopCap = 32 * kCoopGroup;                        // stack entries per group (32 KB per CTA in all)
+constexpr int kCoopDfs = kCoopCap - 96 - 3 * kCoopGroup;         // above this only one entry per round is taken
+constexpr unsigned int kCoopMask = kCoopGroup == 32 ? 0xffffffffu : ((1u << (kCoopGroup & 31)) - 1u);
 
 __global__ void __launch_bounds__(kCoopThreads) k_mesh_walk_long(IsectParams p) {
-  __shared__ int2 cstack[(kCoopThreads / 32) * kCoopCap];
+  __shared__ int2 cstack[(kCoopThreads / kCoopGroup) * kCoopCap];
   const int lane = threadIdx.x & 31;
-  int2* const st = cstack + (threadIdx.x >> 5) * kCoopCap;
-  const unsigned int total = p.ctr->long_count[p.depth];
+  const int gl = lane & (kCoopGroup - 1);           // lane within the group
+  const int gfirst = lane & ~(kCoopGroup - 1);      // first lane of the group
+  int2* const st = cstack + (threadIdx.x / kCoopGroup) * kCoopCap;
+  const unsigned int total = min(p.ctr->long_count[p.depth], (unsigned int)p.long_cap);
   unsigned int* head = &p.ctr->long_ticket[p.depth];
+
+  // ---- group state (replicated in the lanes of the group) ----
+  int ray = -1, g = 0, hit = kNoGeom, sp = 0, best = -1;
+  float t_min = FLT_MAX, tbest = 0.0f, lim = 0.0f, bu = 0.0f, bv = 0.0f;
+  V3 qo = mk(0, 0, 0), qd = mk(0, 0, 1), id = mk(0, 0, 1), noid = mk(0, 0, 0);
+  int offx = 0, offy = 32, offz = 64;
+  const float4* nodes = nullptr;
+  const float4* tris = nullptr;
+  bool exhausted = false;
+
   while (true) {
-    unsigned int q = 0;
-    if (lane == 0) q = atomicAdd(head, 1u);
-    q = __shfl_sync(0xffffffffu, q, 0);
-    if (q >= total) break;
-    const int2 job = p.long_queue[q];
-    const int ray = job.x, g = job.y;
-    const DevGeom& G = p.scene.geoms[g];
-    const DevMesh& M = p.scene.meshes[G.mesh];
-    const float4 a = p.in.s0[ray];
-    const float4 b = p.in.s1[ray];
-    const float t0 = reinterpret_cast<const float*>(p.out.h0 + ray)[0];
-    const int gm0 = __float_as_int(p.out.h1[ray].z);
-    const float t_min = t0 > 0.0f ? t0 : FLT_MAX;
-    const int hit = t0 > 0.0f ? (gm0 & 0xffff) : kNoGeom;
-    const V3 qo = xform(G.inv, mk(a.x, a.y, a.z), 1.0f);
-    const V3 qd = normalize(xform(G.inv, mk(b.x, b.y, b.z), 0.0f));
-    const V3 id = mk(1.0f / qd.x, 1.0f / qd.y, 1.0f / qd.z);
-    const float t_limit = (G.rigid && t_min < FLT_MAX) ? t_min * 1.0001f + 1e-5f : FLT_MAX;
-    float tbest = t_limit;
-    float lim = t_limit >= FLT_MAX ? FLT_MAX : t_limit * 1.00001f + 1e-6f;
-    int best = -1;
-    float bu = 0.0f, bv = 0.0f;
-    const float4* nodes = M.nodes;
-    const float4* tris = M.tris;
-    __syncwarp();
-    if (lane == 0) st[0] = make_int2(M.root, __float_as_int(0.0f));
-    int sp = 1;
-    __syncwarp();
-    while (sp > 0) {
-      const int take = sp > kCoopCap - 256 ? 1 : min(sp, 32);
-      int node = kWalkDone;
-      if (lane < take) {
-        const int2 e = st[sp - 1 - lane];
-        if (__int_as_float(e.y) <= lim) node = e.x;
+    if (sp == 0) {  // group-uniform: fold the finished walk, fetch the next one
+      if (ray >= 0) {
+        if (gl == 0 && best >= 0 && tbest > 0.0f && (tbest < t_min || (tbest == t_min && g < hit))) {
+          const int old_mat = hit == kNoGeom ? 0 : p.scene.geoms[hit].material;
+          const int mat = p.scene.geoms[g].material;
+          if (mat != old_mat) {
+            atomicAdd(&p.ctr->hist[p.depth][mat], 1u);
+            atomicSub(&p.ctr->hist[p.depth][old_mat], 1u);
+          }
+          if (p.live[ray]) {
+            atomicSub(&p.ctr->hist_live[p.depth][old_mat], 1u);
+            p.live[ray] = 0;
+          }
+          p.key[ray] = (uint8_t)mat;
+          reinterpret_cast<float*>(p.out.h0 + ray)[0] = tbest;
+          p.out.h1[ray] = make_float4(bu, bv, __int_as_float((g & 0xffff) | (mat << 16)), __int_as_float(best));
+        }
+        ray = -1;
       }
-      sp -= take;
-      __syncwarp();
-      int ch[4];
-      float tn[4];
-      float t = -1.0f, u = 0.0f, v = 0.0f;
-      int fid = 0x7fffffff;
-      if (walk_is_inner(node)) {
-        const float4* n = nodes + 8 * (size_t)node;
-        const float4 lx = __ldg(n), ly = __ldg(n + 1), lz = __ldg(n + 2);
-        const float4 hx = __ldg(n + 3), hy = __ldg(n + 4), hz = __ldg(n + 5);
-        const float4 cf = __ldg(n + 6);
-        ch[0] = __float_as_int(cf.x); ch[1] = __float_as_int(cf.y); ch[2] = __float_as_int(cf.z); ch[3] = __float_as_int(cf.w);
-        float tf;
-        slab(lx.x, ly.x, lz.x, hx.x, hy.x, hz.x, qo, id, &tn[0], &tf);
-        if (!(tn[0] <= tf && tf >= 0.0f)) ch[0] = kEmptyChild;
-        slab(lx.y, ly.y, lz.y, hx.y, hy.y, hz.y, qo, id, &tn[1], &tf);
-        if (!(tn[1] <= tf && tf >= 0.0f)) ch[1] = kEmptyChild;
-        slab(lx.z, ly.z, lz.z, hx.z, hy.z, hz.z, qo, id, &tn[2], &tf);
-        if (!(tn[2] <= tf && tf >= 0.0f)) ch[2] = kEmptyChild;
-        slab(lx.w, ly.w, lz.w, hx.w, hy.w, hz.w, qo, id, &tn[3], &tf);
-        if (!(tn[3] <= tf && tf >= 0.0f)) ch[3] = kEmptyChild;
-      } else {
-        ch[0] = ch[1] = ch[2] = ch[3] = kEmptyChild;
-        tn[0] = tn[1] = tn[2] = tn[3] = FLT_MAX;
-        if (node < 0) {
-          const float4* tp = tris + 3 * (size_t)(~node);
-          const float4 ta = __ldg(tp), tb = __ldg(tp + 1), tc = __ldg(tp + 2);
-          t = tri_exact(qo, qd, mk(ta.x, ta.y, ta.z), mk(tb.x, tb.y, tb.z), mk(tc.x, tc.y, tc.z), &u, &v);
-          fid = __float_as_int(ta.w);
+      if (!exhausted) {
+        unsigned int q = 0;
+        if (gl == 0) q = atomicAdd(head, 1u);
+        q = __shfl_sync(kCoopMask << gfirst, q, gfirst);
+        if (q >= total) {
+          exhausted = true;
+        } else {
+          const int2 job = p.long_queue[q];
+          ray = job.x;
+          g = job.y;
+          const DevGeom& G = p.scene.geoms[g];
+          const DevMesh& M = p.scene.meshes[G.mesh];
+          const float4 a = p.in.s0[ray];
+          const float4 b = p.in.s1[ray];
+          const float t0 = reinterpret_cast<const float*>(p.out.h0 + ray)[0];
+          const int gm0 = __float_as_int(p.out.h1[ray].z);
+          t_min = t0 > 0.0f ? t0 : FLT_MAX;
+          hit = t0 > 0.0f ? (gm0 & 0xffff) : kNoGeom;
+          qo = xform(G.inv, mk(a.x, a.y, a.z), 1.0f);
+          qd = normalize(xform(G.inv, mk(b.x, b.y, b.z), 0.0f));
+          id = mk(1.0f / qd.x, 1.0f / qd.y, 1.0f / qd.z);
+          noid = mk(-(qo.x * id.x), -(qo.y * id.y), -(qo.z * id.z));
+          slab_offsets(id, &offx, &offy, &offz);
+          const float t_limit = (G.rigid && t_min < FLT_MAX) ? t_min * 1.0001f + 1e-5f : FLT_MAX;
+          // the state k_mesh_walk handed over: closest triangle so far and (if it fitted) the traversal stack
+          const float4 carried = p.long_best[q];
+          const int n_carried = p.long_n[q];
+          tbest = carried.x;
+          best = __float_as_int(carried.w);
+          bu = carried.y;
+          bv = carried.z;
+          lim = best >= 0 ? tbest * 1.00001f + 1e-6f : (t_limit >= FLT_MAX ? FLT_MAX : t_limit * 1.00001f + 1e-6f);
+          nodes = M.nodes;
+          tris = M.tris;
+          if (n_carried > 0) {
+            for (int k = gl; k < n_carried; k += kCoopGroup) st[k] = p.long_stack[(size_t)q * kLongCarry + k];
+            sp = n_carried;
+          } else {
+            if (gl == 0) st[0] = make_int2(M.root, __float_as_int(0.0f));
+            sp = 1;
+          }
         }
       }
-      // closest (t, face) of this round; t >= 0, so the bit patterns order like the values
-      const unsigned int tb_ = t >= 0.0f ? __float_as_uint(t) : 0xffffffffu;
-      const unsigned int mn = __reduce_min_sync(0xffffffffu, tb_);
-      if (mn != 0xffffffffu) {
-        const unsigned int fm = __reduce_min_sync(0xffffffffu, tb_ == mn ? (unsigned int)fid : 0xffffffffu);
-        const float tr = __uint_as_float(mn);
-        const int src = __ffs(__ballot_sync(0xffffffffu, tb_ == mn && (unsigned int)fid == fm)) - 1;
-        const float su = __shfl_sync(0xffffffffu, u, src), sv = __shfl_sync(0xffffffffu, v, src);
-        if (tr < tbest || (tr == tbest && (int)fm < best)) {
+    }
+    __syncwarp();
+    if (!__any_sync(0xffffffffu, sp > 0)) break;
+
+    // ---- one round ----
+    const int take = sp > kCoopDfs ? 1 : min(sp, kCoopGroup);
+    int node = kWalkDone;
+    if (gl < take) {
+      const int2 e = st[sp - 1 - gl];
+      if (__int_as_float(e.y) <= lim) node = e.x;
+    }
+    sp -= take;
+    __syncwarp();
+    int ch[4] = {kEmptyChild, kEmptyChild, kEmptyChild, kEmptyChild};
+    float tn[4] = {FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX};
+    float t = -1.0f, u = 0.0f, v = 0.0f;
+    int fid = 0x7fffffff;
+    if (walk_is_inner(node)) {
+      WideHit wh;
+      float4 cf;
+      wide_slab_fma(nodes + 8 * (size_t)node, offx, offy, offz, id, noid, lim, &wh, &cf);
+      tn[0] = wh.tn[0]; tn[1] = wh.tn[1]; tn[2] = wh.tn[2]; tn[3] = wh.tn[3];
+      ch[0] = wh.ok[0] ? __float_as_int(cf.x) : kEmptyChild;
+      ch[1] = wh.ok[1] ? __float_as_int(cf.y) : kEmptyChild;
+      ch[2] = wh.ok[2] ? __float_as_int(cf.z) : kEmptyChild;
+      ch[3] = wh.ok[3] ? __float_as_int(cf.w) : kEmptyChild;
+    } else if (node < 0) {
+      const float4* tp = tris + 3 * (size_t)(~node);
+      const float4 ta = __ldg(tp), tb = __ldg(tp + 1), tc = __ldg(tp + 2);
+      t = tri_exact(qo, qd, mk(ta.x, ta.y, ta.z), mk(tb.x, tb.y, tb.z), mk(tc.x, tc.y, tc.z), &u, &v);
+      fid = __float_as_int(ta.w);
+    }
+    // closest (t, face) of this round within the group; t >= 0, so the bit patterns order like the values
+    if (__any_sync(0xffffffffu, t >= 0.0f)) {
+      unsigned long long key = t >= 0.0f ? ((unsigned long long)__float_as_uint(t) << 32) | (unsigned int)fid : ~0ull;
+      unsigned long long mn = key;
+#pragma unroll
+      for (int o = kCoopGroup / 2; o > 0; o >>= 1) {
+        const unsigned long long y = __shfl_xor_sync(0xffffffffu, mn, o, kCoopGroup);
+        mn = y < mn ? y : mn;
+      }
+      const unsigned int winners = __ballot_sync(0xffffffffu, key == mn && mn != ~0ull) & (kCoopMask << gfirst);
+      // the shuffles run on the whole warp (this block is warp-uniform); groups without a hit read themselves
+      const int src = winners ? __ffs(winners) - 1 : lane;
+      const float su = __shfl_sync(0xffffffffu, u, src), sv = __shfl_sync(0xffffffffu, v, src);
+      if (winners) {  // group-uniform
+        const float tr = __uint_as_float((unsigned int)(mn >> 32));
+        const int fr = (int)(unsigned int)mn;
+        if (tr < tbest || (tr == tbest && fr < best)) {
           tbest = tr;
-          best = (int)fm;
+          best = fr;
           bu = su;
           bv = sv;
           lim = tr * 1.00001f + 1e-6f;
         }
       }
-      // append the children that are still in front of the closest hit
-      int cnt = 0;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (ch[k] != kEmptyChild && !(tn[k] <= lim)) ch[k] = kEmptyChild;
-        cnt += ch[k] != kEmptyChild;
-      }
-      int incl = cnt;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += y;
-      }
-      const int all = __shfl_sync(0xffffffffu, incl, 31);
-      int w = sp + incl - cnt;
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (ch[k] != kEmptyChild) st[w++] = make_int2(ch[k], __float_as_int(tn[k]));
-      sp += all;
-      __syncwarp();
     }
-    if (lane == 0 && best >= 0 && tbest > 0.0f && (tbest < t_min || (tbest == t_min && g < hit))) {
-      const int old_mat = hit == kNoGeom ? 0 : p.scene.geoms[hit].material;
-      const int mat = G.material;
-      if (mat != old_mat) {
-        atomicAdd(&p.ctr->hist[p.depth][mat], 1u);
-        atomicSub(&p.ctr->hist[p.depth][old_mat], 1u);
-      }
-      if (p.live[ray]) {
-        atomicSub(&p.ctr->hist_live[p.depth][old_mat], 1u);
-        p.live[ray] = 0;
-      }
-      p.key[ray] = (uint8_t)mat;
-      reinterpret_cast<float*>(p.out.h0 + ray)[0] = tbest;
-      p.out.h1[ray] = make_float4(bu, bv, __int_as_float((g & 0xffff) | (mat << 16)), __int_as_float(best));
+    // append the children that are still in front of the closest hit (segmented scan over the group)
+    int cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (ch[k] != kEmptyChild && !(tn[k] <= lim)) ch[k] = kEmptyChild;
+      cnt += ch[k] != kEmptyChild;
     }
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < kCoopGroup; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, incl, o, kCoopGroup);
+      if (gl >= o) incl += y;
+    }
+    const int all = __shfl_sync(0xffffffffu, incl, kCoopGroup - 1, kCoopGroup);
+    int w = sp + incl - cnt;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      if (ch[k] != kEmptyChild) st[w++] = make_int2(ch[k], __float_as_int(tn[k]));
+    sp += all;
     __syncwarp();
   }
 }
