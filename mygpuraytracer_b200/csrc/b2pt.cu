@@ -335,8 +335,8 @@ static int build_mesh(B2ptCtx* c, const float* pos_host, const float* uv_host, i
   float ext = 0.0f;
   for (int k = 0; k < 3; ++k) ext = std::max(ext, std::max(std::fabs(lo[k]), std::fabs(hi[k])));
   // second term: the FMA slab test of k_walk.cuh displaces a plane by up to ~2^-23 * (largest coordinate of a
-  // ray origin in this mesh's object space); origin_radius bounds that coordinate
-  const float pad = 4e-6f * std::max(ext, 1.0f) + 9.5367431640625e-7f * origin_radius;
+  // ray origin in this mesh's object space); origin_radius bounds that coordinate (pad = 2^-19 * it)
+  const float pad = 4e-6f * std::max(ext, 1.0f) + 1.9073486328125e-6f * origin_radius;
 
   TriBounds* bounds = nullptr;
   uint32_t *code = nullptr, *val = nullptr;

@@ -175,12 +175,31 @@ __device__ __forceinline__ float sphere_exact(const DevGeom& G, V3 o, V3 d, V3* 
   return length(o - xform(G.fwd, p, 1.0f));
 }
 
+// 1/x to ~1 ulp (MUFU.RCP) for tests that only prune: the exact tests never see it.
+__device__ __forceinline__ float rcp_fast(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ V3 rcp_fast(V3 d) { return mk(rcp_fast(d.x), rcp_fast(d.y), rcp_fast(d.z)); }
+
+// Ray against a geom's padded world-space box, one FMA per plane: id ~ 1/d, noid = -(o * id).
+// The boxes are padded by >= 1e-3 (world_box), far more than the rounding of the FMA form; NaNs (rays
+// parallel to an axis) are dropped by fminf/fmaxf, i.e. that axis does not constrain the box.
+__device__ __forceinline__ void world_slab(const DevGeom& G, V3 id, V3 noid, float* tn, float* tf) {
+  const float x0 = fmaf(G.wmin.x, id.x, noid.x), x1 = fmaf(G.wmax.x, id.x, noid.x);
+  const float y0 = fmaf(G.wmin.y, id.y, noid.y), y1 = fmaf(G.wmax.y, id.y, noid.y);
+  const float z0 = fmaf(G.wmin.z, id.z, noid.z), z1 = fmaf(G.wmax.z, id.z, noid.z);
+  *tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fminf(z0, z1));
+  *tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
+}
+
 // Conservative world-space pre-test against a geom's padded bounding box.
 // Returns false only if the exact test is certain to miss, or certain to
 // return a distance that cannot beat t_best (strictly closer hits win).
-__device__ __forceinline__ bool may_beat(const DevGeom& G, V3 o, V3 id, float t_best, bool world_metric) {
+__device__ __forceinline__ bool may_beat(const DevGeom& G, V3 id, V3 noid, float t_best, bool world_metric) {
   float tn, tf;
-  slab(G.wmin.x, G.wmin.y, G.wmin.z, G.wmax.x, G.wmax.y, G.wmax.z, o, id, &tn, &tf);
+  world_slab(G, id, noid, &tn, &tf);
   if (!(tn <= tf) || tf < 0.0f) return false;
   // G.wmin.w = slack: the exact tests pull the hit point back by 1e-4 in OBJECT
   // space (getPointOnRay), i.e. by up to 1e-4 * scale in world space
@@ -275,15 +294,26 @@ __global__ void __launch_bounds__(256) k_intersect_analytic(IsectParams p) {
       const float4 a = p.in.s0[i];
       const float4 b = p.in.s1[i];
       const V3 o = mk(a.x, a.y, a.z), d = mk(b.x, b.y, b.z);
-      const V3 id = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+      const V3 id = rcp_fast(d);
+      const V3 noid = mk(-(o.x * id.x), -(o.y * id.y), -(o.z * id.z));
       float t_min = FLT_MAX;
       int hit = -1, kind = 0;
       V3 aux = mk(0, 0, 0);  // box: axis normal; sphere: object-space point
-      // Pass 1 (warp-coherent, cheap): which geoms does this ray's path cross?
+      // Pass 1 (warp-coherent, cheap): which geoms does this ray's path cross?  For meshes: the closest box
+      // entry (minus the distance slack) of the rigid ones, and whether a non-rigid one is crossed at all.
       unsigned long long cand = 0ull;
+      float mesh_tn = FLT_MAX;
+      bool mesh_any = false;
       for (int g = 0; g < n_geoms; ++g) {
         const DevGeom& G = sgeom[g];
-        if ((G.type == 1 || G.type == 0) && may_beat(G, o, id, FLT_MAX, true)) cand |= 1ull << g;
+        float tn, tf;
+        world_slab(G, id, noid, &tn, &tf);
+        if (!(tn <= tf) || tf < 0.0f) continue;
+        if (G.type == 1 || G.type == 0) {
+          cand |= 1ull << g;
+        } else if (G.type == 3 && G.mesh >= 0) {
+          if (G.rigid) mesh_tn = fminf(mesh_tn, tn - G.wmin.w); else mesh_any = true;
+        }
       }
       // Pass 2: each lane runs the exact tests of ITS candidates (typically 1-3
       // of the 8-9 geoms), in geom order; the warp iterates max-popcount times
@@ -292,7 +322,7 @@ __global__ void __launch_bounds__(256) k_intersect_analytic(IsectParams p) {
         const int g = __ffsll((long long)cand) - 1;
         cand &= cand - 1ull;
         const DevGeom& G = sgeom[g];
-        if (!may_beat(G, o, id, t_min, true)) continue;
+        if (!may_beat(G, id, noid, t_min, true)) continue;
         float t;
         V3 taux = mk(0, 0, 0);
         int tkind = 1;
@@ -321,12 +351,9 @@ __global__ void __launch_bounds__(256) k_intersect_analytic(IsectParams p) {
       p.out.h1[i] = h1;
       p.key[i] = (uint8_t)mat;
       p.live[i] = survives ? 1 : 0;
-      if (n_meshes > 0) {
-        for (int g = 0; g < n_geoms && !want_mesh; ++g) {
-          const DevGeom& G = sgeom[g];
-          if (G.type == 3 && G.mesh >= 0) want_mesh = may_beat(G, o, id, t_min, G.rigid != 0);
-        }
-      }
+      // a mesh has to be walked if its box is entered in front of the closest analytic hit (a rigid mesh
+      // reports world-space distances, so t_min bounds it; any other mesh is always walked)
+      want_mesh = mesh_any || (mesh_tn < FLT_MAX && (t_min >= FLT_MAX || mesh_tn <= t_min * 1.0001f));
     }
     const unsigned int active = __ballot_sync(0xffffffffu, valid);
     if (valid) {
@@ -389,7 +416,8 @@ __global__ void __launch_bounds__(kIsectThreads, 3) k_intersect_mesh_brute(Isect
       const float4 h0 = p.out.h0[i];
       const int gm = __float_as_int(p.out.h1[i].z);
       const V3 o = mk(a.x, a.y, a.z), d = mk(b.x, b.y, b.z);
-      const V3 id = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+      const V3 id = rcp_fast(d);
+      const V3 noid = mk(-(o.x * id.x), -(o.y * id.y), -(o.z * id.z));
       float t_min = h0.x > 0.0f ? h0.x : FLT_MAX;
       int hit = h0.x > 0.0f ? (gm & 0xffff) : 0x7fffffff;
       const int old_mat = (gm >> 16) & 0xffff;
@@ -398,7 +426,7 @@ __global__ void __launch_bounds__(kIsectThreads, 3) k_intersect_mesh_brute(Isect
       for (int g = 0; g < n_geoms; ++g) {
         const DevGeom& G = sgeom[g];
         if (G.type != 3 || G.mesh < 0) continue;
-        if (!may_beat(G, o, id, t_min, G.rigid != 0)) continue;
+        if (!may_beat(G, id, noid, t_min, G.rigid != 0)) continue;
         const DevMesh& M = p.scene.meshes[G.mesh];
         const V3 qo = xform(G.inv, o, 1.0f);
         const V3 qd = normalize(xform(G.inv, d, 0.0f));

@@ -64,10 +64,11 @@ constexpr int kNoGeom = 0x7fffffff;
 //     tn = max(near.x*id.x + noid.x, near.y*.., near.z*.., 0)
 //     tf = min(far.x*id.x + noid.x,  far.y*..,  far.z*..,  lim)
 // (B2PT_NODE_LOAD256: three 256-bit loads fetch the pairs and min/max orders them.)
-// Rounding: o*id is rounded once and the FMA once, which displaces each plane by
-// at most ~2^-23 * max(|o|, |plane|) in position space whatever the size of id;
-// the build pads every box by 2^-20 * (largest coordinate a ray origin can have
-// in object space) on top of the extent term, so the test stays conservative.
+// Rounding: id is 1/d to ~1 ulp (MUFU.RCP), o*id is rounded once and the FMA once;
+// together that displaces each plane by at most ~2^-21 * max(|o|, |plane|) in
+// position space whatever the size of id.  The build pads every box by 2^-19 *
+// (largest coordinate a ray origin can have in object space) on top of the
+// extent term, so the test stays conservative.
 // NaNs (0 * inf, inf - inf for rays parallel to an axis) are dropped by
 // fminf / fmaxf: that axis then does not constrain the box.
 struct WideHit {
@@ -206,17 +207,18 @@ __global__ void __launch_bounds__(kWalkThreads, B2PT_WALK_MINBLOCKS) k_mesh_walk
   // Find the next mesh geom >= g0 whose box this ray crosses in front of t_min and
   // set the walk up in its object space.
   auto setup = [&](V3 o, V3 d, int g0) -> bool {
-    const V3 idw = mk(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    const V3 idw = rcp_fast(d);
+    const V3 noidw = mk(-(o.x * idw.x), -(o.y * idw.y), -(o.z * idw.z));
     for (int gg = g0; gg < n_geoms; ++gg) {
       const DevGeom& G = sgeom[gg];
       if (G.type != 3 || G.mesh < 0) continue;
-      if (!may_beat(G, o, idw, t_min, G.rigid != 0)) continue;
+      if (!may_beat(G, idw, noidw, t_min, G.rigid != 0)) continue;
       const DevMesh& M = p.scene.meshes[G.mesh];
       nodes = M.nodes;
       tris = M.tris;
       qo = xform(G.inv, o, 1.0f);
       qd = normalize(xform(G.inv, d, 0.0f));
-      id = mk(1.0f / qd.x, 1.0f / qd.y, 1.0f / qd.z);
+      id = rcp_fast(qd);
       noid = mk(-(qo.x * id.x), -(qo.y * id.y), -(qo.z * id.z));
       slab_offsets(id, &offx, &offy, &offz);
       const float t_limit = (G.rigid && t_min < FLT_MAX) ? t_min * 1.0001f + 1e-5f : FLT_MAX;
@@ -516,7 +518,7 @@ __global__ void __launch_bounds__(kCoopThreads) k_mesh_walk_long(IsectParams p) 
           hit = t0 > 0.0f ? (gm0 & 0xffff) : kNoGeom;
           qo = xform(G.inv, mk(a.x, a.y, a.z), 1.0f);
           qd = normalize(xform(G.inv, mk(b.x, b.y, b.z), 0.0f));
-          id = mk(1.0f / qd.x, 1.0f / qd.y, 1.0f / qd.z);
+          id = rcp_fast(qd);
           noid = mk(-(qo.x * id.x), -(qo.y * id.y), -(qo.z * id.z));
           slab_offsets(id, &offx, &offy, &offz);
           const float t_limit = (G.rigid && t_min < FLT_MAX) ? t_min * 1.0001f + 1e-5f : FLT_MAX;
