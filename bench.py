@@ -279,13 +279,16 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     n_tris = len(pod.face_pos)
     P = pod.n_pixels
     opt = abi.default_options(device=local_rank)
+    # the KC throughput contexts share the GPU (grids sized to a share of the SMs); the e2e leg below uses its
+    # own full-width context, because one pathtrace() call at a time wants the lowest latency
+    opt_shared = abi.default_options(device=local_rank, concurrent_contexts=max(1, args.streams))
     # KC contexts per GPU, each on its own stream with its own accumulator, render
     # interleaved iteration indices (the same samples-per-pixel sharding used
     # across GPUs).  One iteration is 26 short dependent kernels that cannot fill
     # 148 SMs on their own (a depth-7 launch has 250 k rays); independent
     # iterations in flight overlap each other's tails.
     KC = max(1, args.streams)
-    rs = [api.Renderer(scene, opt) for _ in range(KC)]
+    rs = [api.Renderer(scene, opt_shared) for _ in range(KC)]
     r = rs[0]
     mesh_geom = int(np.nonzero(pod.geoms["type"] == abi.OBJ)[0][0])
     bvh = r.bvh_info(mesh_geom)
@@ -364,8 +367,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     host_img = torch.empty(P * 3, dtype=torch.float32).pin_memory()
     host_alb = torch.empty(P * 3, dtype=torch.float32).pin_memory()
     img_np, alb_np = host_img.numpy().reshape(P, 3), host_alb.numpy().reshape(P, 3)
+    r_e2e = api.Renderer(scene, opt)
+    r_e2e.set_stream_ptr(stream.cuda_stream)
     with torch.cuda.stream(stream):
-        r.reset()
+        r = r_e2e
         for i in range(min(W, 3)):
             r.pathtrace(first + i * lanes, img_np, alb_np)
         barrier()
@@ -382,6 +387,10 @@ def run_ours(args, rank: int, world: int, local_rank: int):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * K * P / (float(t.item()) * 1e-3) / 1e6
     checksum = float(np.float64(img_np.sum()))
+    with torch.cuda.stream(stream):
+        prof_full = [r_e2e.profile_kernels(first + (3 * W + 2 * K + KC + i) * lanes) for i in range(5)]
+        barrier()
+    prof_full = {k: statistics.median(p[k] for p in prof_full) for k in prof_full[0]}
 
     if rank == 0:
         peak, peak_src = hbm_peak()
@@ -425,6 +434,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "roofline_iter": {"bytes_per_step": iter_bytes, "achieved": iter_gbs, "peak": peak, "unit": "GB/s",
                               "frac": iter_gbs / peak, "formula": "84*P + 280*S"},
             "kernel_ms_per_step": prof,
+            "kernel_ms_per_step_full_width": prof_full,
+            "kernel_ms_note": "CUDA events around every launch of one iteration run alone: with the grids of the timed "
+                              "region (contexts share the SMs) and with the full-width grids of the e2e context",
             "segments_per_step": segments, "live_paths_per_depth": [int(x) for x in live[: args.depth + 1]],
             "bvh": {"triangles": int(bvh.n_faces), "nodes": int(bvh.n_nodes), "max_depth": int(bvh.max_depth),
                     "build_ms": float(bvh.build_ms)},
@@ -436,7 +448,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             if rg is not None:
                 line["reference_gpu"] = rg
         emit(line)
-    for x in rs:
+    for x in rs + [r_e2e]:
         x.close()
     if dist:
         dist.barrier()
@@ -453,7 +465,7 @@ def main():
     ap.add_argument("--height", type=int, default=HEIGHT)
     ap.add_argument("--depth", type=int, default=DEPTH)
     ap.add_argument("--triangles", type=int, default=250_000)
-    ap.add_argument("--streams", type=int, default=3, help="concurrent iteration streams (contexts) per GPU")
+    ap.add_argument("--streams", type=int, default=4, help="concurrent iteration streams (contexts) per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / reference_gpu legs")
     ap.add_argument("--ref-gpu-iters", type=int, default=1)
     ap.add_argument("--ref-gpu-timeout", type=int, default=240)

@@ -154,7 +154,13 @@ typedef struct B2ptOptions {
   int32_t record_stages;      /* 1 = keep per-depth stage dumps of the next
                                  b2pt_render call readable (def 0)          */
   int32_t use_graph;          /* 1 = replay the iteration as a CUDA graph   */
-  int32_t reserved[8];
+  int32_t concurrent_contexts; /* how many contexts render on this GPU at the
+                                 same time (spp sharding inside one GPU, each
+                                 on its own stream).  > 1 sizes the persistent
+                                 grids to a share of the SMs so that the
+                                 contexts' kernels co-reside: lower latency
+                                 per context is traded for throughput (def 1) */
+  int32_t reserved[7];
 } B2ptOptions;
 
 /* Fills `opt` with the defaults above (the reference's compile-time macros). */

@@ -122,7 +122,8 @@ class Options(C.Structure):
         ("use_bvh", C.c_int32),
         ("record_stages", C.c_int32),
         ("use_graph", C.c_int32),
-        ("reserved", C.c_int32 * 8),
+        ("concurrent_contexts", C.c_int32),
+        ("reserved", C.c_int32 * 7),
     ]
 
 
@@ -144,6 +145,7 @@ def default_options(**kw) -> Options:
     o.use_bvh = 1
     o.record_stages = 0
     o.use_graph = 1
+    o.concurrent_contexts = 1
     for k, v in kw.items():
         if not hasattr(o, k):
             raise AttributeError(f"B2ptOptions has no field {k!r}")

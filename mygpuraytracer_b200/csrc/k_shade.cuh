@@ -106,17 +106,17 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade_compact(ShadeParams p) 
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = p.ctr->n_live[p.depth];
-  if (PRECOMP) {
-    if (tid == 0) s_tile = blockIdx.x;  // no ordering between tiles is needed
-  } else {
+  unsigned int tile = blockIdx.x;  // PRECOMP: no ordering between tiles is needed, the CTAs stride over them
+  if (!PRECOMP) {
     if (tid == 0) s_tile = atomicAdd(&p.ctr->shade_ticket[p.depth], 1u);
+    __syncthreads();
+    tile = s_tile;
   }
-  __syncthreads();
-  const unsigned int tile = s_tile;
-  if ((long long)tile * kShadeThreads >= (long long)n) return;
   const unsigned int epoch = p.ctr->serial * (unsigned int)(kMaxDepth + 1) + (unsigned int)p.depth + 1u;
   const int iter = p.iter_state[0];
   const int ref_depth = p.depth + 1;
+  for (;; tile += gridDim.x) {
+  if ((long long)tile * kShadeThreads >= (long long)n) return;
 
   const int j = (int)tile * kShadeThreads + tid;
   const bool valid = j < n;
@@ -272,11 +272,12 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade_compact(ShadeParams p) 
   // ---- stable compaction: rank among the survivors --------------------------------
   unsigned int ballot = 0;
   if (PRECOMP) {
-    if (!valid) return;
-    const unsigned int pos = (unsigned int)p.apos[j];
-    write_result<RECORD>(p, j, pos, alive, o, d, col, pixel, bounces);
-    if (RECORD && alive != (p.live[p.perm ? p.perm[j] : j] != 0)) atomicAdd(&p.ctr->pred_mismatch, 1u);
-    return;
+    if (valid) {
+      const unsigned int pos = (unsigned int)p.apos[j];
+      write_result<RECORD>(p, j, pos, alive, o, d, col, pixel, bounces);
+      if (RECORD && alive != (p.live[p.perm ? p.perm[j] : j] != 0)) atomicAdd(&p.ctr->pred_mismatch, 1u);
+    }
+    continue;
   }
   ballot = __ballot_sync(0xffffffffu, alive);
   if (lane == 0) warp_cnt[warp] = __popc(ballot);
@@ -302,6 +303,8 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade_compact(ShadeParams p) 
   if (!valid) return;
   const unsigned int pos = s_excl + warp_cnt[warp] + __popc(ballot & ((1u << lane) - 1u));
   write_result<RECORD>(p, j, pos, alive, o, d, col, pixel, bounces);
+  return;
+  }  // tile loop (only PRECOMP comes back here)
 }
 
 }  // namespace b2pt

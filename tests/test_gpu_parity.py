@@ -184,6 +184,30 @@ def test_first_bounce_cache_changes_nothing(tmp_path, scene_kind):
         assert_same_bits(r.read()[0], ref_aa, "cache ignored with AA on")
 
 
+def test_shared_gpu_grids_change_nothing(tmp_path):
+    """concurrent_contexts > 1 only resizes the persistent grids: every stage and
+    the image stay bit-identical, also for four contexts rendering at once."""
+    pod = _mesh_scene(tmp_path, "cornellSpaceship", 160, 90, 20000)
+    ref, _, nlive, _ = oracle.render(pod, abi.default_options(trig_mode=abi.TRIG_PORTABLE), 1, 8, 1)
+    compare_iteration(pod, {"concurrent_contexts": 4}, what="shared grids")
+    opt = abi.default_options(trig_mode=abi.TRIG_PORTABLE, concurrent_contexts=4)
+    rs = [api.Renderer(pod, opt) for _ in range(4)]
+    try:
+        for k, r in enumerate(rs):
+            r.render(k + 1, 2, 4)           # iterations k+1 and k+5, all four contexts in flight
+        total = np.zeros_like(ref)
+        parts = [r.read()[0] for r in rs]
+    finally:
+        for r in rs:
+            r.close()
+    # each context's two iterations are bit-exact; their sum differs from the sequential sum only by float order
+    for k, part in enumerate(parts):
+        one, *_ = oracle.render(pod, abi.default_options(trig_mode=abi.TRIG_PORTABLE), k + 1, 2, 4)
+        assert_same_bits(part, one, f"context {k}")
+        total += part
+    assert np.allclose(total, ref, rtol=1e-5, atol=1e-6)
+
+
 def test_strided_iterations_sum_to_the_sequential_image(tmp_path):
     """spp sharding: ranks rendering {1,3,5,..} and {2,4,6,..} add up to the
     sequential image within float summation order (1e-5 relative)."""
