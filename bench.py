@@ -50,7 +50,10 @@ if ROOT not in sys.path:
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of each kernel, from the committed `ncu --set full`
 # capture of this workload (profiles/, cold caches: an upper bound on the warm traffic)
-TRAFFIC = {}
+TRAFFIC = {  # bytes per launch, depth-1 launch of profiles/r01_final_ncu_depth1.md
+    "k_intersect_analytic": 30.76e6, "k_mesh_walk": 70.92e6, "k_mesh_walk_long": 20.69e6, "k_mesh_finish": 50.09e6,
+    "k_sort_material": 1.99e6, "k_shade_compact": 170.46e6,
+}
 
 METRIC = "Mpaths/s"
 SCENE = "cornellSpaceship"
@@ -426,6 +429,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "clocks": clocks,
             "roofline": {"kernel": dom, "bound": "hbm", "achieved": dom_gbs, "peak": peak, "unit": "GB/s",
                          "frac": dom_gbs / peak, "traffic": TRAFFIC.get(dom), "peak_source": peak_src,
+                         "traffic_note": "dram__bytes_read+write of the depth-1 launch under ncu --set full (cold caches); it "
+                                         "includes the scene traffic (BVH nodes, triangles, texels) that the algorithmic "
+                                         "bytes leave out (SURVEY.md 8d)",
                          "algorithmic_bytes_per_launch": dom_bytes / args.depth, "launches_per_step": args.depth,
                          "ms_per_launch": dom_ms / args.depth, "walks_per_step": n_walks, "long_walks_per_step": n_long,
                          "note": "dominant kernel by device time measured with CUDA events in this run; achieved = algorithmic "
