@@ -161,7 +161,7 @@ struct B2ptCtx {
   float4* long_best = nullptr;
   int2* long_stack = nullptr;
   int* long_n = nullptr;
-  int long_cap = 0;
+  int long_cap = 0, long_carry = kLongCarry;
   int shade_stride_grid = 0;
   int isect_grid = 0, analytic_grid = 0, sort_grid = 0, shade_grid = 0, gen_grid = 0;
   int* mesh_queue = nullptr;
@@ -652,6 +652,8 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mesh_walk_long, kCoopThreads, 0));
   c->long_grid = c->sm_count * std::max(occ, 1);
   if (const char* e = getenv("B2PT_LONG_WALK")) c->long_walk = std::max(atoi(e), 1);
+  if (const char* e = getenv("B2PT_LONG_CARRY")) c->long_carry = std::max(0, std::min(atoi(e), kLongCarry));  // tests: 0 = always restart at the root
+  if (const char* e = getenv("B2PT_LONG_CAP")) c->long_cap = std::max(1, std::min(atoi(e), c->long_cap));      // tests: a full hand-off queue
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_intersect_analytic, 256, 0));
   c->analytic_grid = (int)std::min<size_t>((P + 255) / 256, (size_t)c->sm_count * std::max(occ, 1) * 2);
   if (opt.concurrent_contexts > 1) {
@@ -823,6 +825,7 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
     ip.long_queue = c->long_queue;
     ip.long_walk = c->long_walk;
     ip.long_cap = c->long_cap;
+    ip.long_carry = c->long_carry;
     ip.long_best = c->long_best;
     ip.long_stack = c->long_stack;
     ip.long_n = c->long_n;

@@ -41,6 +41,7 @@ struct IsectParams {
   int2* long_queue;           // (ray, geom) walks that outgrew one lane (filled by k_mesh_walk)
   int long_walk;              // steps after which k_mesh_walk hands a walk to k_mesh_walk_long
   int long_cap;               // capacity of the hand-off queue
+  int long_carry;             // stack entries a hand-off may carry (<= kLongCarry; fewer only in tests)
   float4* long_best;          // [long_cap] (t, bu, bv, face) of the closest triangle found so far
   int2* long_stack;           // [long_cap][kLongCarry] carried traversal stack
   int* long_n;                // [long_cap] carried entries, -1: restart at the root

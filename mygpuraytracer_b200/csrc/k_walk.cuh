@@ -392,7 +392,7 @@ __global__ void __launch_bounds__(kWalkThreads, B2PT_WALK_MINBLOCKS) k_mesh_walk
           p.long_best[lq] = make_float4(tbest, bu, bv, __int_as_float(best));
           int2* ent = p.long_stack + (size_t)lq * kLongCarry;
           int ne = -1;
-          if (sp + 1 <= kLongCarry) {
+          if (sp + 1 <= p.long_carry) {
             for (int k = 0; k < sp; ++k) ent[k] = k < kWalkShort ? sst[k * kWalkThreads] : spill[k - kWalkShort];
             ent[sp] = make_int2(node, __float_as_int(0.0f));
             ne = sp + 1;

@@ -184,6 +184,31 @@ def test_first_bounce_cache_changes_nothing(tmp_path, scene_kind):
         assert_same_bits(r.read()[0], ref_aa, "cache ignored with AA on")
 
 
+@pytest.mark.parametrize("env", [
+    {"B2PT_LONG_WALK": "1"},                              # every walk finishes in the cooperative kernel
+    {"B2PT_LONG_WALK": "3", "B2PT_LONG_CARRY": "0"},      # ... restarting at the root, pruned by the carried hit
+    {"B2PT_LONG_WALK": "2", "B2PT_LONG_CAP": "64"},       # hand-off queue full: lanes keep walking
+    {"B2PT_LONG_WALK": "1000000"},                        # no hand-off at all
+])
+def test_long_walk_handoff_paths_bitexact(tmp_path, monkeypatch, env):
+    """The hand-off of long BVH walks (k_mesh_walk -> k_mesh_walk_long) must not
+    change a single bit whatever the threshold, carried-stack size or queue
+    capacity: closest-hit ids, uv, normals and everything downstream against the
+    oracle's brute-force loop."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    pod = _mesh_scene(tmp_path, "cornellSpaceship", 96, 54, 20000)
+    compare_iteration(pod, {}, what=f"long walk {env}")
+    with api.Renderer(pod, abi.default_options()) as r:
+        r.render(1, 1, 1)
+        walks, longs = int(r.walk_counts().sum()), int(r.walk_counts(True).sum())
+    assert walks > 500
+    if env["B2PT_LONG_WALK"] == "1":
+        assert longs > walks // 4
+    if env["B2PT_LONG_WALK"] == "1000000":
+        assert longs == 0
+
+
 def test_shared_gpu_grids_change_nothing(tmp_path):
     """concurrent_contexts > 1 only resizes the persistent grids: every stage and
     the image stay bit-identical, also for four contexts rendering at once."""
