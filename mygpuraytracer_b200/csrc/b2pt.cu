@@ -266,16 +266,29 @@ struct RadixTemps {
 
 static unsigned int g_radix_epoch = 1;
 
-// Sorts n pairs in place (result ends in key/val after four passes).
-static int radix_sort_pairs_dev(uint32_t* key, uint32_t* val, int n, cudaStream_t s, int64_t* launches) {
-  if (n <= 1) return 0;
-  RadixTemps t;
+static int radix_temps_alloc(RadixTemps* t, int n) {
   const int tiles = (n + kSortTile - 1) / kSortTile;
-  CK(cudaMalloc(&t.hist, 4 * 256 * sizeof(unsigned int)));
-  CK(cudaMalloc(&t.tickets, 4 * sizeof(unsigned int)));
-  CK(cudaMalloc(&t.status, (size_t)tiles * 256 * sizeof(unsigned long long)));
-  CK(cudaMalloc(&t.key_alt, (size_t)n * 4));
-  CK(cudaMalloc(&t.val_alt, (size_t)n * 4));
+  CK(cudaMalloc(&t->hist, 4 * 256 * sizeof(unsigned int)));
+  CK(cudaMalloc(&t->tickets, 4 * sizeof(unsigned int)));
+  CK(cudaMalloc(&t->status, (size_t)tiles * 256 * sizeof(unsigned long long)));
+  CK(cudaMalloc(&t->key_alt, (size_t)std::max(n, 1) * 4));
+  CK(cudaMalloc(&t->val_alt, (size_t)std::max(n, 1) * 4));
+  return 0;
+}
+static void radix_temps_free(RadixTemps* t) {
+  cudaFree(t->hist);
+  cudaFree(t->tickets);
+  cudaFree(t->status);
+  cudaFree(t->key_alt);
+  cudaFree(t->val_alt);
+  *t = RadixTemps();
+}
+
+// Sorts n pairs in place (result ends in key/val after four passes).  Asynchronous on `s`; the temporaries
+// must stay alive until the stream has run the passes.
+static int radix_sort_pairs_dev(uint32_t* key, uint32_t* val, int n, cudaStream_t s, int64_t* launches, const RadixTemps& t) {
+  if (n <= 1) return 0;
+  const int tiles = (n + kSortTile - 1) / kSortTile;
   CK(cudaMemsetAsync(t.hist, 0, 4 * 256 * sizeof(unsigned int), s));
   CK(cudaMemsetAsync(t.tickets, 0, 4 * sizeof(unsigned int), s));
   CK(cudaMemsetAsync(t.status, 0, (size_t)tiles * 256 * sizeof(unsigned long long), s));
@@ -299,12 +312,6 @@ static int radix_sort_pairs_dev(uint32_t* key, uint32_t* val, int n, cudaStream_
   }
   if (launches) *launches += 5;
   CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(s));
-  cudaFree(t.hist);
-  cudaFree(t.tickets);
-  cudaFree(t.status);
-  cudaFree(t.key_alt);
-  cudaFree(t.val_alt);
   return 0;
 }
 
@@ -353,6 +360,8 @@ static int build_mesh(B2ptCtx* c, const float* pos_host, const float* uv_host, i
   CK(cudaMalloc(&children, (size_t)std::max(n - 1, 1) * sizeof(int2)));
   CK(cudaMalloc(&parent, (size_t)(2 * n) * sizeof(int)));
   CK(cudaMalloc(&visit, (size_t)std::max(n - 1, 1) * sizeof(int)));
+  RadixTemps rtemps;  // allocated up front: build_ms below is device time, not cudaMalloc latency
+  if ((rc = radix_temps_alloc(&rtemps, n))) return rc;
 
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
@@ -363,7 +372,7 @@ static int build_mesh(B2ptCtx* c, const float* pos_host, const float* uv_host, i
   k_centroid_bounds<<<std::min(blocks, 1184), 256, 0, s>>>(out->face_pos, n, bounds);
   k_morton<<<blocks, 256, 0, s>>>(out->face_pos, n, bounds, code, val);
   c->launches += 3;
-  if ((rc = radix_sort_pairs_dev(code, val, n, s, &c->launches))) return rc;
+  if ((rc = radix_sort_pairs_dev(code, val, n, s, &c->launches, rtemps))) return rc;
   k_leaves<<<blocks, 256, 0, s>>>(out->face_pos, val, n, pad, out->tris, leaf_box);
   c->launches += 1;
   if (n >= 2) {
@@ -393,6 +402,7 @@ static int build_mesh(B2ptCtx* c, const float* pos_host, const float* uv_host, i
   cudaFree(children);
   cudaFree(parent);
   cudaFree(visit);
+  radix_temps_free(&rtemps);
   if (out->info.max_depth > 2 * (kWalkShort + kWalkSpill) / 3)
     return fail(B2PT_ERR_RANGE, "LBVH deeper than the traversal stack");
   return 0;
@@ -823,7 +833,9 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
     if (kt) kt->mark(1);
     ip.queue = c->mesh_queue;
     ip.long_queue = c->long_queue;
-    ip.long_walk = c->long_walk;
+    // With several meshes a ray can have more than one long walk, and k_mesh_walk_long folds them concurrently
+    // from the closest hit it read when it started: keep every walk in its lane then.
+    ip.long_walk = c->dscene.n_meshes > 1 ? 0x3fffffff : c->long_walk;
     ip.long_cap = c->long_cap;
     ip.long_carry = c->long_carry;
     ip.long_best = c->long_best;
@@ -1475,7 +1487,11 @@ extern "C" int b2pt_radix_sort_pairs_u32(int32_t n, uint32_t* keys_host, uint32_
   CK(S.get(&dv, (size_t)n));
   CK(cudaMemcpy(dk, keys_host, (size_t)n * 4, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(dv, vals_host, (size_t)n * 4, cudaMemcpyHostToDevice));
-  int rc = radix_sort_pairs_dev(dk, dv, n, 0, nullptr);
+  RadixTemps rt;
+  int rc = radix_temps_alloc(&rt, n);
+  if (rc == 0) rc = radix_sort_pairs_dev(dk, dv, n, 0, nullptr, rt);
+  if (rc == 0 && cudaStreamSynchronize(0) != cudaSuccess) rc = fail(B2PT_ERR_CUDA, "radix sort failed");
+  radix_temps_free(&rt);
   if (rc) return rc;
   CK(cudaMemcpy(keys_host, dk, (size_t)n * 4, cudaMemcpyDeviceToHost));
   CK(cudaMemcpy(vals_host, dv, (size_t)n * 4, cudaMemcpyDeviceToHost));

@@ -49,6 +49,12 @@ SCENES: Dict[str, dict] = {
                              objects=_BOX + [("sphere", 1, (-2, 7, -1), (0, 0, 0), (2, 2, 2)),
                                              ("sphere", 5, (1, 6, 0), (0, 0, 0), (2, 2, 2)), _SHIP]),
     "sphere": dict(file="sphere", materials=[_LIGHT], objects=[("sphere", 0, (0, 0, 0), (0, 0, 0), (3, 3, 3))]),
+    # NOT one of the reference's scenes: two OBJ geoms in one scene (the loader appends one material per OBJ,
+    # scene.cpp:221-231), the second one scaled by 1.5, so that its object-space distances (world / 1.5) compete with
+    # world-space ones exactly as the reference's mixed `min` does.  Used by the parity tests of the several-meshes path.
+    "twoShips": dict(file="cornell", materials=[_LIGHT, _WHITE, _RED, _GREEN, _MIRROR, _GLASS],
+                     objects=_BOX + [("sphere", 5, (1, 6, 0), (0, 0, 0), (2, 2, 2)), _SHIP,
+                                     ("obj", None, (-2, 6.5, -2), (30, 0, 10), (1.5, 1.5, 1.5))]),
 }
 
 

@@ -102,6 +102,24 @@ def test_mesh_scenes_bvh_bitexact(tmp_path, name, tris):
     assert (pod.geoms["type"][np.maximum(d0.geom, 0)][d0.t > 0] == abi.OBJ).sum() > 20, "mesh must be visible"
 
 
+@pytest.mark.parametrize("tris,env", [(1000, {}), (20000, {}), (20000, {"B2PT_LONG_WALK": "2"})])
+def test_two_meshes_one_scaled_bitexact(tmp_path, monkeypatch, tris, env):
+    """Two OBJ geoms, the second scaled by 1.5 (not rigid: its object-space
+    distances compete with world-space ones exactly as in the reference,
+    SURVEY.md Q8): a lane walks the meshes of its ray one after the other;
+    every stage identical to the oracle's loop over geoms and faces."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    pod = _mesh_scene(tmp_path, "twoShips", 96, 54, tris)
+    assert int((pod.geoms["type"] == abi.OBJ).sum()) == 2
+    compare_iteration(pod, {}, what=f"twoShips/{tris}")
+    d0 = oracle.intersect(pod, oracle.generate(pod, abi.default_options(), 1).origin,
+                          oracle.generate(pod, abi.default_options(), 1).dir)
+    hit_geoms = set(int(g) for g in d0.geom[d0.t > 0])
+    obj_ids = [int(i) for i in np.nonzero(pod.geoms["type"] == abi.OBJ)[0]]
+    assert all(g in hit_geoms for g in obj_ids), "both meshes must be visible"
+
+
 def test_bvh_equals_brute_force_at_full_size(tmp_path):
     """Size-independent property at BASELINE.json's full size: at 1920x1080
     with the 250k-triangle stand-in mesh, the BVH kernel and the brute-force
