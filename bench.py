@@ -226,6 +226,30 @@ def reference_gpu(root: str, args):
         return {"error": f"timed out after {args.ref_gpu_timeout}s"}
 
 
+def reference_host_adapter(root: str, args, iters: int):
+    """The reference's own host code (Scene, scene.cpp, the pathtrace() call loop of main.cpp) linked with
+    integration/pathtrace_b2pt.cpp + libb2pt.so instead of apps/src/pathtrace.cu (oracle/_ref/ref_adapter)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_adapter")
+    if not os.access(exe, os.X_OK):
+        return None
+    from mygpuraytracer_b200 import assets
+
+    scene_txt = assets.scene_file(SCENE, args.width, args.height, depth=args.depth, root=root)
+    try:
+        p = subprocess.run([exe, "--scene", scene_txt, "--iters", str(iters)], cwd=os.path.join(root, "bin"),
+                           capture_output=True, text=True, timeout=300)
+        for line in p.stdout.splitlines():
+            if line.startswith("REF_ADAPTER_RESULT"):
+                r = json.loads(line.split(" ", 1)[1])
+                return {"what": "reference host code (scene.cpp loader + the pathtrace() loop of main.cpp:245-264) calling "
+                                "integration/pathtrace_b2pt.cpp -> libb2pt.so; state.image / state.albedo on the host after every call",
+                        "iterations": r["iters"], "ms_per_call": r["call_ms_per_iter"],
+                        "timer_ms_per_call": r["timer_ms_per_iter"], "mpaths_per_s": r["mpaths_per_s_call"]}
+        return {"error": (p.stderr or p.stdout)[-300:]}
+    except subprocess.TimeoutExpired:
+        return {"error": "timed out"}
+
+
 # ---------------------------------------------------------------------------------------
 # arms
 # ---------------------------------------------------------------------------------------
@@ -453,6 +477,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             rg = reference_gpu(root, args)
             if rg is not None:
                 line["reference_gpu"] = rg
+            ra = reference_host_adapter(root, args, max(20, min(K, 200)))
+            if ra is not None:
+                line["e2e_reference_host"] = ra
         emit(line)
     for x in rs + [r_e2e]:
         x.close()

@@ -78,7 +78,7 @@ def run(binary: str, scene_txt: str, out_dir: Optional[str] = None, b2s: Optiona
     if p.returncode != 0:
         raise RuntimeError(f"{binary} failed ({p.returncode}):\n{p.stdout[-2000:]}\n{p.stderr[-2000:]}")
     for line in p.stdout.splitlines():
-        m = re.match(r"REF_(CPU|GPU)_RESULT (\{.*\})", line)
+        m = re.match(r"REF_(CPU|GPU|ADAPTER)_RESULT (\{.*\})", line)
         if m:
             return json.loads(m.group(2))
     return {}

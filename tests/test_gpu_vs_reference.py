@@ -113,3 +113,22 @@ def test_default_build_of_the_reference_statistical(tmp_path):
           f"{int((~same_geom).sum())} depth-0 id flips")
     assert close > 0.97
     assert p >= 50.0
+
+
+@pytest.mark.parametrize("scene,w,h,tris", [("cornellGlass", 160, 120, None), ("cornellSpaceship", 128, 72, 1000)])
+def test_reference_host_code_through_the_adapter(tmp_path, scene, w, h, tris):
+    """The drop-in itself: oracle/_ref/ref_adapter is the reference's OWN host code
+    (Scene, scene.cpp, pathtrace.h, the call order of main.cpp:245-261) linked with
+    integration/pathtrace_b2pt.cpp + libb2pt.so INSTEAD of apps/src/pathtrace.cu.
+    scene->state.image / .albedo after 4 pathtrace() calls must be bit-identical
+    to what the reference's own pathtrace.cu (ref_gpu_strict) leaves there."""
+    need("ref_gpu_strict")
+    need("ref_adapter")
+    pod, ref = run_reference("ref_gpu_strict", scene, w, h, 4, 1, tmp_path, tris)
+    txt = str(tmp_path / f"{scene}.txt")
+    out = str(tmp_path / "out_adapter")
+    res = harness.run("ref_adapter", txt, out, iters=4)
+    got = harness.load_dump(out)
+    assert_same_bits(got["image"], ref["image"], "state.image through the adapter")
+    assert_same_bits(got["albedo"], ref["albedo"], "state.albedo through the adapter")
+    assert res["iters"] == 4 and res["timer_ms_per_iter"] > 0.0, "timer() still reports the GPU time of a call"
