@@ -91,12 +91,17 @@ def emit(line: dict):
 # ---------------------------------------------------------------------------------------
 # workload
 # ---------------------------------------------------------------------------------------
-def prepare_assets(triangles: int):
+def prepare_assets(triangles: int, write: bool = True):
+    """The run tree (scene files, stand-in mesh, textures).  Only ONE process may create / repoint it
+    (write=True, rank 0); the other ranks look at the finished tree after a barrier."""
     from mygpuraytracer_b200 import assets
 
-    ref_tex = os.path.join(ROOT, "oracle", "_ref", "run", "textures")
-    root = assets.prepare(reference_textures=ref_tex if os.path.isdir(ref_tex) else None)
-    assets.set_mesh(root, triangles)
+    if write:
+        ref_tex = os.path.join(ROOT, "oracle", "_ref", "run", "textures")
+        root = assets.prepare(reference_textures=ref_tex if os.path.isdir(ref_tex) else None)
+        assets.set_mesh(root, triangles)
+    else:
+        root = assets.DEFAULT_ROOT
     return root, ("reference JPEGs" if assets.textures_are_reference(root) else "procedural 4096x4096 (reference JPEGs absent)")
 
 
@@ -293,14 +298,17 @@ def run_ours(args, rank: int, world: int, local_rank: int):
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
+    scene_txt = None
     if rank == 0:
         root, textures = prepare_assets(args.triangles)
+        scene_txt = assets.scene_file(SCENE, args.width, args.height, depth=args.depth, root=root)
     if dist:
         dist.barrier()
     if rank != 0:
-        root, textures = prepare_assets(args.triangles)
+        root, textures = prepare_assets(args.triangles, write=False)
+        scene_txt = os.path.join(root, "scenes", f"{SCENE}_{args.width}x{args.height}_d{args.depth}.txt")
     t0 = time.time()
-    scene = api.Scene(assets.scene_file(SCENE, args.width, args.height, depth=args.depth, root=root))
+    scene = api.Scene(scene_txt)
     load_s = time.time() - t0
     pod = scene.pod
     n_tris = len(pod.face_pos)
