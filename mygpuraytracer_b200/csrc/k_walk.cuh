@@ -29,30 +29,15 @@
 
 namespace b2pt {
 
-#ifndef B2PT_WALK_THREADS
-#define B2PT_WALK_THREADS 256
-#endif
-#ifndef B2PT_WALK_MINBLOCKS
-#define B2PT_WALK_MINBLOCKS 3
-#endif
-#ifndef B2PT_REFILL_MIN
-#define B2PT_REFILL_MIN 8
-#endif
-#ifndef B2PT_WALK_PREFETCH
-#define B2PT_WALK_PREFETCH 0
-#endif
-constexpr int kWalkThreads = B2PT_WALK_THREADS;
+constexpr int kWalkThreads = 256;
+constexpr int kWalkMinBlocks = 3;  // resident CTAs per SM the register budget is set for
 constexpr int kWalkShort = 8;    // (node, tn) entries per lane in shared memory
 constexpr int kWalkSpill = 88;   // spill entries per lane: 96 in all = 3 per level of a 32-level wide tree
-constexpr int kRefillMin = B2PT_REFILL_MIN;    // idle lanes that trigger a refill
+constexpr int kRefillMin = 8;    // idle lanes that trigger a refill
 constexpr int kLongCarry = 32;  // stack entries a long walk carries over to k_mesh_walk_long
 constexpr int kWalkDone = 0x7fffffff;
 constexpr int kNoGeom = 0x7fffffff;
 
-
-#ifndef B2PT_NODE_LOAD256
-#define B2PT_NODE_LOAD256 0
-#endif
 
 // Box test of the four children of a wide node with one FMA per plane.
 // The ray keeps id = 1/d and noid = -(o * id).  A node stores, per axis, the four
@@ -63,7 +48,6 @@ constexpr int kNoGeom = 0x7fffffff;
 // needs no min/max between the two planes of an axis:
 //     tn = max(near.x*id.x + noid.x, near.y*.., near.z*.., 0)
 //     tf = min(far.x*id.x + noid.x,  far.y*..,  far.z*..,  lim)
-// (B2PT_NODE_LOAD256: three 256-bit loads fetch the pairs and min/max orders them.)
 // Rounding: id is 1/d to ~1 ulp (MUFU.RCP), o*id is rounded once and the FMA once;
 // together that displaces each plane by at most ~2^-21 * max(|o|, |plane|) in
 // position space whatever the size of id.  The build pads every box by 2^-19 *
@@ -75,32 +59,8 @@ struct WideHit {
   float tn[4];
   bool ok[4];
 };
-__device__ __forceinline__ void ldg256(const void* p, float4* a, float4* b) {
-  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=f"(a->x), "=f"(a->y), "=f"(a->z), "=f"(a->w), "=f"(b->x), "=f"(b->y), "=f"(b->z), "=f"(b->w)
-               : "l"(p));
-}
 __device__ __forceinline__ void wide_slab_fma(const float4* node, int offx, int offy, int offz, V3 id, V3 noid, float lim,
                                               WideHit* h, float4* cf) {
-#if B2PT_NODE_LOAD256
-  float4 ax, bx, ay, by, az, bz;
-  ldg256(node, &ax, &bx);
-  ldg256(node + 2, &ay, &by);
-  ldg256(node + 4, &az, &bz);
-  *cf = __ldg(node + 6);
-#define B2PT_ONE(k, c)                                                                                         \
-  {                                                                                                            \
-    const float x0 = fmaf(ax.c, id.x, noid.x), x1 = fmaf(bx.c, id.x, noid.x);                                  \
-    const float y0 = fmaf(ay.c, id.y, noid.y), y1 = fmaf(by.c, id.y, noid.y);                                  \
-    const float z0 = fmaf(az.c, id.z, noid.z), z1 = fmaf(bz.c, id.z, noid.z);                                  \
-    const float a = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));                    \
-    const float b = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), lim));                     \
-    h->tn[k] = a;                                                                                              \
-    h->ok[k] = a <= b;                                                                                         \
-  }
-  B2PT_ONE(0, x) B2PT_ONE(1, y) B2PT_ONE(2, z) B2PT_ONE(3, w)
-#undef B2PT_ONE
-#else
   const char* nb = reinterpret_cast<const char*>(node);
   const float4 nx = __ldg(reinterpret_cast<const float4*>(nb + offx));
   const float4 fx = __ldg(reinterpret_cast<const float4*>(nb + (offx ^ 16)));
@@ -120,7 +80,6 @@ __device__ __forceinline__ void wide_slab_fma(const float4* node, int offx, int 
   }
   B2PT_ONE(0, x) B2PT_ONE(1, y) B2PT_ONE(2, z) B2PT_ONE(3, w)
 #undef B2PT_ONE
-#endif
 }
 __device__ __forceinline__ void slab_offsets(V3 id, int* offx, int* offy, int* offz) {
   *offx = id.x >= 0.0f ? 0 : 16;
@@ -131,7 +90,7 @@ __device__ __forceinline__ void slab_offsets(V3 id, int* offx, int* offy, int* o
 __device__ __forceinline__ bool walk_is_inner(int node) { return (unsigned int)node < 0x40000000u; }
 
 template <bool STATS>
-__global__ void __launch_bounds__(kWalkThreads, B2PT_WALK_MINBLOCKS) k_mesh_walk(IsectParams p) {
+__global__ void __launch_bounds__(kWalkThreads, kWalkMinBlocks) k_mesh_walk(IsectParams p) {
   __shared__ DevGeom sgeom[kMaxGeoms];
   __shared__ int shist[kMaxMaterials];
   __shared__ int slive[kMaxMaterials];
@@ -452,10 +411,7 @@ __global__ void __launch_bounds__(kWalkThreads, B2PT_WALK_MINBLOCKS) k_mesh_walk
 // (depth-first, growth <= 3 per level).  The loop is warp-uniform: the four
 // groups of a warp run their rounds in lockstep and refill independently.
 constexpr int kCoopThreads = 128;
-#ifndef B2PT_COOP_GROUP
-#define B2PT_COOP_GROUP 16
-#endif
-constexpr int kCoopGroup = B2PT_COOP_GROUP;
+constexpr int kCoopGroup = 16;
 constexpr int kCoopCap = 32 * kCoopGroup;                        // stack entries per group (32 KB per CTA in all)
 constexpr int kCoopDfs = kCoopCap - 96 - 3 * kCoopGroup;         // above this only one entry per round is taken
 constexpr unsigned int kCoopMask = kCoopGroup == 32 ? 0xffffffffu : ((1u << (kCoopGroup & 31)) - 1u);
