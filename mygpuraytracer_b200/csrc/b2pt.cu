@@ -703,13 +703,16 @@ extern "C" void b2pt_destroy(B2ptCtx* c) {
       if (!s[0]) continue;
       fprintf(stderr, "[b2pt traversal] depth %d: %llu walks, nodes/walk %.1f (max %llu), tris/walk %.1f (max %llu), log2 hist:",
               d, s[0], (double)s[1] / s[0], s[3], (double)s[2] / s[0], s[4]);
-      for (int k = 0; k < 16; ++k) fprintf(stderr, " %llu", s[5 + k]);
+      for (int k = 0; k < 13; ++k) fprintf(stderr, " %llu", s[5 + k]);
       fprintf(stderr, "\n");
       if (s[21])
         fprintf(stderr, "[b2pt traversal]   per warp: %llu warps, loop iterations avg %.1f max %llu, cycles avg %.0f max %llu, "
                         "refills avg %.1f (%.0f cycles each), prologue %.0f cycles, lanes per node step %.1f\n",
                 s[21], (double)s[22] / s[21], s[23], (double)s[24] / s[21], s[25], (double)s[26] / s[21],
                 s[26] ? (double)s[27] / s[26] : 0.0, (double)s[28] / s[21], s[30] ? (double)s[29] / s[30] : 0.0);
+      if (s[21])
+        fprintf(stderr, "[b2pt traversal]   cycles per node step %.0f (%llu steps), per leaf step %.0f (%llu steps), hand-off check %.0f per iteration\n",
+                s[30] ? (double)s[31] / s[30] : 0.0, s[30], s[19] ? (double)s[20] / s[19] : 0.0, s[19], s[22] ? (double)s[18] / s[22] : 0.0);
     }
   }
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);

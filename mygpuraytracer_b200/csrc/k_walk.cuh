@@ -101,7 +101,8 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkMinBlocks) k_mesh_walk(Isec
   const unsigned int total = p.ctr->mesh_count[p.depth];
   if (total == 0) return;
   const long long clk_start = STATS ? clock64() : 0;
-  long long clk_loop = 0, clk_refill = 0;
+  long long clk_loop = 0, clk_refill = 0, clk_node = 0, clk_leaf = 0, clk_handoff = 0;
+  unsigned int w_leaf_iters = 0;
   unsigned int w_iters = 0, w_refills = 0, w_node_iters = 0, w_node_lanes = 0;
   unsigned int a_walks = 0, a_nodes = 0, a_tris = 0, a_maxn = 0, a_maxt = 0;
   __shared__ unsigned long long sstat[32];  // per-CTA copy of p.stats, flushed once
@@ -283,7 +284,9 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkMinBlocks) k_mesh_walk(Isec
     // One kind of step per iteration, whichever has more lanes waiting: a NODE step (the four child boxes of
     // every lane's inner node) or a LEAF step (the exact triangle test), so the two code paths never
     // serialise inside one iteration.
-    if (__popc(nm) >= __popc(lm)) {
+    const long long clk_step = STATS ? clock64() : 0;
+    const bool node_step = __popc(nm) >= __popc(lm);
+    if (node_step) {
       if (can_node) {
         if (STATS) ++n_nodes;
         WideHit wh;
@@ -334,6 +337,12 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkMinBlocks) k_mesh_walk(Isec
         ++steps;
       }
     }
+    if (STATS) {
+      __syncwarp();
+      const long long dt = clock64() - clk_step;
+      if (node_step) clk_node += dt; else { clk_leaf += dt; ++w_leaf_iters; }
+    }
+    const long long clk_hand = STATS ? clock64() : 0;
     // A walk that outgrew its lane is handed to k_mesh_walk_long together with its state: the closest hit so
     // far and the traversal stack plus what the lane was about to do (up to kLongCarry entries; more restarts
     // at the root, still pruned by the carried hit).  One atomic per warp; if the hand-off queue is full the
@@ -364,6 +373,7 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkMinBlocks) k_mesh_walk(Isec
         }
       }
     }
+    if (STATS) clk_handoff += clock64() - clk_hand;
   }
 #undef B2PT_WALK_PUSH
 #undef B2PT_WALK_POP_NEXT
@@ -385,6 +395,10 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkMinBlocks) k_mesh_walk(Isec
       atomicAdd(&sstat[28], (unsigned long long)(clk_loop - clk_start));
       atomicAdd(&sstat[29], (unsigned long long)w_node_lanes);
       atomicAdd(&sstat[30], (unsigned long long)w_node_iters);
+      atomicAdd(&sstat[31], (unsigned long long)clk_node);
+      atomicAdd(&sstat[20], (unsigned long long)clk_leaf);
+      atomicAdd(&sstat[19], (unsigned long long)w_leaf_iters);
+      atomicAdd(&sstat[18], (unsigned long long)clk_handoff);
     }
   }
   __syncthreads();
