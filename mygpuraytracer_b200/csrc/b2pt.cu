@@ -7,9 +7,11 @@
 //   k_iter_begin                       (iteration number and counters live on the device)
 //   k_generate                         generateRayFromCamera
 //   for d in 0 .. depth-1:
-//     k_intersect<d>                   memset + computeIntersections + sort-key extraction + histogram
-//     k_onesweep_pass<MaterialSort,d>  thrust::sort_by_key  -> 4-byte permutation only
-//     k_shade_compact<d>               shadeFakeMaterial + stable_partition + finalGather
+//     k_intersect_analytic             memset + computeIntersections (cubes, spheres) + sort key + histograms
+//     k_mesh_walk, k_mesh_walk_long,   computeIntersections (OBJ geoms): LBVH walk, long walks, record completion
+//     k_mesh_finish
+//     k_sort_material                  thrust::sort_by_key  -> 4-byte permutation + compaction ranks
+//     k_shade_compact                  shadeFakeMaterial + stable_partition + finalGather
 //
 // Every kernel reads its element count from device memory, so the sequence is
 // identical for every iteration and is captured once into a CUDA graph.

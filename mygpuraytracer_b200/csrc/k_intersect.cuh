@@ -1,23 +1,22 @@
-// k_intersect.cuh -- closest hit (computeIntersections, apps/src/pathtrace.cu:303-386).
+// k_intersect.cuh -- closest hit (computeIntersections, apps/src/pathtrace.cu:303-386): the analytic geoms.
 //
-// Persistent kernel: the grid is sized to the machine (SMs x resident CTAs),
-// each warp claims 32 rays at a time from a device ticket and keeps going
-// until the live range [0, n_live[depth]) is exhausted, so the cost of a few
-// long BVH walks is spread over the whole chip.  Analytic geoms (cubes,
-// spheres) are staged in shared memory once per CTA; OBJ geoms are walked
-// through their LBVH (k_lbvh.cuh) with a per-thread short stack in shared
-// memory that spills to local memory.
+//  k_intersect_analytic    one thread per ray against the cubes and spheres (staged in shared memory once per
+//                          CTA): a cheap padded world-box pre-test, then the reference's exact tests; writes the
+//                          hit record, the sort key, the survival flag and the material histograms, and queues
+//                          the rays that may hit a mesh for k_walk.cuh.
+//  k_intersect_mesh_brute  validation only (use_bvh = 0): the reference's loop over every face.
+// Shared device functions: the exact cube / sphere / triangle tests, the texel fetch, the mesh part of a hit
+// record (uv, normals, bump map).
 //
 // Parity rules:
-//  * the BVH only prunes.  Boxes are inflated at build time and the slab test
-//    is conservative; the leaf test is glm::intersectRayTriangle exactly
-//    (gtx/intersect.inl:44-73) followed by t = distance(p, origin) in object
-//    space (apps/src/intersections.h:219-223);
-//  * ties are resolved as the reference's strict `<` loops do: lowest face id
-//    within a mesh (intersections.h:223), lowest geom id across geoms
-//    (pathtrace.cu:360);
-//  * per-geom work that only the winner needs (normals, uv, the bump texel)
-//    is deferred until the closest geom is known; the values are identical.
+//  * pre-tests only prune: boxes are padded and the slab tests are conservative; what decides is the
+//    reference's arithmetic, evaluated in glm's operation order without FMA contraction (pt_math.cuh);
+//  * the mesh leaf test is glm::intersectRayTriangle exactly (gtx/intersect.inl:44-73) followed by
+//    t = distance(p, origin) in object space (apps/src/intersections.h:219-223);
+//  * ties are resolved as the reference's strict `<` loops do: lowest face id within a mesh
+//    (intersections.h:223), lowest geom id across geoms (pathtrace.cu:360);
+//  * per-geom work that only the winner needs (normals, uv, the bump texel) is deferred until the closest
+//    geom is known; the values are identical.
 #pragma once
 
 #include <float.h>

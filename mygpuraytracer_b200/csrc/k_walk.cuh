@@ -17,6 +17,11 @@
 //                 time without touching memory.
 //                 The winner's (t, barycentrics, face, geom) goes straight into
 //                 the ray's hit record; key and material histogram are patched.
+//                 A walk of more than `long_walk` steps is handed off with its
+//                 state (closest hit, stack) so that it cannot hold its CTA.
+//  k_mesh_walk_long  The handed-off walks, 16 lanes per ray: the lanes of a group
+//                 take the top entries of a shared stack each round, reduce the
+//                 closest (t, face) and append the surviving children by a scan.
 //  k_mesh_finish  One thread per queued ray, full warps: rays the mesh won get
 //                 their uv, geometric normal, bump-mapped normal and survival
 //                 flag (intersections.h:226,235-279, interactions.h:171-186).
