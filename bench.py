@@ -51,8 +51,8 @@ if ROOT not in sys.path:
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of each kernel, from the committed `ncu --set full`
 # capture of this workload (profiles/, cold caches: an upper bound on the warm traffic)
 TRAFFIC = {  # bytes per launch, depth-1 launch of profiles/r01_final_ncu_depth1.md
-    "k_intersect_analytic": 30.76e6, "k_mesh_walk": 70.92e6, "k_mesh_walk_long": 20.69e6, "k_mesh_finish": 50.09e6,
-    "k_sort_material": 1.99e6, "k_shade_compact": 170.46e6,
+    "k_intersect_analytic": 31.24e6, "k_mesh_walk": 71.61e6, "k_mesh_walk_long": 20.69e6, "k_mesh_finish": 50.24e6,
+    "k_sort_material": 1.99e6, "k_shade_compact": 169.64e6,
 }
 
 METRIC = "Mpaths/s"
