@@ -308,6 +308,49 @@ def test_edge_cases(tmp_path):
     compare_iteration(pod, {}, iters=(1, 2), what="1x1")
 
 
+def test_many_geoms_and_materials(tmp_path):
+    """Capacity corners: 64 geoms (the shared-memory staging and the 64-bit
+    candidate mask of k_intersect_analytic) and 200 materials of all four BSDF
+    kinds (200 populated bins in the one-pass material sort, look-back per bin)."""
+    rng = np.random.default_rng(7)
+    mats = [scenes._LIGHT]
+    for i in range(199):
+        kind = i % 4
+        rgb = tuple(float(x) for x in rng.uniform(0.2, 0.95, 3).round(3))
+        if kind == 0:
+            mats.append((rgb, 0, (0, 0, 0), 0, 0, 0, 0))                      # diffuse
+        elif kind == 1:
+            mats.append((rgb, 0, rgb, 1, 0, 0, 0))                            # mirror
+        elif kind == 2:
+            mats.append((rgb, 0, rgb, 0, 1, round(float(rng.uniform(1.2, 1.8)), 2), 0))  # glass
+        else:
+            mats.append((rgb, 0, (0, 0, 0), 0, 0, 0, round(float(rng.uniform(0.5, 3.0)), 2)))  # small emitters
+    objs = list(scenes._BOX)
+    for i in range(58):
+        kind = "sphere" if i % 2 else "cube"
+        pos = tuple(float(x) for x in (rng.uniform(-4, 4), rng.uniform(0.5, 9), rng.uniform(-4, 4)))
+        rot = tuple(float(x) for x in rng.uniform(0, 90, 3).round(1))
+        scl = tuple(float(x) for x in rng.uniform(0.4, 1.3, 3).round(2))
+        objs.append((kind, int(rng.integers(1, 200)), tuple(round(v, 2) for v in pos), rot, scl))
+    assert len(objs) == 64
+    scenes.SCENES["_capacity"] = dict(file="cornell", materials=mats, objects=objs)
+    try:
+        pod = api.Scene(scenes.write_scene("_capacity", str(tmp_path / "cap.txt"), width=96, height=64)).pod
+    finally:
+        del scenes.SCENES["_capacity"]
+    assert len(pod.geoms) == 64 and len(pod.materials) == 200
+    compare_iteration(pod, {}, iters=(1, 2), what="64 geoms / 200 materials")
+    compare_iteration(pod, {"sort_by_material": 0}, iters=(1,), what="64 geoms, no sort")
+    # one geom too many is refused, not truncated
+    scenes.SCENES["_over"] = dict(file="cornell", materials=mats, objects=objs + [objs[-1]])
+    try:
+        over = api.Scene(scenes.write_scene("_over", str(tmp_path / "over.txt"), width=8, height=8)).pod
+    finally:
+        del scenes.SCENES["_over"]
+    with pytest.raises(api.B2ptError):
+        api.Renderer(over)
+
+
 def test_invalid_scenes_are_rejected():
     pod, *_ = load_golden("cornell_32x32")
     bad = pod.copy()
