@@ -517,7 +517,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "kernel_ms_per_step": prof,
             "kernel_ms_per_step_full_width": prof_full,
             "kernel_ms_note": "CUDA events around every launch of one iteration run alone: with the grids of the timed "
-                              "region (contexts share the SMs) and with the full-width grids of the e2e context",
+                              "region (contexts share the SMs) and with the full-width grids of the e2e context, where "
+                              "the analytic intersection is fused into generate / shade (k_generate_trace, k_shade_trace)",
             "segments_per_step": segments, "live_paths_per_depth": [int(x) for x in live[: args.depth + 1]],
             "bvh": {"triangles": int(bvh.n_faces), "nodes": int(bvh.n_nodes), "max_depth": int(bvh.max_depth),
                     "build_ms": float(bvh.build_ms)},

@@ -35,6 +35,7 @@
 #include "k_shade.cuh"
 #include "k_sort.cuh"
 #include "k_walk.cuh"
+#include "k_fused.cuh"
 #include "host/png_writer.h"
 #include "pt_device.cuh"
 
@@ -126,9 +127,10 @@ struct B2ptCtx {
   GenParams gen{};
 
   PathBuf buf[2]{};
-  HitBuf hits{};
-  uint8_t* key = nullptr;
-  uint8_t* live = nullptr;
+  HitBuf hits[2]{};        // hit records, sort keys and survival flags of depth d live in buffer d & 1:
+  uint8_t* key[2]{};       // the fused shade kernel writes those of depth d+1 while it reads those of depth d
+  uint8_t* live[2]{};
+  bool fuse = true;        // analytic intersection fused into generate / shade (k_fused.cuh)
   int* perm = nullptr;
   int* apos = nullptr;
   unsigned long long* sort_status_live = nullptr;
@@ -164,7 +166,7 @@ struct B2ptCtx {
   int2* long_stack = nullptr;
   int* long_n = nullptr;
   int long_cap = 0, long_carry = kLongCarry;
-  int shade_stride_grid = 0;
+  int shade_stride_grid = 0, gen_trace_grid = 0;
   int isect_grid = 0, analytic_grid = 0, sort_grid = 0, shade_grid = 0, gen_grid = 0;
   int* mesh_queue = nullptr;
   cudaEvent_t ev_loop_a = nullptr, ev_loop_b = nullptr;
@@ -599,11 +601,13 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
     if ((rc = c->dalloc(&c->buf[b].s1, P))) return rc;
     if ((rc = c->dalloc(&c->buf[b].s2, P))) return rc;
   }
-  if ((rc = c->dalloc(&c->hits.h0, P))) return rc;
-  if ((rc = c->dalloc(&c->hits.h1, P))) return rc;
-  if ((rc = c->dalloc(&c->key, P))) return rc;
+  for (int b = 0; b < 2; ++b) {
+    if ((rc = c->dalloc(&c->hits[b].h0, P))) return rc;
+    if ((rc = c->dalloc(&c->hits[b].h1, P))) return rc;
+    if ((rc = c->dalloc(&c->key[b], P))) return rc;
+    if ((rc = c->dalloc(&c->live[b], P))) return rc;
+  }
   if ((rc = c->dalloc(&c->perm, P))) return rc;
-  if ((rc = c->dalloc(&c->live, P))) return rc;
   if ((rc = c->dalloc(&c->apos, P))) return rc;
   if ((rc = c->dalloc(&c->mesh_queue, P))) return rc;
   c->long_cap = (int)std::max<size_t>(P / 4, 4096);
@@ -661,8 +665,13 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
   if (const char* e = getenv("B2PT_WALK_CTAS")) c->walk_grid = c->sm_count * std::max(1, std::min(atoi(e), std::max(occ, 1)));
   c->finish_grid = c->sm_count * 8;
   c->shade_stride_grid = c->sm_count * 12;
+  c->gen_trace_grid = (int)std::min<size_t>((P + 255) / 256, (size_t)c->sm_count * 8);
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mesh_walk_long, kCoopThreads, 0));
   c->long_grid = c->sm_count * std::max(occ, 1);
+  // the fused kernels shorten the chain of one context (1.435 -> 1.39 ms) but cost 2 % of aggregate throughput
+  // when several contexts share the GPU (their two phases serialise inside a CTA)
+  c->fuse = opt.concurrent_contexts <= 1;
+  if (const char* e = getenv("B2PT_FUSE")) c->fuse = atoi(e) != 0;
   if (const char* e = getenv("B2PT_LONG_WALK")) c->long_walk = std::max(atoi(e), 1);
   if (const char* e = getenv("B2PT_LONG_CARRY")) c->long_carry = std::max(0, std::min(atoi(e), kLongCarry));  // tests: 0 = always restart at the root
   if (const char* e = getenv("B2PT_LONG_CAP")) c->long_cap = std::max(1, std::min(atoi(e), c->long_cap));      // tests: a full hand-off queue
@@ -766,8 +775,11 @@ __global__ void k_first_bounce_hist(Counters* ctr, unsigned int* saved, int n_pa
 }
 
 template <int TRIG>
-static void launch_generate(B2ptCtx* c) {
-  k_generate<TRIG><<<c->gen_grid, 256, 0, c->stream>>>(c->gen, c->iter_state, c->buf[0]);
+static void launch_generate(B2ptCtx* c, const IsectParams* next) {
+  if (next)
+    k_generate_trace<TRIG><<<c->gen_trace_grid, 256, 0, c->stream>>>(c->gen, c->iter_state, c->buf[0], *next);
+  else
+    k_generate<TRIG><<<c->gen_grid, 256, 0, c->stream>>>(c->gen, c->iter_state, c->buf[0]);
 }
 
 template <int TRIG, bool RECORD>
@@ -805,7 +817,28 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
   const int slots = c->loop_depth + 1;
   k_iter_begin<<<8, 256, 0, s>>>(c->ctr, c->iter_state, c->P, slots);
   if (kt) kt->mark(0);
-  if (c->opt.trig_mode == B2PT_TRIG_PORTABLE) launch_generate<1>(c); else launch_generate<0>(c);
+  // Fused form (k_fused.cuh): the kernel that produces the rays of depth d+1 also intersects them with the
+  // analytic geoms.  Not when the records are read back between the stages, without the compaction ranks of
+  // the material sort, or for the depth whose hits the first-bounce cache keeps.
+  const bool fused = c->fuse && !record && c->opt.sort_by_material;
+  auto next_params = [&](int depth) {
+    IsectParams np;
+    memset(&np, 0, sizeof np);
+    np.scene = c->dscene;
+    np.out = c->hits[depth & 1];
+    np.key = c->key[depth & 1];
+    np.live = c->live[depth & 1];
+    np.ctr = c->ctr;
+    np.depth = depth;
+    np.queue = c->mesh_queue;
+    return np;
+  };
+  const bool fused_gen = fused && !c->fb_enabled;
+  {
+    const IsectParams np = next_params(0);
+    if (c->opt.trig_mode == B2PT_TRIG_PORTABLE) launch_generate<1>(c, fused_gen ? &np : nullptr);
+    else launch_generate<0>(c, fused_gen ? &np : nullptr);
+  }
   c->launches += 2;
   if (time_loop) CK(cudaEventRecordWithFlags(c->ev_loop_a, s, capturing ? cudaEventRecordExternal : cudaEventRecordDefault));
   if (record) c->records.assign(c->loop_depth, StageRecord());
@@ -823,9 +856,10 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
       CK(cudaMemcpy(R->in_s2.data(), in.s2, (size_t)n * 16, cudaMemcpyDeviceToHost));
     }
     const bool fb = c->fb_enabled && d == 0;
-    const HitBuf hits_d = fb ? c->fb_hits : c->hits;
-    uint8_t* const key_d = fb ? c->fb_key : c->key;
-    uint8_t* const live_d = fb ? c->fb_live : c->live;
+    const HitBuf hits_d = fb ? c->fb_hits : c->hits[d & 1];
+    uint8_t* const key_d = fb ? c->fb_key : c->key[d & 1];
+    uint8_t* const live_d = fb ? c->fb_live : c->live[d & 1];
+    const bool analytic_done = d == 0 ? fused_gen : fused;  // by the kernel that produced this depth's rays
     IsectParams ip;
     ip.scene = c->dscene;
     ip.in = in;
@@ -850,8 +884,10 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
       k_first_bounce_hist<<<1, 256, 0, s>>>(c->ctr, c->fb_hist, c->P, 1);
       c->launches += 1;
     } else {
-    k_intersect_analytic<<<c->analytic_grid, 256, 0, s>>>(ip);
-    c->launches += 1;
+    if (!analytic_done) {
+      k_intersect_analytic<<<c->analytic_grid, 256, 0, s>>>(ip);
+      c->launches += 1;
+    }
     if (c->dscene.n_meshes > 0) {
       if (c->opt.use_bvh) {
         if (kt) kt->mark(4);
@@ -918,7 +954,13 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
     sp.rec_dead = c->rec_dead; sp.rec_live = c->rec_live;
     const bool portable = c->opt.trig_mode == B2PT_TRIG_PORTABLE;
     if (kt) kt->mark(3);
-    if (record) {
+    if (fused) {
+      const IsectParams np = next_params(d + 1);
+      const int tiles = (c->P + kFusedThreads - 1) / kFusedThreads;
+      const int grid = std::min(tiles, c->shade_stride_grid * (kShadeThreads / kFusedThreads));
+      if (portable) k_shade_trace<1><<<grid, kFusedThreads, 0, s>>>(sp, np);
+      else k_shade_trace<0><<<grid, kFusedThreads, 0, s>>>(sp, np);
+    } else if (record) {
       if (portable) launch_shade<1, true>(c, sp); else launch_shade<0, true>(c, sp);
     } else {
       if (portable) launch_shade<1, false>(c, sp); else launch_shade<0, false>(c, sp);

@@ -70,11 +70,10 @@ __device__ __forceinline__ void concentric_disk(float px, float py, float* ox, f
 // One thread per pixel; a warp covers 32 consecutive pixels of a row, so the
 // three 128-bit stores per path are fully coalesced (the reference writes a
 // 44-byte AoS element from an 8x8 block).
+// The primary ray of pixel `index` (generateRayFromCamera, pathtrace.cu:248-297).
 template <int TRIG>
-__global__ void __launch_bounds__(256) k_generate(GenParams gp, const int* __restrict__ iter_state, PathBuf out) {
-  const int P = gp.cam.res_x * gp.cam.res_y;
-  const int iter = iter_state[0];
-  for (int index = blockIdx.x * blockDim.x + threadIdx.x; index < P; index += gridDim.x * blockDim.x) {
+__device__ __forceinline__ void camera_ray(const GenParams& gp, int iter, int index, V3* origin, V3* direction) {
+  {
     const int x = index % gp.cam.res_x;
     const int y = index / gp.cam.res_x;
     uint32_t rng = rng_seed(iter, index, gp.trace_depth);
@@ -101,6 +100,18 @@ __global__ void __launch_bounds__(256) k_generate(GenParams gp, const int* __res
       o = o + mk(lx, ly, 0.0f);
       d = normalize(focus - o);
     }
+    *origin = o;
+    *direction = d;
+  }
+}
+
+template <int TRIG>
+__global__ void __launch_bounds__(256) k_generate(GenParams gp, const int* __restrict__ iter_state, PathBuf out) {
+  const int P = gp.cam.res_x * gp.cam.res_y;
+  const int iter = iter_state[0];
+  for (int index = blockIdx.x * blockDim.x + threadIdx.x; index < P; index += gridDim.x * blockDim.x) {
+    V3 o, d;
+    camera_ray<TRIG>(gp, iter, index, &o, &d);
     out.s0[index] = make_float4(o.x, o.y, o.z, __int_as_float(index));
     out.s1[index] = make_float4(d.x, d.y, d.z, __int_as_float(gp.trace_depth));
     out.s2[index] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);

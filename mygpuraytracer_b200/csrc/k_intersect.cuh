@@ -265,118 +265,144 @@ __device__ __forceinline__ bool will_survive(const DevMaterial* __restrict__ mat
 //     wins get their record, key and histogram entry rewritten.
 // The closest hit is the lexicographic minimum of (t, geom id) over all geoms,
 // which is what the reference's strict `<` loop in geom order returns.
-__global__ void __launch_bounds__(256) k_intersect_analytic(IsectParams p) {
-  __shared__ DevGeom sgeom[kMaxGeoms];
-  __shared__ int shist[kMaxMaterials];
-  __shared__ int slive[kMaxMaterials];
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int n_geoms = p.scene.n_geoms;
-  {
-    const float4* src = reinterpret_cast<const float4*>(p.scene.geoms);
-    float4* dst = reinterpret_cast<float4*>(sgeom);
-    const int words = n_geoms * (int)(sizeof(DevGeom) / 16);
-    for (int i = tid; i < words; i += blockDim.x) dst[i] = __ldg(src + i);
-    for (int i = tid; i < kMaxMaterials; i += blockDim.x) {
-      shist[i] = 0;
-      slive[i] = 0;
+// The analytic half of one ray: closest cube / sphere, its record, and whether a mesh has to be walked.
+struct AnalyticHit {
+  float4 h0, h1;
+  int mat;
+  bool survives, want_mesh;
+};
+__device__ __forceinline__ void analytic_trace(const DevGeom* sgeom, int n_geoms, const DevMaterial* __restrict__ mats, V3 o,
+                                               V3 d, int bounces, AnalyticHit* r) {
+  const V3 id = rcp_fast(d);
+  const V3 noid = mk(-(o.x * id.x), -(o.y * id.y), -(o.z * id.z));
+  float t_min = FLT_MAX;
+  int hit = -1, kind = 0;
+  V3 aux = mk(0, 0, 0);  // box: axis normal; sphere: object-space point
+  // Pass 1 (warp-coherent, cheap): which geoms does this ray's path cross?  For meshes: the closest box
+  // entry (minus the distance slack) of the rigid ones, and whether a non-rigid one is crossed at all.
+  unsigned long long cand = 0ull;
+  float mesh_tn = FLT_MAX;
+  bool mesh_any = false;
+  for (int g = 0; g < n_geoms; ++g) {
+    const DevGeom& G = sgeom[g];
+    float tn, tf;
+    world_slab(G, id, noid, &tn, &tf);
+    if (!(tn <= tf) || tf < 0.0f) continue;
+    if (G.type == 1 || G.type == 0) {
+      cand |= 1ull << g;
+    } else if (G.type == 3 && G.mesh >= 0) {
+      if (G.rigid) mesh_tn = fminf(mesh_tn, tn - G.wmin.w); else mesh_any = true;
     }
   }
-  __syncthreads();
-  const int n = p.ctr->n_live[p.depth];
-  const int n_meshes = p.scene.n_meshes;
-  // whole warps stride over the rays so that the ballots below are warp-wide
-  for (int base = (blockIdx.x * blockDim.x + tid) & ~31; base < n; base += gridDim.x * blockDim.x) {
-    const int i = base + lane;
-    const bool valid = i < n;
-    int mat = 0;
-    bool want_mesh = false, survives = false;
-    if (valid) {
-      const float4 a = p.in.s0[i];
-      const float4 b = p.in.s1[i];
-      const V3 o = mk(a.x, a.y, a.z), d = mk(b.x, b.y, b.z);
-      const V3 id = rcp_fast(d);
-      const V3 noid = mk(-(o.x * id.x), -(o.y * id.y), -(o.z * id.z));
-      float t_min = FLT_MAX;
-      int hit = -1, kind = 0;
-      V3 aux = mk(0, 0, 0);  // box: axis normal; sphere: object-space point
-      // Pass 1 (warp-coherent, cheap): which geoms does this ray's path cross?  For meshes: the closest box
-      // entry (minus the distance slack) of the rigid ones, and whether a non-rigid one is crossed at all.
-      unsigned long long cand = 0ull;
-      float mesh_tn = FLT_MAX;
-      bool mesh_any = false;
-      for (int g = 0; g < n_geoms; ++g) {
-        const DevGeom& G = sgeom[g];
-        float tn, tf;
-        world_slab(G, id, noid, &tn, &tf);
-        if (!(tn <= tf) || tf < 0.0f) continue;
-        if (G.type == 1 || G.type == 0) {
-          cand |= 1ull << g;
-        } else if (G.type == 3 && G.mesh >= 0) {
-          if (G.rigid) mesh_tn = fminf(mesh_tn, tn - G.wmin.w); else mesh_any = true;
-        }
-      }
-      // Pass 2: each lane runs the exact tests of ITS candidates (typically 1-3
-      // of the 8-9 geoms), in geom order; the warp iterates max-popcount times
-      // instead of once per geom.
-      while (cand) {
-        const int g = __ffsll((long long)cand) - 1;
-        cand &= cand - 1ull;
-        const DevGeom& G = sgeom[g];
-        if (!may_beat(G, id, noid, t_min, true)) continue;
-        float t;
-        V3 taux = mk(0, 0, 0);
-        int tkind = 1;
-        if (G.type == 1) t = box_exact(G, o, d, &taux); else t = sphere_exact(G, o, d, &taux, &tkind);
-        if (t > 0.0f && t_min > t) {  // candidates are visited in index order: strict < keeps the lowest id
-          t_min = t;
-          hit = g;
-          kind = tkind;
-          aux = taux;
-        }
-      }
-      float4 h0, h1;
-      if (hit < 0) {
-        h0 = make_float4(-1.0f, 0.0f, 0.0f, 0.0f);
-        h1 = make_float4(0.0f, 0.0f, __int_as_float(0xffff), __int_as_float(-1));
-      } else {
-        const DevGeom& G = sgeom[hit];
-        V3 nrm = normalize(xform(G.invT, aux, 0.0f));
-        if (kind == 3) nrm = -nrm;
-        mat = G.material;
-        survives = will_survive(p.scene.materials, mat, __float_as_int(b.w), false);
-        h0 = make_float4(t_min, nrm.x, nrm.y, nrm.z);
-        h1 = make_float4(0.0f, 0.0f, __int_as_float((hit & 0xffff) | (mat << 16)), __int_as_float(-1));
-      }
-      p.out.h0[i] = h0;
-      p.out.h1[i] = h1;
-      p.key[i] = (uint8_t)mat;
-      p.live[i] = survives ? 1 : 0;
-      // a mesh has to be walked if its box is entered in front of the closest analytic hit (a rigid mesh
-      // reports world-space distances, so t_min bounds it; any other mesh is always walked)
-      want_mesh = mesh_any || (mesh_tn < FLT_MAX && (t_min >= FLT_MAX || mesh_tn <= t_min * 1.0001f));
-    }
-    const unsigned int active = __ballot_sync(0xffffffffu, valid);
-    if (valid) {
-      const unsigned int peers = __match_any_sync(active, mat);
-      if (lane == __ffs(peers) - 1) atomicAdd(&shist[mat], __popc(peers));
-      const unsigned int lpeers = peers & __ballot_sync(active, survives);
-      if (lpeers && lane == __ffs(lpeers) - 1) atomicAdd(&slive[mat], __popc(lpeers));
-    }
-    const unsigned int mm = __ballot_sync(0xffffffffu, want_mesh);
-    if (mm) {
-      unsigned int qbase = 0;
-      if (lane == 0) qbase = atomicAdd(&p.ctr->mesh_count[p.depth], (unsigned int)__popc(mm));
-      qbase = __shfl_sync(0xffffffffu, qbase, 0);
-      if (want_mesh) p.queue[qbase + __popc(mm & ((1u << lane) - 1u))] = i;
+  // Pass 2: each lane runs the exact tests of ITS candidates (typically 1-3 of the 8-9 geoms), in geom
+  // order; the warp iterates max-popcount times instead of once per geom.
+  while (cand) {
+    const int g = __ffsll((long long)cand) - 1;
+    cand &= cand - 1ull;
+    const DevGeom& G = sgeom[g];
+    if (!may_beat(G, id, noid, t_min, true)) continue;
+    float t;
+    V3 taux = mk(0, 0, 0);
+    int tkind = 1;
+    if (G.type == 1) t = box_exact(G, o, d, &taux); else t = sphere_exact(G, o, d, &taux, &tkind);
+    if (t > 0.0f && t_min > t) {  // candidates are visited in index order: strict < keeps the lowest id
+      t_min = t;
+      hit = g;
+      kind = tkind;
+      aux = taux;
     }
   }
-  __syncthreads();
-  for (int i = tid; i < kMaxMaterials; i += blockDim.x) {
+  r->mat = 0;
+  r->survives = false;
+  if (hit < 0) {
+    r->h0 = make_float4(-1.0f, 0.0f, 0.0f, 0.0f);
+    r->h1 = make_float4(0.0f, 0.0f, __int_as_float(0xffff), __int_as_float(-1));
+  } else {
+    const DevGeom& G = sgeom[hit];
+    V3 nrm = normalize(xform(G.invT, aux, 0.0f));
+    if (kind == 3) nrm = -nrm;
+    r->mat = G.material;
+    r->survives = will_survive(mats, r->mat, bounces, false);
+    r->h0 = make_float4(t_min, nrm.x, nrm.y, nrm.z);
+    r->h1 = make_float4(0.0f, 0.0f, __int_as_float((hit & 0xffff) | (r->mat << 16)), __int_as_float(-1));
+  }
+  // a mesh has to be walked if its box is entered in front of the closest analytic hit (a rigid mesh
+  // reports world-space distances, so t_min bounds it; any other mesh is always walked)
+  r->want_mesh = mesh_any || (mesh_tn < FLT_MAX && (t_min >= FLT_MAX || mesh_tn <= t_min * 1.0001f));
+}
+
+// Store the record of slot i, count it in the CTA's histograms and queue it for the mesh walk.  Called by
+// WHOLE WARPS (lanes without a ray pass valid = false): the histogram and queue updates are warp-aggregated.
+__device__ __forceinline__ void analytic_commit(const IsectParams& p, int* shist, int* slive, int i, bool valid,
+                                                const AnalyticHit& r) {
+  const int lane = threadIdx.x & 31;
+  if (valid) {
+    p.out.h0[i] = r.h0;
+    p.out.h1[i] = r.h1;
+    p.key[i] = (uint8_t)r.mat;
+    p.live[i] = r.survives ? 1 : 0;
+  }
+  const unsigned int active = __ballot_sync(0xffffffffu, valid);
+  if (valid) {
+    const unsigned int peers = __match_any_sync(active, r.mat);
+    if (lane == __ffs(peers) - 1) atomicAdd(&shist[r.mat], __popc(peers));
+    const unsigned int lpeers = peers & __ballot_sync(active, r.survives);
+    if (lpeers && lane == __ffs(lpeers) - 1) atomicAdd(&slive[r.mat], __popc(lpeers));
+  }
+  const bool want = valid && r.want_mesh;
+  const unsigned int mm = __ballot_sync(0xffffffffu, want);
+  if (mm) {
+    unsigned int qbase = 0;
+    if (lane == 0) qbase = atomicAdd(&p.ctr->mesh_count[p.depth], (unsigned int)__popc(mm));
+    qbase = __shfl_sync(0xffffffffu, qbase, 0);
+    if (want) p.queue[qbase + __popc(mm & ((1u << lane) - 1u))] = i;
+  }
+}
+
+// Shared-memory set-up / flush of the two helpers above.
+__device__ __forceinline__ void analytic_stage(const DevScene& scene, DevGeom* sgeom, int* shist, int* slive) {
+  const float4* src = reinterpret_cast<const float4*>(scene.geoms);
+  float4* dst = reinterpret_cast<float4*>(sgeom);
+  const int words = scene.n_geoms * (int)(sizeof(DevGeom) / 16);
+  for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = __ldg(src + i);
+  for (int i = threadIdx.x; i < kMaxMaterials; i += blockDim.x) {
+    shist[i] = 0;
+    slive[i] = 0;
+  }
+}
+__device__ __forceinline__ void analytic_flush(const IsectParams& p, const int* shist, const int* slive) {
+  for (int i = threadIdx.x; i < kMaxMaterials; i += blockDim.x) {
     const int c = shist[i];
     if (c) atomicAdd(&p.ctr->hist[p.depth][i], (unsigned int)c);
     const int cl = slive[i];
     if (cl) atomicAdd(&p.ctr->hist_live[p.depth][i], (unsigned int)cl);
   }
+}
+
+__global__ void __launch_bounds__(256) k_intersect_analytic(IsectParams p) {
+  __shared__ DevGeom sgeom[kMaxGeoms];
+  __shared__ int shist[kMaxMaterials];
+  __shared__ int slive[kMaxMaterials];
+  const int tid = threadIdx.x, lane = tid & 31;
+  analytic_stage(p.scene, sgeom, shist, slive);
+  __syncthreads();
+  const int n = p.ctr->n_live[p.depth];
+  // whole warps stride over the rays so that the ballots of analytic_commit are warp-wide
+  for (int base = (blockIdx.x * blockDim.x + tid) & ~31; base < n; base += gridDim.x * blockDim.x) {
+    const int i = base + lane;
+    const bool valid = i < n;
+    AnalyticHit r;
+    r.mat = 0;
+    r.survives = r.want_mesh = false;
+    if (valid) {
+      const float4 a = p.in.s0[i];
+      const float4 b = p.in.s1[i];
+      analytic_trace(sgeom, p.scene.n_geoms, p.scene.materials, mk(a.x, a.y, a.z), mk(b.x, b.y, b.z), __float_as_int(b.w), &r);
+    }
+    analytic_commit(p, shist, slive, i, valid, r);
+  }
+  __syncthreads();
+  analytic_flush(p, shist, slive);
   if (blockIdx.x == 0 && tid == 0) atomicAdd(&p.ctr->segments, (unsigned long long)n);
 }
 

@@ -95,6 +95,149 @@ __device__ __forceinline__ void write_result(const ShadeParams& p, int j, unsign
   }
 }
 
+// Shade sorted slot j (shadeFakeMaterial + scatterRay, pathtrace.cu:397-498, interactions.h:112-258): gathers
+// the hit record and the path state through the sort permutation, returns the scattered path.
+template <int TRIG>
+__device__ __forceinline__ void shade_slot(const ShadeParams& p, int j, int iter, int ref_depth, V3& o, V3& d, V3& col,
+                                           int& pixel, int& bounces) {
+  const int i = p.perm ? p.perm[j] : j;
+  const float4 h0 = p.hits.h0[i];
+  const float4 h1 = p.hits.h1[i];
+  const float4 s0 = p.in.s0[i], s1 = p.in.s1[i], s2 = p.in.s2[i];
+  o = mk(s0.x, s0.y, s0.z);
+  d = mk(s1.x, s1.y, s1.z);
+  col = mk(s2.x, s2.y, s2.z);
+  pixel = __float_as_int(s0.w);
+  bounces = __float_as_int(s1.w);
+  const float t = h0.x;
+  const int gm = __float_as_int(h1.z);
+  const int geom_id = gm & 0xffff;
+  const int mat_id = (gm >> 16) & 0xffff;
+  const float tu = h1.x, tv = h1.y;
+
+  // albedo AOV, pathtrace.cu:412-462 (iteration 1, first shade only)
+  if (p.albedo != nullptr && iter == 1 && ref_depth == 1) {
+    V3 a = mk(0, 0, 0);
+    if (t > 0.0f) {
+      const DevMaterial& m = p.scene.materials[mat_id];
+      a = mk(m.color[0], m.color[1], m.color[2]);
+      const DevGeom& G = p.scene.geoms[geom_id];
+      if (G.type == 3) {
+        const DevMesh& M = p.scene.meshes[G.mesh];
+        V3 emission = mk(0, 0, 0);
+        if (M.ke.channels) emission = fetch_texel(M.ke, tu, tv);
+        if (emission.x > FLT_EPSILON || emission.y > FLT_EPSILON || emission.z > FLT_EPSILON) {
+          a = emission * 5.0f;
+        } else if (M.kd.channels) {
+          a = fetch_texel(M.kd, tu, tv);
+        }
+      } else if (m.emittance > 0.0f) {
+        a = a * m.emittance;
+      } else if (m.has_refractive > 0.0f) {
+        a = mk(m.specular_color[0], m.specular_color[1], m.specular_color[2]);
+      }
+    }
+    float* ap = p.albedo + 3 * (size_t)pixel;
+    ap[0] = a.x;
+    ap[1] = a.y;
+    ap[2] = a.z;
+  }
+
+  if (t > 0.0f) {
+    uint32_t rng = p.rng_pixel ? rng_seed(iter, pixel, ref_depth) : rng_seed(iter, j, 0);
+    const DevMaterial m = p.scene.materials[mat_id];
+    const V3 mcol = mk(m.color[0], m.color[1], m.color[2]);
+    const V3 scol = mk(m.specular_color[0], m.specular_color[1], m.specular_color[2]);
+    if (m.emittance > 0.0f) {
+      col = mulv(col, mcol * m.emittance);
+      bounces = 0;
+    } else if (bounces == 1) {
+      col = mk(0, 0, 0);
+      bounces = 0;
+    } else {
+      // scatterRay, interactions.h:112-258
+      const V3 x = o + d * t;
+      V3 nrm = mk(h0.y, h0.z, h0.w);
+      bool done = false;
+      if (m.has_reflective > 0) {
+        const V3 rdir = reflect(d, nrm);
+        const float spec = powf_exponent(glm_max(dot(-d, rdir), 0.0f), m.specular_exponent);
+        col = mulv(col, scol * (m.has_reflective * spec));
+        o = x + nrm * 0.01f;
+        d = rdir;
+      } else if (m.has_refractive > 0) {
+        float ior1 = 1.0f, ior2 = m.ior;
+        float cos_t = dot(-d, nrm);
+        if (cos_t < 0) {
+          nrm = nrm * -1.0f;
+          ior1 = ior2;
+          ior2 = 1.0f;
+          cos_t = fabsf(cos_t);
+        }
+        const float sin_t = (float)sqrt(1.0 - (double)(cos_t * cos_t));
+        if (ior1 / ior2 * sin_t > 1.0f) {
+          d = reflect(d, nrm);
+        } else {
+          const float r0 = ((ior1 - ior2) / (ior1 + ior2)) * ((ior1 - ior2) / (ior1 + ior2));
+          const float coeff = (float)((double)r0 + (double)(1.0f - r0) * pow5_mode<TRIG>(1.0 - (double)cos_t));
+          const float rnd = rng_uniform(rng, 0.0f, 1.0f);
+          if (rnd < coeff) {
+            d = reflect(d, nrm);
+          } else {
+            // glm::refract, detail/func_geometric.inl:193-200
+            const float eta = ior1 / ior2;
+            const float dv = dot(nrm, d);
+            const float k = 1.0f - eta * eta * (1.0f - dv * dv);
+            d = (d * eta - nrm * (eta * dv + sqrtf(k))) * (k >= 0.0f ? 1.0f : 0.0f);
+          }
+        }
+        col = mulv(col, scol);
+        o = x + d * 0.01f;
+      } else {
+        const DevGeom& G = p.scene.geoms[geom_id];
+        if (G.type == 3) {
+          const DevMesh& M = p.scene.meshes[G.mesh];
+          V3 emission = mk(0, 0, 0);
+          if (M.ke.channels) emission = fetch_texel(M.ke, tu, tv);
+          if (emission.x > FLT_EPSILON || emission.y > FLT_EPSILON || emission.z > FLT_EPSILON) {
+            col = mulv(col, emission * 5.0f);
+            bounces = 1;  // interactions.h:184; decremented to 0 below
+            done = true;
+          }
+          if (!done) {
+            const float ior1 = 1.0f, ior2 = m.ior;
+            const float cos_t = dot(-d, nrm);
+            const float r0 = ((ior1 - ior2) / (ior1 + ior2)) * ((ior1 - ior2) / (ior1 + ior2));
+            const float coeff = (float)((double)r0 + (double)(1.0f - r0) * pow5_mode<TRIG>(1.0 - (double)cos_t));
+            const float rnd = rng_uniform(rng, 0.0f, 1.0f);
+            if (rnd < coeff) {
+              const V3 rdir = reflect(d, nrm);
+              V3 sc = M.ks.channels ? fetch_texel(M.ks, tu, tv) : scol;
+              sc = sc * 1.0f;  // spec = pow(x, 0.0f) == 1, interactions.h:204,214
+              col = mulv(col, sc);
+              o = x + nrm * 0.01f;
+              d = rdir;
+            } else {
+              const V3 dc = M.kd.channels ? fetch_texel(M.kd, tu, tv) : mcol;
+              col = mulv(col, dc);
+              d = hemisphere<TRIG>(nrm, rng);
+              o = x + d * 0.01f;
+            }
+          }
+        } else {
+          d = hemisphere<TRIG>(nrm, rng);
+          o = x + d * 0.01f;
+          col = mulv(col, mcol);
+        }
+      }
+      bounces -= 1;
+    }
+  } else {
+    col = mk(0, 0, 0);
+    bounces = 0;
+  }
+}
+
 // PRECOMP: the compaction ranks come from k_sort_material (apos); the kernel is
 // then embarrassingly parallel -- no shared memory, no barrier, no look-back.
 // Without the material sort (SORT_BY_MATERIAL 0) it scans the survivors itself.
@@ -125,142 +268,7 @@ __global__ void __launch_bounds__(kShadeThreads) k_shade_compact(ShadeParams p) 
   int pixel = 0, bounces = 0;
 
   if (valid) {
-    const int i = p.perm ? p.perm[j] : j;
-    const float4 h0 = p.hits.h0[i];
-    const float4 h1 = p.hits.h1[i];
-    const float4 s0 = p.in.s0[i], s1 = p.in.s1[i], s2 = p.in.s2[i];
-    o = mk(s0.x, s0.y, s0.z);
-    d = mk(s1.x, s1.y, s1.z);
-    col = mk(s2.x, s2.y, s2.z);
-    pixel = __float_as_int(s0.w);
-    bounces = __float_as_int(s1.w);
-    const float t = h0.x;
-    const int gm = __float_as_int(h1.z);
-    const int geom_id = gm & 0xffff;
-    const int mat_id = (gm >> 16) & 0xffff;
-    const float tu = h1.x, tv = h1.y;
-
-    // albedo AOV, pathtrace.cu:412-462 (iteration 1, first shade only)
-    if (p.albedo != nullptr && iter == 1 && ref_depth == 1) {
-      V3 a = mk(0, 0, 0);
-      if (t > 0.0f) {
-        const DevMaterial& m = p.scene.materials[mat_id];
-        a = mk(m.color[0], m.color[1], m.color[2]);
-        const DevGeom& G = p.scene.geoms[geom_id];
-        if (G.type == 3) {
-          const DevMesh& M = p.scene.meshes[G.mesh];
-          V3 emission = mk(0, 0, 0);
-          if (M.ke.channels) emission = fetch_texel(M.ke, tu, tv);
-          if (emission.x > FLT_EPSILON || emission.y > FLT_EPSILON || emission.z > FLT_EPSILON) {
-            a = emission * 5.0f;
-          } else if (M.kd.channels) {
-            a = fetch_texel(M.kd, tu, tv);
-          }
-        } else if (m.emittance > 0.0f) {
-          a = a * m.emittance;
-        } else if (m.has_refractive > 0.0f) {
-          a = mk(m.specular_color[0], m.specular_color[1], m.specular_color[2]);
-        }
-      }
-      float* ap = p.albedo + 3 * (size_t)pixel;
-      ap[0] = a.x;
-      ap[1] = a.y;
-      ap[2] = a.z;
-    }
-
-    if (t > 0.0f) {
-      uint32_t rng = p.rng_pixel ? rng_seed(iter, pixel, ref_depth) : rng_seed(iter, j, 0);
-      const DevMaterial m = p.scene.materials[mat_id];
-      const V3 mcol = mk(m.color[0], m.color[1], m.color[2]);
-      const V3 scol = mk(m.specular_color[0], m.specular_color[1], m.specular_color[2]);
-      if (m.emittance > 0.0f) {
-        col = mulv(col, mcol * m.emittance);
-        bounces = 0;
-      } else if (bounces == 1) {
-        col = mk(0, 0, 0);
-        bounces = 0;
-      } else {
-        // scatterRay, interactions.h:112-258
-        const V3 x = o + d * t;
-        V3 nrm = mk(h0.y, h0.z, h0.w);
-        bool done = false;
-        if (m.has_reflective > 0) {
-          const V3 rdir = reflect(d, nrm);
-          const float spec = powf_exponent(glm_max(dot(-d, rdir), 0.0f), m.specular_exponent);
-          col = mulv(col, scol * (m.has_reflective * spec));
-          o = x + nrm * 0.01f;
-          d = rdir;
-        } else if (m.has_refractive > 0) {
-          float ior1 = 1.0f, ior2 = m.ior;
-          float cos_t = dot(-d, nrm);
-          if (cos_t < 0) {
-            nrm = nrm * -1.0f;
-            ior1 = ior2;
-            ior2 = 1.0f;
-            cos_t = fabsf(cos_t);
-          }
-          const float sin_t = (float)sqrt(1.0 - (double)(cos_t * cos_t));
-          if (ior1 / ior2 * sin_t > 1.0f) {
-            d = reflect(d, nrm);
-          } else {
-            const float r0 = ((ior1 - ior2) / (ior1 + ior2)) * ((ior1 - ior2) / (ior1 + ior2));
-            const float coeff = (float)((double)r0 + (double)(1.0f - r0) * pow5_mode<TRIG>(1.0 - (double)cos_t));
-            const float rnd = rng_uniform(rng, 0.0f, 1.0f);
-            if (rnd < coeff) {
-              d = reflect(d, nrm);
-            } else {
-              // glm::refract, detail/func_geometric.inl:193-200
-              const float eta = ior1 / ior2;
-              const float dv = dot(nrm, d);
-              const float k = 1.0f - eta * eta * (1.0f - dv * dv);
-              d = (d * eta - nrm * (eta * dv + sqrtf(k))) * (k >= 0.0f ? 1.0f : 0.0f);
-            }
-          }
-          col = mulv(col, scol);
-          o = x + d * 0.01f;
-        } else {
-          const DevGeom& G = p.scene.geoms[geom_id];
-          if (G.type == 3) {
-            const DevMesh& M = p.scene.meshes[G.mesh];
-            V3 emission = mk(0, 0, 0);
-            if (M.ke.channels) emission = fetch_texel(M.ke, tu, tv);
-            if (emission.x > FLT_EPSILON || emission.y > FLT_EPSILON || emission.z > FLT_EPSILON) {
-              col = mulv(col, emission * 5.0f);
-              bounces = 1;  // interactions.h:184; decremented to 0 below
-              done = true;
-            }
-            if (!done) {
-              const float ior1 = 1.0f, ior2 = m.ior;
-              const float cos_t = dot(-d, nrm);
-              const float r0 = ((ior1 - ior2) / (ior1 + ior2)) * ((ior1 - ior2) / (ior1 + ior2));
-              const float coeff = (float)((double)r0 + (double)(1.0f - r0) * pow5_mode<TRIG>(1.0 - (double)cos_t));
-              const float rnd = rng_uniform(rng, 0.0f, 1.0f);
-              if (rnd < coeff) {
-                const V3 rdir = reflect(d, nrm);
-                V3 sc = M.ks.channels ? fetch_texel(M.ks, tu, tv) : scol;
-                sc = sc * 1.0f;  // spec = pow(x, 0.0f) == 1, interactions.h:204,214
-                col = mulv(col, sc);
-                o = x + nrm * 0.01f;
-                d = rdir;
-              } else {
-                const V3 dc = M.kd.channels ? fetch_texel(M.kd, tu, tv) : mcol;
-                col = mulv(col, dc);
-                d = hemisphere<TRIG>(nrm, rng);
-                o = x + d * 0.01f;
-              }
-            }
-          } else {
-            d = hemisphere<TRIG>(nrm, rng);
-            o = x + d * 0.01f;
-            col = mulv(col, mcol);
-          }
-        }
-        bounces -= 1;
-      }
-    } else {
-      col = mk(0, 0, 0);
-      bounces = 0;
-    }
+    shade_slot<TRIG>(p, j, iter, ref_depth, o, d, col, pixel, bounces);
     alive = bounces > 0;
     if (RECORD) {
       p.rec_s0[j] = make_float4(o.x, o.y, o.z, __int_as_float(pixel));

@@ -227,6 +227,32 @@ def test_long_walk_handoff_paths_bitexact(tmp_path, monkeypatch, env):
         assert longs == 0
 
 
+@pytest.mark.parametrize("scene_kind", ["cornellGlass", "mesh", "twoShips"])
+def test_fused_and_unfused_kernels_agree(tmp_path, monkeypatch, scene_kind):
+    """k_generate_trace / k_shade_trace (analytic intersection fused into the kernel
+    that produces the rays) against the separate kernels and the oracle: images,
+    albedo and live counts bit-identical over several iterations, odd sizes included."""
+    if scene_kind == "cornellGlass":
+        pod = api.Scene(scenes.write_scene("cornellGlass", str(tmp_path / "s.txt"), width=333, height=127)).pod
+    else:
+        pod = _mesh_scene(tmp_path, "cornellSpaceship" if scene_kind == "mesh" else "twoShips", 173, 99, 20000)
+    ref, ref_alb, nlive, _ = oracle.render(pod, abi.default_options(trig_mode=abi.TRIG_PORTABLE), 1, 5, 1)
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("B2PT_FUSE", fuse)
+        for graph in (1, 0):
+            with api.Renderer(pod, abi.default_options(trig_mode=abi.TRIG_PORTABLE, use_graph=graph)) as r:
+                r.render(1, 2, 1)
+                r.render(3, 3, 1)
+                img, alb = r.read()
+                assert_same_bits(img, ref, f"{scene_kind} fuse={fuse} graph={graph} image")
+                assert_same_bits(alb, ref_alb, f"{scene_kind} fuse={fuse} albedo")
+                assert list(r.live_counts()[: len(nlive)]) == list(nlive)
+                launches = r.launch_count()
+        if fuse == "1":
+            fused_launches = launches
+    assert fused_launches < launches, "the fused form has fewer launches"
+
+
 def test_shared_gpu_grids_change_nothing(tmp_path):
     """concurrent_contexts > 1 only resizes the persistent grids: every stage and
     the image stay bit-identical, also for four contexts rendering at once."""
