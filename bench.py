@@ -525,13 +525,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "scene_load_s": round(load_s, 2), "image_checksum": checksum,
         }
         if world == 1 and not args.no_cpu:
+            ra = reference_host_adapter(root, args, max(20, min(K, 200)))
+            if ra is not None:
+                line["e2e_reference_host"] = ra
             line["cpu_baseline"] = {k: v for k, v in cpu_sample(root, args, 1).items()}
             rg = reference_gpu(root, args)
             if rg is not None:
                 line["reference_gpu"] = rg
-            ra = reference_host_adapter(root, args, max(20, min(K, 200)))
-            if ra is not None:
-                line["e2e_reference_host"] = ra
         emit(line)
     for x in rs + [r_e2e]:
         x.close()
