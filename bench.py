@@ -50,9 +50,9 @@ if ROOT not in sys.path:
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of each kernel, from the committed `ncu --set full`
 # capture of this workload (profiles/, cold caches: an upper bound on the warm traffic)
-TRAFFIC = {  # bytes per launch, depth-1 launch of profiles/r01_final_ncu_depth1.md
+TRAFFIC = {  # bytes per launch, depth-1 launches of profiles/r01_final_ncu_depth01.md and r01_final_ncu_unfused_depth1.md
     "k_intersect_analytic": 31.24e6, "k_mesh_walk": 71.61e6, "k_mesh_walk_long": 20.69e6, "k_mesh_finish": 50.24e6,
-    "k_sort_material": 1.99e6, "k_shade_compact": 169.64e6,
+    "k_sort_material": 1.99e6, "k_shade_compact": 169.64e6, "k_shade_trace": 197.83e6, "k_generate_trace": 123.39e6,
 }
 
 METRIC = "Mpaths/s"
