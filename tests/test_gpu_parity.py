@@ -143,6 +143,24 @@ def test_bvh_equals_brute_force_at_full_size(tmp_path):
     assert n_obj > 10000
 
 
+@pytest.mark.parametrize("scene,w,h,tris,iters", [("cornellSpaceship", 240, 135, 20000, 120), ("twoShips", 160, 90, 5000, 200)])
+def test_bvh_never_loses_a_hit_soak(tmp_path, scene, w, h, tris, iters):
+    """The BVH only prunes -- checked statistically: over >10 M path segments
+    (many iterations, AA on, every depth) the accumulated image of the BVH walk
+    is bit-identical to the brute-force kernel's (the reference's loop over every
+    face).  One triangle culled wrongly by the padded FMA slab test, one tie
+    resolved differently, would change a pixel."""
+    pod = _mesh_scene(tmp_path, scene, w, h, tris)
+    imgs, segs = [], []
+    for bvh in (1, 0):
+        with api.Renderer(pod, abi.default_options(use_bvh=bvh)) as r:
+            r.render(1, iters, 1)
+            imgs.append(r.read()[0])
+            segs.append(int(r.live_counts()[:8].sum()))
+    assert_same_bits(imgs[0], imgs[1], f"{scene}: BVH vs brute force after {iters} iterations")
+    assert segs[0] == segs[1] and segs[0] * iters > 5_000_000, "too few segments for a soak test"
+
+
 def test_multi_iteration_image_and_graph_replay(tmp_path):
     """50 iterations through the CUDA-graph path == 50 single launches == oracle."""
     pod = api.Scene(scenes.write_scene("cornellGlass", str(tmp_path / "s.txt"), width=64, height=64)).pod
