@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
@@ -268,7 +269,7 @@ struct RadixTemps {
   uint32_t* val_alt = nullptr;
 };
 
-static unsigned int g_radix_epoch = 1;
+static std::atomic<unsigned int> g_radix_epoch{1};  // contexts may be created from several host threads
 
 static int radix_temps_alloc(RadixTemps* t, int n) {
   const int tiles = (n + kSortTile - 1) / kSortTile;
@@ -307,7 +308,7 @@ static int radix_sort_pairs_dev(uint32_t* key, uint32_t* val, int n, cudaStream_
     pol.hist = t.hist + pass * 256;
     pol.ticket_ = t.tickets + pass;
     pol.status_ = t.status;
-    pol.epoch_ = g_radix_epoch++;
+    pol.epoch_ = g_radix_epoch.fetch_add(1u);
     pol.n_ = n;
     pol.shift = pass * 8;
     k_onesweep_pass<RadixPassPolicy><<<tiles, kSortThreads, 0, s>>>(pol);

@@ -271,6 +271,37 @@ def test_fused_and_unfused_kernels_agree(tmp_path, monkeypatch, scene_kind):
     assert fused_launches < launches, "the fused form has fewer launches"
 
 
+def test_contexts_are_independent_across_host_threads(tmp_path):
+    """Two host threads, each creating, driving and destroying its own context
+    (BVH build included) at the same time: both images equal the single-threaded one."""
+    import threading
+
+    pod = _mesh_scene(tmp_path, "cornellSpaceship", 128, 72, 5000)
+    opt = abi.default_options(trig_mode=abi.TRIG_PORTABLE)
+    with api.Renderer(pod, opt) as r:
+        r.render(1, 12, 1)
+        want, _ = r.read()
+    out, errs = [None, None], []
+
+    def work(k):
+        try:
+            for _ in range(3):  # create / destroy repeatedly while the other thread renders
+                with api.Renderer(pod, abi.default_options(trig_mode=abi.TRIG_PORTABLE)) as rr:
+                    rr.render(1, 12, 1)
+                    out[k] = rr.read()[0]
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    for k in range(2):
+        assert_same_bits(out[k], want, f"thread {k}")
+
+
 def test_shared_gpu_grids_change_nothing(tmp_path):
     """concurrent_contexts > 1 only resizes the persistent grids: every stage and
     the image stay bit-identical, also for four contexts rendering at once."""
