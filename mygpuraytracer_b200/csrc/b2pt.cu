@@ -882,34 +882,35 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
     ip.long_stack = c->long_stack;
     ip.long_n = c->long_n;
     if (fb && c->fb_valid) {
+      // the depth-0 records are still in the first-bounce buffers: only the histograms come back
       k_first_bounce_hist<<<1, 256, 0, s>>>(c->ctr, c->fb_hist, c->P, 1);
       c->launches += 1;
     } else {
-    if (!analytic_done) {
-      k_intersect_analytic<<<c->analytic_grid, 256, 0, s>>>(ip);
-      c->launches += 1;
-    }
-    if (c->dscene.n_meshes > 0) {
-      if (c->opt.use_bvh) {
-        if (kt) kt->mark(4);
-        if (c->trav_stats)
-          k_mesh_walk<true><<<c->walk_grid, kWalkThreads, 0, s>>>(ip);
-        else
-          k_mesh_walk<false><<<c->walk_grid, kWalkThreads, 0, s>>>(ip);
-        if (kt) kt->mark(5);
-        k_mesh_walk_long<<<c->long_grid, kCoopThreads, 0, s>>>(ip);
-        if (kt) kt->mark(6);
-        k_mesh_finish<<<c->finish_grid, 256, 0, s>>>(ip);
-        c->launches += 3;
-      } else {
-        k_intersect_mesh_brute<<<c->isect_grid, kIsectThreads, 0, s>>>(ip);
+      if (!analytic_done) {
+        k_intersect_analytic<<<c->analytic_grid, 256, 0, s>>>(ip);
         c->launches += 1;
       }
-    }
-    if (fb) {
-      k_first_bounce_hist<<<1, 256, 0, s>>>(c->ctr, c->fb_hist, c->P, 0);
-      c->launches += 1;
-    }
+      if (c->dscene.n_meshes > 0) {
+        if (c->opt.use_bvh) {
+          if (kt) kt->mark(4);
+          if (c->trav_stats)
+            k_mesh_walk<true><<<c->walk_grid, kWalkThreads, 0, s>>>(ip);
+          else
+            k_mesh_walk<false><<<c->walk_grid, kWalkThreads, 0, s>>>(ip);
+          if (kt) kt->mark(5);
+          k_mesh_walk_long<<<c->long_grid, kCoopThreads, 0, s>>>(ip);
+          if (kt) kt->mark(6);
+          k_mesh_finish<<<c->finish_grid, 256, 0, s>>>(ip);
+          c->launches += 3;
+        } else {
+          k_intersect_mesh_brute<<<c->isect_grid, kIsectThreads, 0, s>>>(ip);
+          c->launches += 1;
+        }
+      }
+      if (fb) {
+        k_first_bounce_hist<<<1, 256, 0, s>>>(c->ctr, c->fb_hist, c->P, 0);
+        c->launches += 1;
+      }
     }
     if (c->opt.sort_by_material) {
       MatSortParams mp;
