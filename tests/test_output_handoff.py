@@ -75,6 +75,29 @@ def test_png_decoder_handles_every_filter_type(tmp_path):
     assert np.array_equal(decode_png_rgb8(str(path)), img)
 
 
+def test_png_writer_container_roundtrip(tmp_path):
+    """csrc/host/png_writer.h on its own (compiled with g++, no GPU): chunk CRCs, the stored-deflate stream
+    and the Adler-32 are accepted by zlib, and the pixels come back unchanged -- including an image whose raw
+    size crosses several 65535-byte stored blocks."""
+    src = tmp_path / "t.cpp"
+    src.write_text(
+        '#include <stdio.h>\n#include <stdlib.h>\n#include <vector>\n'
+        f'#include "{ROOT}/mygpuraytracer_b200/csrc/host/png_writer.h"\n'
+        'int main(int argc, char** argv) { int w = atoi(argv[2]), h = atoi(argv[3]); std::vector<uint8_t> px((size_t)w * h * 3);\n'
+        '  FILE* f = fopen(argv[1], "rb"); if (!f || fread(px.data(), 1, px.size(), f) != px.size()) return 2; fclose(f);\n'
+        '  std::string e = b2pt_host::write_png_rgb8(argv[4], w, h, px.data()); if (!e.empty()) { puts(e.c_str()); return 1; }\n'
+        '  return b2pt_host::write_png_rgb8("/nonexistent_dir/x.png", w, h, px.data()).empty() ? 3 : 0; }\n')
+    exe = tmp_path / "t"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", str(src), "-o", str(exe)])
+    rng = np.random.default_rng(11)
+    for w, h in ((1, 1), (7, 3), (301, 217)):  # 301*217*3 + 217 = 196 168 raw bytes: four stored blocks
+        img = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+        raw, out = tmp_path / "in.raw", tmp_path / f"o_{w}.png"
+        img.tofile(raw)
+        subprocess.check_call([str(exe), str(raw), str(w), str(h), str(out)])
+        assert np.array_equal(decode_png_rgb8(str(out)), img)
+
+
 @pytest.mark.gpu
 def test_resolve_and_png_on_the_golden_buffer(tmp_path):
     """Crafted accumulation buffer (values on, just below and just above every
