@@ -36,13 +36,12 @@ namespace b2pt {
 
 constexpr int kWalkThreads = 256;
 constexpr int kWalkMinBlocks = 3;  // resident CTAs per SM the register budget is set for
-constexpr int kWalkShort = 8;    // (node, tn) entries per lane in shared memory
-constexpr int kWalkSpill = 88;   // spill entries per lane: 96 in all = 3 per level of a 32-level wide tree
-constexpr int kRefillMin = 8;    // idle lanes that trigger a refill
-constexpr int kLongCarry = 32;  // stack entries a long walk carries over to k_mesh_walk_long
+constexpr int kWalkShort = 8;      // (node, tn) entries per lane in shared memory
+constexpr int kWalkSpill = 88;     // spill entries per lane: 96 in all = 3 per level of a 32-level wide tree
+constexpr int kRefillMin = 8;      // idle lanes that trigger a refill
+constexpr int kLongCarry = 32;     // stack entries a long walk carries over to k_mesh_walk_long
 constexpr int kWalkDone = 0x7fffffff;
 constexpr int kNoGeom = 0x7fffffff;
-
 
 // Box test of the four children of a wide node with one FMA per plane.
 // The ray keeps id = 1/d and noid = -(o * id).  A node stores, per axis, the four
@@ -418,7 +417,7 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkMinBlocks) k_mesh_walk(Isec
   }
 }
 
-// Long walks, kCoopGroup lanes per ray (four rays per warp).  A group shares one
+// Long walks, kCoopGroup lanes per ray (two rays per warp).  A group shares one
 // stack of (node, entry distance) pairs in shared memory, seeded with the state
 // k_mesh_walk handed over; each round its lanes take the top entries, inner nodes
 // test their four child boxes, leaves run the exact triangle test, the closest
@@ -427,8 +426,10 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkMinBlocks) k_mesh_walk(Isec
 // nearest-first, which is harmless: the winner is the lexicographic minimum of
 // (t, face id) whatever the order, and entries behind it are dropped.  Close to
 // the capacity of the stack a group falls back to one entry per round
-// (depth-first, growth <= 3 per level).  The loop is warp-uniform: the four
-// groups of a warp run their rounds in lockstep and refill independently.
+// (depth-first, growth <= 3 per level).  The loop is warp-uniform: the groups
+// of a warp run their rounds in lockstep and refill independently.  (8 lanes per
+// ray are better for aggregate throughput, 32 for one context alone; 16 is the
+// compromise, profiles/r01_notes.md.)
 constexpr int kCoopThreads = 128;
 constexpr int kCoopGroup = 16;
 constexpr int kCoopCap = 32 * kCoopGroup;                        // stack entries per group (32 KB per CTA in all)
