@@ -369,7 +369,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     rs = [api.Renderer(scene, opt_shared) for _ in range(KC)]
     r = rs[0]
     mesh_geom = int(np.nonzero(pod.geoms["type"] == abi.OBJ)[0][0])
-    bvh = r.bvh_info(mesh_geom)
+    # every context builds its own BVH; the first build of a process also pays CUDA's lazy kernel loading
+    bvh = min((x.bvh_info(mesh_geom) for x in rs), key=lambda b: b.build_ms)
 
     streams = [torch.cuda.Stream() for _ in range(KC)]
     accs = [torch.zeros(P * 3, dtype=torch.float32, device="cuda") for _ in range(KC)]
@@ -521,7 +522,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                               "the analytic intersection is fused into generate / shade (k_generate_trace, k_shade_trace)",
             "segments_per_step": segments, "live_paths_per_depth": [int(x) for x in live[: args.depth + 1]],
             "bvh": {"triangles": int(bvh.n_faces), "nodes": int(bvh.n_nodes), "max_depth": int(bvh.max_depth),
-                    "build_ms": float(bvh.build_ms)},
+                    "build_ms": float(bvh.build_ms), "build_ms_note": "device time, fastest of the contexts of this process"},
             "scene_load_s": round(load_s, 2), "image_checksum": checksum,
         }
         if world == 1 and not args.no_cpu:
