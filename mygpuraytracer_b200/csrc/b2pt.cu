@@ -389,6 +389,13 @@ static int build_mesh(B2ptCtx* c, const float* pos_host, const float* uv_host, i
     k_node_depth<<<iblocks, 256, 0, s>>>(n, parent, visit);  // visit[] is free again: reuse it for the depths
     k_emit_wide4<<<iblocks, 256, 0, s>>>(n, children, visit, leaf_box, node_box, out->nodes);
     c->launches += 5;
+    // depth of the wide tree (visit[] is free again): one level per launch until nothing is reached any more;
+    // a binary tree of depth D gives at most D wide levels
+    CK(cudaMemsetAsync(visit, 0, (size_t)(n - 1) * sizeof(int), s));
+    const int one = 1;
+    CK(cudaMemcpyAsync(visit, &one, sizeof(int), cudaMemcpyHostToDevice, s));
+    for (int level = 1; level <= 64; ++level) k_wide_levels<<<iblocks, 256, 0, s>>>(n, out->nodes, visit, level, bounds);
+    c->launches += 64;
   }
   CK(cudaEventRecord(e1, s));
   CK(cudaGetLastError());
@@ -397,6 +404,10 @@ static int build_mesh(B2ptCtx* c, const float* pos_host, const float* uv_host, i
   TriBounds hb;
   CK(cudaMemcpy(&hb, bounds, sizeof hb, cudaMemcpyDeviceToHost));
   out->info.max_depth = n >= 2 ? hb.max_depth : 1;
+  const int wide_depth = n >= 2 ? hb.wide_depth : 0;
+  if (getenv("B2PT_TRAVERSAL_STATS"))
+    fprintf(stderr, "[b2pt bvh] %d triangles: binary depth %d, 4-wide depth %d (stack bound %d of %d entries)\n", n,
+            out->info.max_depth, wide_depth, 3 * wide_depth, kWalkShort + kWalkSpill);
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
   cudaFree(bounds);
@@ -408,7 +419,9 @@ static int build_mesh(B2ptCtx* c, const float* pos_host, const float* uv_host, i
   cudaFree(parent);
   cudaFree(visit);
   radix_temps_free(&rtemps);
-  if (out->info.max_depth > 2 * (kWalkShort + kWalkSpill) / 3)
+  // a walk's stack holds at most three entries per inner wide node on its path (nearest child first, the other
+  // hits pushed); k_mesh_walk_long's depth-first fallback relies on the same bound
+  if (out->info.max_depth > 64 || 3 * wide_depth > kWalkShort + kWalkSpill)
     return fail(B2PT_ERR_RANGE, "LBVH deeper than the traversal stack");
   return 0;
 }

@@ -10,9 +10,10 @@
 //   4. the Karras 2012 hierarchy (one thread per internal node, duplicates
 //      broken by index)
 //   5. bottom-up refit with one atomic counter per internal node
-//   6. 4-wide traversal nodes (k_emit_wide4): a binary node at even depth plus its
-//      grandchildren's boxes in one 128-byte line, and triangles in leaf order as
-//      3 x float4 (v0|face id, v1, v2).
+//   6. 4-wide traversal nodes (k_emit_wide4): a binary node's two children, the larger inner
+//      one opened twice (surface-area greedy), their boxes in one 128-byte line; triangles in
+//      leaf order as 3 x float4 (v0|face id, v1, v2); the depth of the wide tree (k_wide_levels)
+//      bounds the traversal stacks.
 // Boxes are inflated by `pad` (a few 1e-6 of the mesh extent) so that the
 // conservative slab test can never cull a triangle the reference's exact test
 // would accept: the BVH prunes, it never decides.
@@ -43,6 +44,7 @@ struct TriBounds {
   unsigned int lo[3];  // ordered-int min of centroids
   unsigned int hi[3];
   int max_depth;
+  int wide_depth;  // inner 4-wide nodes on the longest root-to-leaf path (k_wide_levels)
 };
 
 __global__ void k_bounds_init(TriBounds* b) {
@@ -52,6 +54,7 @@ __global__ void k_bounds_init(TriBounds* b) {
       b->hi[k] = 0u;
     }
     b->max_depth = 0;
+    b->wide_depth = 0;
   }
 }
 
@@ -212,9 +215,9 @@ __global__ void __launch_bounds__(256) k_node_depth(int n, const int* __restrict
   depth[i] = d;
 }
 
-// 4-wide traversal nodes: every binary node at EVEN depth becomes a wide node
-// whose children are its grandchildren (or a child that is a leaf), so a walk
-// makes half as many dependent memory round trips.  One wide node is exactly
+// 4-wide traversal nodes: a wide node's children are the binary node's two children with the
+// largest inner box opened twice (fixed two-level collapse = always the four grandchildren when
+// B2PT_WIDE_SAH is 0), so a walk makes about half as many dependent memory round trips.  One wide node is exactly
 // one 128-byte line, boxes stored per axis for the four slots:
 //   f0 = min.x[0..3]  f1 = max.x   f2 = min.y  f3 = max.y   f4 = min.z  f5 = max.z
 //   f6 = child ids as int bits (>= 0: wide node, < 0: ~leaf slot, kEmptyChild: unused)   f7 = pad
@@ -223,13 +226,49 @@ __global__ void __launch_bounds__(256) k_node_depth(int n, const int* __restrict
 // Wide nodes keep the index of the binary node they come from.
 constexpr int kEmptyChild = 0x40000000;
 
+#ifndef B2PT_WIDE_SAH
+#define B2PT_WIDE_SAH 1
+#endif
+__device__ __forceinline__ float box_area(const float4* b) {
+  const float dx = b[1].x - b[0].x, dy = b[1].y - b[0].y, dz = b[1].z - b[0].z;
+  return dx * dy + dy * dz + dz * dx;
+}
+
 __global__ void __launch_bounds__(256) k_emit_wide4(int n, const int2* __restrict__ children, const int* __restrict__ depth,
                                                     const float4* __restrict__ leaf_box, const float4* __restrict__ node_box,
                                                     float4* nodes) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1) return;
-  if (depth[i] & 1) return;
   int id[4] = {kEmptyChild, kEmptyChild, kEmptyChild, kEmptyChild};
+#if B2PT_WIDE_SAH
+  // Every binary node gets a wide node (only those reachable from the root are ever visited): start from its
+  // two children and twice replace the inner child with the LARGEST surface area by its own two children,
+  // instead of always taking the four grandchildren.  Big boxes are opened early, small ones stay closed.
+  (void)depth;
+  int k = 2;
+  {
+    const int2 c = children[i];
+    id[0] = c.x;
+    id[1] = c.y;
+  }
+  for (int round = 0; round < 2; ++round) {
+    int pick = -1;
+    float best_area = -1.0f;
+    for (int q = 0; q < k; ++q) {
+      if (id[q] < 0) continue;  // a leaf cannot be opened
+      const float a = box_area(node_box + 2 * (size_t)id[q]);
+      if (a > best_area) {
+        best_area = a;
+        pick = q;
+      }
+    }
+    if (pick < 0) break;
+    const int2 g = children[id[pick]];
+    id[pick] = g.x;
+    id[k++] = g.y;
+  }
+#else
+  if (depth[i] & 1) return;
   int k = 0;
   const int2 c = children[i];
   const int side[2] = {c.x, c.y};
@@ -242,6 +281,7 @@ __global__ void __launch_bounds__(256) k_emit_wide4(int n, const int2* __restric
       id[k++] = g.y;
     }
   }
+#endif
   float lo[3][4], hi[3][4];
   for (int q = 0; q < 4; ++q) {
     float4 b0 = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, 0.0f), b1 = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, 0.0f);
@@ -260,6 +300,20 @@ __global__ void __launch_bounds__(256) k_emit_wide4(int n, const int2* __restric
   }
   o[6] = make_float4(__int_as_float(id[0]), __int_as_float(id[1]), __int_as_float(id[2]), __int_as_float(id[3]));
   o[7] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+
+// Depth of the 4-wide tree, one level per launch: the nodes reached at `level` mark their inner children
+// with level + 1 (wdepth[0] = 1 for the root before the first launch).  A walk's stack holds at most three
+// entries per inner wide node on its path, which is what the traversal stacks are sized against.
+__global__ void __launch_bounds__(256) k_wide_levels(int n, const float4* __restrict__ nodes, int* wdepth, int level,
+                                                     TriBounds* info) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1 || wdepth[i] != level) return;
+  const float4 cf = nodes[8 * (size_t)i + 6];
+  const int ch[4] = {__float_as_int(cf.x), __float_as_int(cf.y), __float_as_int(cf.z), __float_as_int(cf.w)};
+  for (int k = 0; k < 4; ++k)
+    if (ch[k] >= 0 && ch[k] != kEmptyChild) wdepth[ch[k]] = level + 1;
+  atomicMax(&info->wide_depth, level);
 }
 
 }  // namespace b2pt
