@@ -208,6 +208,52 @@ int b2pt_read_accum(B2ptCtx* ctx, float* image_host, float* albedo_host);
  * persistent vector); b2pt_read_accum always copies. */
 int b2pt_pathtrace(B2ptCtx* ctx, int32_t iter, float* image_host, float* albedo_host);
 
+/* ---- pipelined pathtrace() --------------------------------------------------------
+ * The reference's host asks for ONE iteration per call, with consecutive
+ * iteration numbers (pathtrace(pbo, 0, ++iteration), apps/src/main.cpp:255), and
+ * reads scene->state.image after every call (apps/src/pathtrace.cu:663-668).
+ * A B2ptPipe serves exactly that contract with `lanes` contexts on one GPU:
+ * while the host consumes iteration i (merge into the running sum + copy to the
+ * host), the lanes already render i+stride, i+2*stride, ...  Each iteration is
+ * rendered once and merged in call order; the host image is bit-identical to
+ * b2pt_pathtrace() on a single context.  A call that does not continue the
+ * sequence (restart, another stride) drops the speculated iterations, adopts
+ * the new stride (iter - previous iter) and starts over; nothing is lost but
+ * the overlap.  (csrc/pipe.cu) */
+typedef struct B2ptPipe B2ptPipe;
+
+/* pathtraceInit for a pipelined host.  `opt` as for b2pt_create
+ * (concurrent_contexts is set to `lanes`; record_stages is refused).
+ * 1 <= lanes <= 16; 4 is what bench.py measures. */
+int b2pt_pipe_create(const B2ptScene* scene, const B2ptOptions* opt, int32_t lanes, B2ptPipe** out);
+
+/* pathtraceFree.  NULL is accepted. */
+void b2pt_pipe_destroy(B2ptPipe* pipe);
+
+/* One reference pathtrace(pbo, frame, iter) call: on return image_host holds
+ * the running sum including iteration `iter`, albedo_host the iteration-1
+ * albedo AOV (copied only when it changed or the pointer is new; either may be
+ * NULL).  Synchronous for the caller; the lanes keep rendering ahead. */
+int b2pt_pipe_pathtrace(B2ptPipe* pipe, int32_t iter, float* image_host, float* albedo_host);
+
+/* Zero the running sum, the albedo and every lane (Free + Init of
+ * apps/src/main.cpp:245-248); with `cam` != NULL also replace the camera. */
+int b2pt_pipe_reset(B2ptPipe* pipe, const B2ptCamera* cam);
+
+/* The running sum / the albedo AOV on the device (W*H*3 floats), valid after
+ * a b2pt_pipe_pathtrace call: the inputs of b2pt_tonemap_rgba8 and of a
+ * device-side denoiser. */
+float* b2pt_pipe_device_image(B2ptPipe* pipe);
+float* b2pt_pipe_device_albedo(B2ptPipe* pipe);
+
+/* Introspection: number of lanes, the context of lane k (statistics, BVH
+ * info, tonemap), kernel launches of all lanes + merges, and how often a call
+ * did not continue the predicted sequence. */
+int32_t b2pt_pipe_lanes(B2ptPipe* pipe);
+B2ptCtx* b2pt_pipe_lane(B2ptPipe* pipe, int32_t k);
+int64_t b2pt_pipe_launch_count(B2ptPipe* pipe);
+int64_t b2pt_pipe_misses(B2ptPipe* pipe);
+
 /* Device pointers of the accumulators (W*H*3 floats), for zero-copy hand-off
  * to a collective or a device-side denoiser. */
 float* b2pt_device_image(B2ptCtx* ctx);

@@ -22,7 +22,9 @@
 #include "b2pt.h"  // include/b2pt.h
 
 static Scene* hst_scene = NULL;
-static B2ptCtx* ctx = NULL;
+// main.cpp asks for one iteration per call with consecutive numbers (main.cpp:255): a B2ptPipe renders the
+// next ones on the same GPU while this one is copied to scene->state.image (B2PT_PIPE_LANES=1: no look-ahead)
+static B2ptPipe* pipe = NULL;
 static float* dev_denoised = NULL;
 static bool albedo_on_host = false;
 
@@ -101,7 +103,9 @@ void pathtraceInit(Scene* scene) {
   s.iterations = (int)scene->state.iterations;
   B2ptOptions opt;
   b2pt_default_options(&opt);  // = the macros of apps/src/pathtrace.cu:36-42
-  b2pt_check(b2pt_create(&s, &opt, &ctx), "pathtraceInit");
+  int lanes = 4;
+  if (const char* e = getenv("B2PT_PIPE_LANES")) lanes = atoi(e) > 0 ? atoi(e) : 1;
+  b2pt_check(b2pt_pipe_create(&s, &opt, lanes, &pipe), "pathtraceInit");
   cudaMalloc(&dev_denoised, sizeof(glm::vec3) * scene->state.image.size());
   albedo_on_host = false;
   // state.image / state.albedo are sized once by the loader (scene.cpp:379-381): page-lock them so that the
@@ -112,31 +116,30 @@ void pathtraceInit(Scene* scene) {
 }
 
 void pathtraceFree() {  // tolerates the Free-before-Init of apps/src/main.cpp:245-248
-  if (ctx && hst_scene) {
+  if (pipe && hst_scene) {
     cudaHostUnregister(hst_scene->state.image.data());
     cudaHostUnregister(hst_scene->state.albedo.data());
     cudaGetLastError();
   }
-  b2pt_destroy(ctx);
-  ctx = NULL;
+  b2pt_pipe_destroy(pipe);
+  pipe = NULL;
   cudaFree(dev_denoised);
   dev_denoised = NULL;
 }
 
 void pathtrace(uchar4* /*pbo*/, int /*frame*/, int iter) {  // pbo and frame are unused upstream too (AI_DENOISE 1)
-  timer().startGpuTimer();  // main.cpp:263 reads timer().getGpuElapsedTimeForPreviousOperation()
-  b2pt_check(b2pt_render(ctx, iter, 1, 1), "pathtrace");
-  b2pt_check(b2pt_sync(ctx), "pathtrace");
-  timer().endGpuTimer();
   // apps/src/pathtrace.cu:663-668: running sum and albedo AOV to scene->state every call; the albedo only
-  // changes on iteration 1 (pathtrace.cu:412), so later copies would rewrite the same bytes
-  float* albedo = (iter == 1 || !albedo_on_host) ? reinterpret_cast<float*>(hst_scene->state.albedo.data()) : NULL;
-  b2pt_check(b2pt_read_accum(ctx, reinterpret_cast<float*>(hst_scene->state.image.data()), albedo), "pathtrace");
+  // changes on iteration 1 (pathtrace.cu:412), the pipe skips the copies that would rewrite the same bytes
+  timer().startGpuTimer();  // main.cpp:263 reads timer().getGpuElapsedTimeForPreviousOperation()
+  b2pt_check(b2pt_pipe_pathtrace(pipe, iter, reinterpret_cast<float*>(hst_scene->state.image.data()),
+                                 reinterpret_cast<float*>(hst_scene->state.albedo.data())),
+             "pathtrace");
+  timer().endGpuTimer();
   albedo_on_host = true;
 }
 
 void sendToGPU(uchar4* pbo, int /*iter*/) {  // apps/src/pathtrace.cu:673-685
   cudaMemcpy(dev_denoised, hst_scene->state.output.data(), sizeof(glm::vec3) * hst_scene->state.output.size(),
              cudaMemcpyHostToDevice);
-  b2pt_check(b2pt_tonemap_rgba8(ctx, dev_denoised, 0, reinterpret_cast<uint8_t*>(pbo)), "sendToGPU");
+  b2pt_check(b2pt_tonemap_rgba8(b2pt_pipe_lane(pipe, 0), dev_denoised, 0, reinterpret_cast<uint8_t*>(pbo)), "sendToGPU");
 }

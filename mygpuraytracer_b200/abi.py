@@ -187,6 +187,16 @@ SYMBOLS = {
     "b2pt_sync": (C.c_int, [_vp]),
     "b2pt_read_accum": (C.c_int, [_vp, _vp, _vp]),
     "b2pt_pathtrace": (C.c_int, [_vp, _i32, _vp, _vp]),
+    "b2pt_pipe_create": (C.c_int, [C.POINTER(Scene), C.POINTER(Options), _i32, C.POINTER(_vp)]),
+    "b2pt_pipe_destroy": (None, [_vp]),
+    "b2pt_pipe_pathtrace": (C.c_int, [_vp, _i32, _vp, _vp]),
+    "b2pt_pipe_reset": (C.c_int, [_vp, C.POINTER(Camera)]),
+    "b2pt_pipe_device_image": (_vp, [_vp]),
+    "b2pt_pipe_device_albedo": (_vp, [_vp]),
+    "b2pt_pipe_lanes": (_i32, [_vp]),
+    "b2pt_pipe_lane": (_vp, [_vp, _i32]),
+    "b2pt_pipe_launch_count": (_i64, [_vp]),
+    "b2pt_pipe_misses": (_i64, [_vp]),
     "b2pt_device_image": (_vp, [_vp]),
     "b2pt_device_albedo": (_vp, [_vp]),
     "b2pt_set_device_image": (C.c_int, [_vp, _vp]),

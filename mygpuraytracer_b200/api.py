@@ -287,6 +287,73 @@ class Renderer:
 
 
 # ---------------------------------------------------------------------------------------
+# Pipeline: pathtrace() one iteration per call, the next ones rendered ahead (csrc/pipe.cu)
+# ---------------------------------------------------------------------------------------
+class Pipeline:
+    """``lanes`` contexts on one GPU behind the one-iteration-per-call contract of
+    ``pathtrace(pbo, frame, iter)`` (apps/src/main.cpp:255, apps/src/pathtrace.cu:663-668)."""
+
+    def __init__(self, scene, options: Optional[abi.Options] = None, lanes: int = 4, **opt_kw):
+        self.lib = load_library()
+        self.pod: PodScene = scene.pod if isinstance(scene, Scene) else scene
+        self.options = options if options is not None else abi.default_options(**opt_kw)
+        self._cscene = self.pod.as_ctypes()
+        self._h = C.c_void_p()
+        _check(self.lib.b2pt_pipe_create(C.byref(self._cscene), C.byref(self.options), lanes, C.byref(self._h)))
+        self.n_pixels = self.pod.n_pixels
+        self.lanes = lanes
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.b2pt_pipe_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # pragma: no cover - interpreter shutdown
+            pass
+
+    def pathtrace(self, iteration: int, image: np.ndarray, albedo: Optional[np.ndarray]) -> None:
+        _check(self.lib.b2pt_pipe_pathtrace(self._h, iteration, image.ctypes.data,
+                                            albedo.ctypes.data if albedo is not None else None))
+
+    def reset(self, camera: Optional[np.ndarray] = None) -> None:
+        if camera is None:
+            _check(self.lib.b2pt_pipe_reset(self._h, None))
+            return
+        cam = abi.Camera()
+        C.memmove(C.byref(cam), np.ascontiguousarray(camera).ctypes.data, C.sizeof(abi.Camera))
+        _check(self.lib.b2pt_pipe_reset(self._h, C.byref(cam)))
+
+    def device_image_ptr(self) -> int:
+        return int(self.lib.b2pt_pipe_device_image(self._h) or 0)
+
+    def device_albedo_ptr(self) -> int:
+        return int(self.lib.b2pt_pipe_device_albedo(self._h) or 0)
+
+    def launch_count(self) -> int:
+        return int(self.lib.b2pt_pipe_launch_count(self._h))
+
+    def misses(self) -> int:
+        return int(self.lib.b2pt_pipe_misses(self._h))
+
+    def last_loop_ms(self) -> float:
+        return float(self.lib.b2pt_last_loop_ms(self.lib.b2pt_pipe_lane(self._h, 0)))
+
+    def tonemap_rgba8(self, dst_ptr: int, iteration: int, src_ptr: int = 0) -> None:
+        """``sendImageToPBO`` of the running sum (or of ``src_ptr``)."""
+        _check(self.lib.b2pt_tonemap_rgba8(self.lib.b2pt_pipe_lane(self._h, 0),
+                                           C.c_void_p(src_ptr or self.device_image_ptr()), iteration, C.c_void_p(dst_ptr)))
+
+
+# ---------------------------------------------------------------------------------------
 # standalone primitives (apps/stream_compaction surface)
 # ---------------------------------------------------------------------------------------
 def scan_exclusive(a: np.ndarray) -> np.ndarray:
@@ -328,8 +395,9 @@ def radix_sort_pairs(keys: np.ndarray, vals: np.ndarray):
 # the reference's five free functions (global state, like apps/src/pathtrace.cu:118-128)
 # ---------------------------------------------------------------------------------------
 _hst_scene: Optional[Scene] = None
-_renderer: Optional[Renderer] = None
+_renderer = None  # Renderer, or Pipeline after set_pipeline_lanes(n > 1)
 _options_for_next_init: Optional[abi.Options] = None
+_lanes_for_next_init: int = 1
 
 
 class _Timer:
@@ -352,12 +420,21 @@ def set_options(options: Optional[abi.Options]) -> None:
     _options_for_next_init = options
 
 
+def set_pipeline_lanes(lanes: int) -> None:
+    """``lanes`` > 1: the next :func:`pathtraceInit` serves ``pathtrace`` from a :class:`Pipeline`."""
+    global _lanes_for_next_init
+    _lanes_for_next_init = max(1, int(lanes))
+
+
 def pathtraceInit(scene: Scene) -> None:
     global _hst_scene, _renderer
     if _renderer is not None:
         _renderer.close()
     _hst_scene = scene
-    _renderer = Renderer(scene, _options_for_next_init)
+    if _lanes_for_next_init > 1:
+        _renderer = Pipeline(scene, _options_for_next_init, lanes=_lanes_for_next_init)
+    else:
+        _renderer = Renderer(scene, _options_for_next_init)
 
 
 def pathtraceFree() -> None:

@@ -88,6 +88,9 @@ __global__ void __launch_bounds__(256) k_centroid_bounds(const float* __restrict
   }
 }
 
+#ifndef B2PT_MORTON_UNIFORM
+#define B2PT_MORTON_UNIFORM 1
+#endif
 __device__ __forceinline__ unsigned int expand10(unsigned int v) {
   v = (v * 0x00010001u) & 0xFF0000FFu;
   v = (v * 0x00000101u) & 0x0F00F00Fu;
@@ -104,8 +107,14 @@ __global__ void __launch_bounds__(256) k_morton(const float* __restrict__ face_p
   for (int k = 0; k < 9; ++k) fp[k] = face_pos[9 * (size_t)i + k];
   const V3 c = tri_centroid(fp);
   const float lx = ord2f(b->lo[0]), ly = ord2f(b->lo[1]), lz = ord2f(b->lo[2]);
-  const float ex = fmaxf(ord2f(b->hi[0]) - lx, 1e-30f), ey = fmaxf(ord2f(b->hi[1]) - ly, 1e-30f);
-  const float ez = fmaxf(ord2f(b->hi[2]) - lz, 1e-30f);
+  float ex = fmaxf(ord2f(b->hi[0]) - lx, 1e-30f), ey = fmaxf(ord2f(b->hi[1]) - ly, 1e-30f);
+  float ez = fmaxf(ord2f(b->hi[2]) - lz, 1e-30f);
+#if B2PT_MORTON_UNIFORM
+  // cubic cells: the grid spans the longest axis on all three, so the radix splits cut boxes towards cubes
+  // instead of keeping the aspect ratio of the mesh (tools/exp_tree_quality.c: -4 % node visits, -6 % long
+  // walks on the stand-in hull, whose extent is 4.6 x 1.9 x 4.8)
+  ex = ey = ez = fmaxf(ex, fmaxf(ey, ez));
+#endif
   const unsigned int qx = (unsigned int)fminf(fmaxf((c.x - lx) / ex * 1024.0f, 0.0f), 1023.0f);
   const unsigned int qy = (unsigned int)fminf(fmaxf((c.y - ly) / ey * 1024.0f, 0.0f), 1023.0f);
   const unsigned int qz = (unsigned int)fminf(fmaxf((c.z - lz) / ez * 1024.0f, 0.0f), 1023.0f);
