@@ -366,7 +366,11 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     # 148 SMs on their own (a depth-7 launch has 250 k rays); independent
     # iterations in flight overlap each other's tails.
     KC = max(1, args.streams)
-    rs = [api.Renderer(scene, opt_shared) for _ in range(KC)]
+    rs = [api.Renderer(scene, opt_shared)]
+    if args.private_scenes:
+        rs += [api.Renderer(scene, opt_shared) for _ in range(KC - 1)]
+    else:  # one copy of the scene (BVH, triangles, textures) on the device, shared by the KC contexts
+        rs += [api.Renderer(scene, opt_shared, share=rs[0]) for _ in range(KC - 1)]
     r = rs[0]
     mesh_geom = int(np.nonzero(pod.geoms["type"] == abi.OBJ)[0][0])
     # every context builds its own BVH; the first build of a process also pays CUDA's lazy kernel loading
@@ -583,6 +587,7 @@ def main():
     ap.add_argument("--triangles", type=int, default=250_000)
     ap.add_argument("--streams", type=int, default=4, help="concurrent iteration streams (contexts) per GPU")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / reference_gpu legs")
+    ap.add_argument("--private-scenes", action="store_true", help="every context uploads its own copy of the scene (A/B of b2pt_create_shared)")
     ap.add_argument("--ref-gpu-iters", type=int, default=1)
     ap.add_argument("--ref-gpu-timeout", type=int, default=240)
     args = ap.parse_args()

@@ -174,6 +174,16 @@ typedef struct B2ptCtx B2ptCtx;
  * state, hit records and the zeroed accumulation / albedo images. */
 int b2pt_create(const B2ptScene* scene, const B2ptOptions* opt, B2ptCtx** out);
 
+/* Another context on the parent's GPU that SHARES the parent's scene on the
+ * device (geoms, materials, BVHs, triangles, textures: read only for every
+ * kernel) and owns only its path state and accumulators.  `scene` must be the
+ * scene the parent was created from (camera, resolution and depth are taken
+ * from it).  Contexts that render the same scene at once (b2pt_pipe_*, spp
+ * sharding inside a GPU) then walk ONE BVH, which stays resident in L2, instead
+ * of one copy each.  The shared data lives until the last context using it is
+ * destroyed; parent and children may be destroyed in any order. */
+int b2pt_create_shared(B2ptCtx* parent, const B2ptScene* scene, const B2ptOptions* opt, B2ptCtx** out);
+
 /* pathtraceFree (apps/src/pathtrace.cu:196-223).  NULL is accepted. */
 void b2pt_destroy(B2ptCtx* ctx);
 

@@ -180,6 +180,7 @@ _i32p, _u8p, _u32p = C.POINTER(C.c_int32), C.POINTER(C.c_uint8), C.POINTER(C.c_u
 SYMBOLS = {
     "b2pt_default_options": (None, [C.POINTER(Options)]),
     "b2pt_create": (C.c_int, [C.POINTER(Scene), C.POINTER(Options), C.POINTER(_vp)]),
+    "b2pt_create_shared": (C.c_int, [_vp, C.POINTER(Scene), C.POINTER(Options), C.POINTER(_vp)]),
     "b2pt_destroy": (None, [_vp]),
     "b2pt_set_camera": (C.c_int, [_vp, C.POINTER(Camera)]),
     "b2pt_reset_accum": (C.c_int, [_vp]),

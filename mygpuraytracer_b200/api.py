@@ -135,13 +135,18 @@ class Scene:
 # Renderer: one context
 # ---------------------------------------------------------------------------------------
 class Renderer:
-    def __init__(self, scene, options: Optional[abi.Options] = None, **opt_kw):
+    def __init__(self, scene, options: Optional[abi.Options] = None, share: Optional["Renderer"] = None, **opt_kw):
+        """``share``: a Renderer of the SAME scene on the same GPU whose device copy of the scene (BVH,
+        triangles, textures) this context uses instead of uploading its own (``b2pt_create_shared``)."""
         self.lib = load_library()
         self.pod: PodScene = scene.pod if isinstance(scene, Scene) else scene
         self.options = options if options is not None else abi.default_options(**opt_kw)
         self._cscene = self.pod.as_ctypes()
         self._h = C.c_void_p()
-        _check(self.lib.b2pt_create(C.byref(self._cscene), C.byref(self.options), C.byref(self._h)))
+        if share is not None:
+            _check(self.lib.b2pt_create_shared(share._h, C.byref(self._cscene), C.byref(self.options), C.byref(self._h)))
+        else:
+            _check(self.lib.b2pt_create(C.byref(self._cscene), C.byref(self.options), C.byref(self._h)))
         self.n_pixels = self.pod.n_pixels
 
     # -- lifetime ------------------------------------------------------------------------

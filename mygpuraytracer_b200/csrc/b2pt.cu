@@ -25,6 +25,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -111,6 +112,15 @@ struct StageRecord {
   int n_live_out = 0;
 };
 
+struct SceneStore {
+  int device = 0;
+  std::vector<void*> allocs;
+  ~SceneStore() {
+    cudaSetDevice(device);
+    for (void* p : allocs) cudaFree(p);
+  }
+};
+
 struct B2ptCtx {
   int device = 0;
   cudaStream_t stream = nullptr;      // where work is queued
@@ -121,7 +131,11 @@ struct B2ptCtx {
   int sm_count = 0;
   float origin_world = 0.0f;  // rays start inside [-origin_world, origin_world]^3 (BVH padding, set_camera check)
 
-  std::vector<void*> allocs;  // every cudaMalloc, freed in b2pt_destroy
+  std::vector<void*> allocs;  // every cudaMalloc of this context, freed in b2pt_destroy
+  // geoms, materials, BVHs, triangles and textures: owned by the first context of a scene and shared (read
+  // only) with the contexts created from it by b2pt_create_shared; freed with the last of them
+  std::shared_ptr<SceneStore> scene_store;
+  bool alloc_to_scene = false;
   std::vector<MeshBuild> meshes;
   std::vector<int> geom_mesh;
   DevScene dscene{};
@@ -182,7 +196,7 @@ struct B2ptCtx {
     void* q = nullptr;
     cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
     if (e != cudaSuccess) return fail(B2PT_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
-    allocs.push_back(q);
+    (alloc_to_scene && scene_store ? scene_store->allocs : allocs).push_back(q);
     *p = (T*)q;
     return 0;
   }
@@ -450,7 +464,7 @@ static int upload_texture(B2ptCtx* c, const B2ptScene* sc, int idx, DevTexture* 
   return 0;
 }
 
-static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* c) {
+static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* c, B2ptCtx* parent = nullptr) {
   B2ptOptions opt;
   b2pt_default_options(&opt);
   if (opt_in) {
@@ -490,6 +504,23 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
   CK(cudaEventCreate(&c->ev_loop_b));
 
   int rc;
+  if (parent) {
+    // the scene already lives on this device: share it (read only) instead of uploading and building again
+    if (parent->device != c->device) return fail(B2PT_ERR_INVALID, "a shared context must be on its parent's device");
+    if (parent->n_geoms != sc->n_geoms || parent->n_materials != sc->n_materials)
+      return fail(B2PT_ERR_INVALID, "b2pt_create_shared: `scene` is not the scene the parent was created from");
+    c->scene_store = parent->scene_store;
+    c->origin_world = parent->origin_world;
+    c->geom_mesh = parent->geom_mesh;
+    c->meshes = parent->meshes;
+    c->dscene = parent->dscene;
+    c->l2_window_ptr = parent->l2_window_ptr;
+    c->l2_window_bytes = parent->l2_window_bytes;
+    if (c->l2_window_ptr) apply_l2_policy(c, c->stream);
+  } else {
+  c->scene_store = std::make_shared<SceneStore>();
+  c->scene_store->device = c->device;
+  c->alloc_to_scene = true;
   // ---- where rays can start: every geom's world box and the camera, with a 4x margin for camera moves ----
   float origin_world = 0.0f;
   for (int k = 0; k < 3; ++k) origin_world = std::max(origin_world, std::fabs(sc->camera.position[k]));
@@ -607,6 +638,8 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
   c->dscene.n_geoms = sc->n_geoms;
   c->dscene.n_meshes = (int)hm.size();
   c->dscene.n_materials = sc->n_materials;
+  c->alloc_to_scene = false;
+  }  // !parent
 
   // ---- wavefront buffers -------------------------------------------------------------
   const size_t P = (size_t)c->P;
@@ -749,12 +782,23 @@ extern "C" void b2pt_destroy(B2ptCtx* c) {
   delete c;
 }
 
+static int create_ctx(const B2ptScene* scene, const B2ptOptions* opt, B2ptCtx* parent, B2ptCtx** out);
+
 extern "C" int b2pt_create(const B2ptScene* scene, const B2ptOptions* opt, B2ptCtx** out) {
+  return create_ctx(scene, opt, nullptr, out);
+}
+
+extern "C" int b2pt_create_shared(B2ptCtx* parent, const B2ptScene* scene, const B2ptOptions* opt, B2ptCtx** out) {
+  if (!parent) return fail(B2PT_ERR_INVALID, "parent is NULL");
+  return create_ctx(scene, opt, parent, out);
+}
+
+static int create_ctx(const B2ptScene* scene, const B2ptOptions* opt, B2ptCtx* parent, B2ptCtx** out) {
   if (!scene || !out) return fail(B2PT_ERR_INVALID, "scene and out must not be NULL");
   *out = nullptr;
   B2ptCtx* c = new (std::nothrow) B2ptCtx();
   if (!c) return fail(B2PT_ERR_NOMEM, "out of host memory");
-  int rc = create_impl(scene, opt, c);
+  int rc = create_impl(scene, opt, c, parent);
   if (rc != 0) {
     std::string keep = g_last_error;
     b2pt_destroy(c);

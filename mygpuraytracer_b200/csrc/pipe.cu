@@ -22,6 +22,7 @@
 // Built on the public C ABI of include/b2pt.h only.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
 #include <new>
 #include <string>
 #include <vector>
@@ -176,7 +177,10 @@ extern "C" int b2pt_pipe_create(const B2ptScene* scene, const B2ptOptions* opt, 
   if (e != cudaSuccess) rc = pipe_fail(B2PT_ERR_CUDA, std::string("b2pt_pipe_create: ") + cudaGetErrorString(e));
   for (int k = 0; k < lanes && rc == 0; ++k) {
     Lane& L = p->lanes[(size_t)k];
-    rc = b2pt_create(scene, &o, &L.ctx);
+    // one copy of the scene on the device: every lane walks the same BVH, which then stays resident in L2
+    // (B2PT_PIPE_PRIVATE_SCENES=1: a copy per lane, for A/B measurements)
+    const bool share = k > 0 && !getenv("B2PT_PIPE_PRIVATE_SCENES");
+    rc = share ? b2pt_create_shared(p->lanes[0].ctx, scene, &o, &L.ctx) : b2pt_create(scene, &o, &L.ctx);
     if (rc) break;
     L.stream = (cudaStream_t)b2pt_stream(L.ctx);
     if (cudaEventCreateWithFlags(&L.rendered, cudaEventDisableTiming) != cudaSuccess ||

@@ -114,3 +114,29 @@ def test_pipe_rejects_bad_arguments(tmp_path):
         api.Pipeline(pod, abi.default_options(), lanes=0)
     with pytest.raises(api.B2ptError):
         api.Pipeline(pod, abi.default_options(record_stages=1), lanes=2)
+
+
+def test_shared_scene_contexts_bitexact_and_outlive_their_parent(tmp_path):
+    """b2pt_create_shared: contexts that use the parent's device copy of the scene render the same bits, also
+    after the parent has been destroyed (the shared data lives until its last user goes)."""
+    pod = _mesh_scene(tmp_path, "cornellSpaceship", 128, 72, 5000)
+    n = pod.n_pixels
+    with api.Renderer(pod, abi.default_options()) as alone:
+        alone.render(1, 3, 1)
+        ref, ref_alb = alone.read()
+    parent = api.Renderer(pod, abi.default_options(concurrent_contexts=3))
+    kids = [api.Renderer(pod, abi.default_options(concurrent_contexts=3), share=parent) for _ in range(2)]
+    assert kids[0].bvh_info(int(np.nonzero(pod.geoms["type"] == abi.OBJ)[0][0])).n_faces == parent.bvh_info(
+        int(np.nonzero(pod.geoms["type"] == abi.OBJ)[0][0])).n_faces
+    parent.render(1, 3, 1)
+    img, alb = parent.read()
+    assert_same_bits(ref, img, "parent of shared contexts")
+    parent.close()
+    for k in kids:  # both at once, on their own streams, after the parent is gone
+        k.render(1, 3, 1)
+    for k in kids:
+        img, alb = k.read()
+        assert_same_bits(ref, img, "shared context image")
+        assert_same_bits(ref_alb, alb, "shared context albedo")
+        k.close()
+    assert n > 0
