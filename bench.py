@@ -452,6 +452,8 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     img_np, alb_np = host_img.numpy().reshape(P, 3), host_alb.numpy().reshape(P, 3)
     r_e2e = api.Renderer(scene, opt)
     r_e2e.set_stream_ptr(stream.cuda_stream)
+    # the first LBVH build of a process also pays CUDA's lazy kernel loading; this context builds its own
+    bvh = min([bvh, r_e2e.bvh_info(mesh_geom)], key=lambda b: b.build_ms)
     with torch.cuda.stream(stream):
         r = r_e2e
         for i in range(min(W, 3)):
@@ -556,7 +558,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                               "the analytic intersection is fused into generate / shade (k_generate_trace, k_shade_trace)",
             "segments_per_step": segments, "live_paths_per_depth": [int(x) for x in live[: args.depth + 1]],
             "bvh": {"triangles": int(bvh.n_faces), "nodes": int(bvh.n_nodes), "max_depth": int(bvh.max_depth),
-                    "build_ms": float(bvh.build_ms), "build_ms_note": "device time, fastest of the contexts of this process"},
+                    "build_ms": float(bvh.build_ms), "build_ms_note": "device time, fastest build of this process (the first one also pays CUDA's lazy kernel loading)"},
             "scene_load_s": round(load_s, 2), "image_checksum": checksum,
         }
         if world == 1 and not args.no_cpu:
