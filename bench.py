@@ -515,13 +515,23 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "k_mesh_walk_long": ("walk_long", 57.0 * n_long),
             # per queued ray: queue slot 4 B + partial record 20 B read, record 32 B + flag 1 B written
             "k_mesh_finish": ("finish", 57.0 * n_walks),
-            "k_sort_material": ("sort", 6.0 * segments),       # key 1 B + flag 1 B read, permutation 4 B written
+            "k_sort_material": ("sort", 10.0 * segments),      # key 1 B + flag 1 B read, permutation 4 B + compaction rank 4 B written
             "k_shade_compact": ("shade", 132.0 * segments),    # permutation 4 B + hit 32 B + state 48 B read, state 48 B written
         }
         dom = max(kern, key=lambda k: prof[kern[k][0]])
         dom_ms = prof[kern[dom][0]]
         dom_bytes = kern[dom][1]
         dom_gbs = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+        # every kernel of the iteration against the HBM roofline: algorithmic bytes (kernel table) over
+        # its device time in one iteration of a context running alone with the shared-SM grids of the timed region
+        kern_all = dict(kern)
+        kern_all["k_generate"] = ("generate", 44.0 * P)
+        roofline_kernels = {}
+        for name, (key, nbytes) in kern_all.items():
+            kms = prof.get(key, 0.0)
+            gbs = nbytes / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
+            roofline_kernels[name] = {"ms_per_step": kms, "algorithmic_bytes_per_step": nbytes, "achieved": gbs,
+                                      "unit": "GB/s", "frac": gbs / peak}
         iter_bytes = 84.0 * P + 280.0 * segments
         iter_gbs = iter_bytes / (ms_max / K * 1e-3) / 1e9
         line = {
@@ -551,6 +561,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                                  "bound: see profiles/ for issue-slot, FP32-pipe and divergence counters"},
             "roofline_iter": {"bytes_per_step": iter_bytes, "achieved": iter_gbs, "peak": peak, "unit": "GB/s",
                               "frac": iter_gbs / peak, "formula": "84*P + 280*S"},
+            "roofline_kernels": roofline_kernels,
             "kernel_ms_per_step": prof,
             "kernel_ms_per_step_full_width": prof_full,
             "kernel_ms_note": "CUDA events around every launch of one iteration run alone: with the grids of the timed "
