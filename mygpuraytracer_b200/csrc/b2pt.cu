@@ -709,7 +709,7 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
   else
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mesh_walk<false>, kWalkThreads, 0));
   c->walk_grid = c->sm_count * std::max(occ, 1);
-  if (const char* e = getenv("B2PT_WALK_CTAS")) c->walk_grid = c->sm_count * std::max(1, std::min(atoi(e), std::max(occ, 1)));
+  const int walk_occ = std::max(occ, 1);  // B2PT_WALK_CTAS is applied below, after the shared-SM sizing
   c->finish_grid = c->sm_count * 8;
   c->shade_stride_grid = c->sm_count * 12;
   c->gen_trace_grid = (int)std::min<size_t>((P + 255) / 256, (size_t)c->sm_count * 8);
@@ -734,6 +734,7 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
     c->shade_stride_grid = c->sm_count * 4;
   }
   // experiment knobs: resident CTAs per SM of the persistent / grid-stride kernels
+  if (const char* e = getenv("B2PT_WALK_CTAS")) c->walk_grid = c->sm_count * std::max(1, std::min(atoi(e), walk_occ));
   if (const char* e = getenv("B2PT_LONG_CTAS")) c->long_grid = c->sm_count * std::max(1, atoi(e));
   if (const char* e = getenv("B2PT_ANALYTIC_CTAS")) c->analytic_grid = c->sm_count * std::max(1, atoi(e));
   if (const char* e = getenv("B2PT_FINISH_CTAS")) c->finish_grid = c->sm_count * std::max(1, atoi(e));
