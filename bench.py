@@ -544,7 +544,9 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                             "one iteration per call, host image after every call",
                     "ms_per_step": float(tp.item()) / K, "lanes": KC, "mispredicted_calls": int(pipe_misses),
                     "note": "steady state of the pipeline: the lanes hold the next %d iterations when the timed region "
-                            "starts and when it ends; K iterations are rendered and K consumed inside it" % KC},
+                            "starts and when it ends; K iterations are rendered and K consumed inside it.  The copy to the host "
+                            "and the merge overlap the other lanes' kernels, so this leg is bound by the same %d-context GPU "
+                            "throughput as `value` (e2e_single_context is the unoverlapped form)" % (KC, KC)},
             "e2e_single_context": {"value": e2e_value, "unit": METRIC, "ms_per_step": float(t.item()) / K,
                                    "call": "b2pt_pathtrace(ctx, iter, host_image, host_albedo): render, then copy, nothing overlapped"},
             "gpu_launches": int(launches), "streams_per_gpu": KC,
