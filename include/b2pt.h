@@ -307,6 +307,12 @@ int b2pt_resolve_rgb8(B2ptCtx* ctx, int32_t aov, int32_t samples, int32_t mirror
  * PNG at `path` (the caller composes the "<FILE>.<time>.<n>samp.png" name). */
 int b2pt_save_png(B2ptCtx* ctx, int32_t aov, int32_t samples, const char* path);
 
+/* saveImage + image::saveHDR (apps/src/image.cpp:41-45; the call is commented
+ * out at apps/src/main.cpp:163): the same mirrored AOV, unquantised, as a
+ * Radiance .hdr file.  The RGBE pixels are the ones stbi_write_hdr produces;
+ * scanlines are stored flat instead of run-length encoded. */
+int b2pt_save_hdr(B2ptCtx* ctx, int32_t aov, int32_t samples, const char* path);
+
 /* The denoiser's "color" input (CPUdenoise, apps/src/main.cpp:189-203):
  * color = image / (float)iter as W*H Float3, written to color_dev (device
  * memory, may be NULL) and/or color_host (may be NULL).  Together with

@@ -209,6 +209,7 @@ SYMBOLS = {
     "b2pt_tonemap_rgba8": (C.c_int, [_vp, _vp, _i32, _vp]),
     "b2pt_resolve_rgb8": (C.c_int, [_vp, _i32, _i32, _i32, _vp]),
     "b2pt_save_png": (C.c_int, [_vp, _i32, _i32, C.c_char_p]),
+    "b2pt_save_hdr": (C.c_int, [_vp, _i32, _i32, C.c_char_p]),
     "b2pt_resolve_color": (C.c_int, [_vp, _i32, _vp, _vp]),
     "b2pt_live_counts": (C.c_int, [_vp, _i32p, _i32]),
     "b2pt_walk_counts": (C.c_int, [_vp, _i32p, _i32p, _i32]),

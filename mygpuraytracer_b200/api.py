@@ -204,6 +204,10 @@ class Renderer:
     def save_png(self, path: str, aov: int = abi.AOV_IMAGE, samples: int = 1) -> None:
         _check(self.lib.b2pt_save_png(self._h, aov, samples, os.fsencode(path)))
 
+    def save_hdr(self, path: str, aov: int = abi.AOV_IMAGE, samples: int = 1) -> None:
+        """``saveImage`` + ``image::saveHDR`` (apps/src/image.cpp:41-45)."""
+        _check(self.lib.b2pt_save_hdr(self._h, aov, samples, os.fsencode(path)))
+
     def resolve_color(self, iteration: int, color_dev: int = 0) -> np.ndarray:
         """``image / iteration`` as Float3: the denoiser's colour input (main.cpp:194-201)."""
         out = np.empty((self.n_pixels, 3), np.float32)

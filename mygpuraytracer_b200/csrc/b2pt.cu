@@ -38,6 +38,7 @@
 #include "k_sort.cuh"
 #include "k_walk.cuh"
 #include "k_fused.cuh"
+#include "host/hdr_writer.h"
 #include "host/png_writer.h"
 #include "pt_device.cuh"
 
@@ -1414,6 +1415,30 @@ extern "C" int b2pt_resolve_color(B2ptCtx* c, int32_t iter, float* color_dev, fl
   }
   if (!color_dev) cudaFree(d);
   if (e != cudaSuccess) return fail(B2PT_ERR_CUDA, cudaGetErrorString(e));
+  return 0;
+}
+
+// saveImage + image::saveHDR (main.cpp:115-135,163, image.cpp:41-45): the mirrored image / samples (or the
+// albedo as it is) as a Radiance RGBE file.  The division runs on the device (k_resolve_color, IEEE like
+// glm's vec3 / float), mirror and encoding on the host (csrc/host/hdr_writer.h).
+extern "C" int b2pt_save_hdr(B2ptCtx* c, int32_t aov, int32_t samples, const char* path) {
+  if (!c || !path) return fail(B2PT_ERR_INVALID, "ctx and path must not be NULL");
+  if (aov != B2PT_AOV_IMAGE && aov != B2PT_AOV_ALBEDO) return fail(B2PT_ERR_INVALID, "aov must be B2PT_AOV_IMAGE or B2PT_AOV_ALBEDO");
+  std::vector<float> px((size_t)c->P * 3);
+  int rc;
+  if (aov == B2PT_AOV_IMAGE) {
+    if (samples <= 0) return fail(B2PT_ERR_INVALID, "samples must be > 0");
+    rc = b2pt_resolve_color(c, samples, nullptr, px.data());
+  } else {
+    rc = b2pt_read_accum(c, nullptr, px.data());
+  }
+  if (rc) return rc;
+  std::vector<float> mirrored(px.size());
+  for (int y = 0; y < c->H; ++y)
+    for (int x = 0; x < c->W; ++x)
+      memcpy(&mirrored[((size_t)y * c->W + (c->W - 1 - x)) * 3], &px[((size_t)y * c->W + x) * 3], 12);
+  const std::string err = b2pt_host::write_hdr_rgb(path, c->W, c->H, mirrored.data());
+  if (!err.empty()) return fail(B2PT_ERR_IO, err);
   return 0;
 }
 

@@ -321,6 +321,32 @@ def save_image_rgb8(image: np.ndarray, width: int, height: int, samples: float =
     return out[:, ::-1, :].copy() if mirror_x else out
 
 
+def save_image_rgbe(image: np.ndarray, width: int, height: int, samples: float = 1.0, divide: bool = True,
+                    mirror_x: bool = True) -> np.ndarray:
+    """saveImage + image::saveHDR (apps/src/main.cpp:115-135,163, apps/src/image.cpp:41-45): the pixels are
+    mirrored and divided as for the PNG, then stb_image_write's Radiance encoder turns each into shared-exponent
+    RGBE (Ward's float2rgbe as stbi_write_hdr states it): with m the largest channel, a pixel below 1e-32 is
+    four zero bytes, otherwise ``frexp(m) = (f, e)``, ``scale = float(f) * 256.0f / m`` in single precision,
+    mantissas ``(unsigned char)(channel * scale)`` (truncation) and exponent byte ``e + 128``.
+    Returns (H, W, 4) uint8.  Pinned against the reference's own image.cpp (tests/golden/hdr_golden.npz)."""
+    v = np.asarray(image, np.float32).reshape(height, width, 3)
+    if divide:
+        v = (v / np.float32(samples)).astype(np.float32)
+    if mirror_x:
+        v = v[:, ::-1, :]
+    m = np.maximum(v[..., 0], np.maximum(v[..., 1], v[..., 2])).astype(np.float32)
+    live = ~(m.astype(np.float64) < 1e-32)
+    f, e = np.frexp(np.where(live, m, np.float32(1)))
+    scale = (f.astype(np.float32) * np.float32(256.0)).astype(np.float32)
+    scale = (scale / np.where(live, m, np.float32(1))).astype(np.float32)
+    out = np.zeros((height, width, 4), np.uint8)
+    for c in range(3):
+        out[..., c] = (v[..., c] * scale).astype(np.float32).astype(np.int32).astype(np.uint8)
+    out[..., 3] = (e + 128).astype(np.uint8)
+    out[~live] = 0
+    return out
+
+
 def denoise_color(image: np.ndarray, iteration: int) -> np.ndarray:
     """inputColor[index] = image[index] / (float)iteration (CPUdenoise, apps/src/main.cpp:194-199)."""
     return (np.asarray(image, np.float32) / np.float32(iteration)).astype(np.float32)

@@ -146,3 +146,77 @@ def test_saved_render_matches_oracle_and_reference_writer(tmp_path):
         img.astype(np.float32).tofile(raw)
         subprocess.check_call([REF_PNG, raw, "96", "64", str(n), "1", str(tmp_path / "ref")], stdout=subprocess.DEVNULL)
         assert np.array_equal(decode_png_rgb8(str(tmp_path / "ref.png")), want_img)
+
+
+# ---- saveImage + image::saveHDR (apps/src/image.cpp:41-45; the call is commented out at main.cpp:163) ----------
+REF_HDR = os.path.join(ROOT, "oracle", "_ref", "ref_hdr")
+
+
+def _hdr_golden():
+    z = np.load(os.path.join(GOLDEN, "hdr_golden.npz"))
+    for tag in "ab":
+        w, h, samples = (int(x) for x in z[f"{tag}_dims"])
+        yield z[f"{tag}_image"], w, h, samples, z[f"{tag}_divided"], z[f"{tag}_plain"]
+
+
+def test_oracle_rgbe_matches_the_reference_hdr_pixels():
+    """The numpy restatement of stbi_write_hdr's pixel encoding against RGBE bytes decoded from files the
+    REFERENCE'S OWN image.cpp + stb_image_write wrote (RLE scanlines at width 37, flat ones at width 5)."""
+    from util import decode_hdr_rgbe  # noqa: F401  (the decoder made the golden arrays)
+
+    for img, w, h, samples, divided, plain in _hdr_golden():
+        assert np.array_equal(oracle.save_image_rgbe(img, w, h, samples, divide=True), divided)
+        assert np.array_equal(oracle.save_image_rgbe(img, w, h, samples, divide=False), plain)
+        assert np.array_equal(oracle.save_image_rgbe(img, w, h, samples, mirror_x=False)[:, ::-1], divided)
+        assert divided[..., 3].max() > 128 and (divided == 0).all(axis=-1).any(), "large radiances and the 1e-32 cut-off are covered"
+
+
+def test_hdr_writer_on_its_own(tmp_path):
+    """csrc/host/hdr_writer.h compiled with g++ (no GPU): the files decode to the reference's RGBE pixels."""
+    from util import decode_hdr_rgbe
+
+    src = tmp_path / "t.cpp"
+    src.write_text(
+        '#include <stdio.h>\n#include <stdlib.h>\n#include <vector>\n'
+        f'#include "{ROOT}/mygpuraytracer_b200/csrc/host/hdr_writer.h"\n'
+        'int main(int argc, char** argv) { int w = atoi(argv[2]), h = atoi(argv[3]); std::vector<float> px((size_t)w * h * 3);\n'
+        '  FILE* f = fopen(argv[1], "rb"); if (!f || fread(px.data(), 4, px.size(), f) != px.size()) return 2; fclose(f);\n'
+        '  std::string e = b2pt_host::write_hdr_rgb(argv[4], w, h, px.data()); if (!e.empty()) { puts(e.c_str()); return 1; }\n'
+        '  return b2pt_host::write_hdr_rgb("/nonexistent_dir/x.hdr", w, h, px.data()).empty() ? 3 : 0; }\n')
+    exe = tmp_path / "t"
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", str(src), "-o", str(exe)])
+    for k, (img, w, h, samples, divided, plain) in enumerate(_hdr_golden()):
+        # the writer takes the pixels saveImage hands to image::saveHDR: mirrored, not divided here
+        px = img.reshape(h, w, 3)[:, ::-1, :].astype(np.float32)
+        raw, out = tmp_path / f"in{k}.raw", tmp_path / f"o{k}.hdr"
+        np.ascontiguousarray(px).tofile(raw)
+        subprocess.check_call([str(exe), str(raw), str(w), str(h), str(out)])
+        assert np.array_equal(decode_hdr_rgbe(str(out)), plain)
+
+
+@pytest.mark.gpu
+def test_save_hdr_matches_oracle_and_reference_writer(tmp_path):
+    from util import decode_hdr_rgbe
+
+    pod = api.Scene(scenes.write_scene("cornellGlass", str(tmp_path / "s.txt"), width=96, height=64)).pod
+    n = 12
+    with api.Renderer(pod, abi.default_options()) as r:
+        r.render(1, n, 1)
+        img, alb = r.read()
+        hdr_img, hdr_alb = str(tmp_path / "img.hdr"), str(tmp_path / "alb.hdr")
+        r.save_hdr(hdr_img, abi.AOV_IMAGE, n)
+        r.save_hdr(hdr_alb, abi.AOV_ALBEDO, n)
+        with pytest.raises(api.B2ptError):
+            r.save_hdr(str(tmp_path / "no_such_dir" / "x.hdr"), abi.AOV_IMAGE, 1)
+        with pytest.raises(api.B2ptError):
+            r.save_hdr(hdr_img, abi.AOV_IMAGE, 0)
+    want_img = oracle.save_image_rgbe(img, 96, 64, n, divide=True)
+    want_alb = oracle.save_image_rgbe(alb, 96, 64, n, divide=False)
+    assert np.array_equal(decode_hdr_rgbe(hdr_img), want_img)
+    assert np.array_equal(decode_hdr_rgbe(hdr_alb), want_alb)
+    assert want_img[..., 3].max() >= 128, "the render is not blank"
+    if os.path.exists(REF_HDR):  # the reference's own writer on the same accumulation buffer
+        raw = str(tmp_path / "in.raw")
+        img.astype(np.float32).tofile(raw)
+        subprocess.check_call([REF_HDR, raw, "96", "64", str(n), "1", str(tmp_path / "ref")], stdout=subprocess.DEVNULL)
+        assert np.array_equal(decode_hdr_rgbe(str(tmp_path / "ref.hdr")), want_img)

@@ -98,3 +98,40 @@ def decode_png_rgb8(path):
         out[y] = cur
         prev = cur
     return out.astype(np.uint8).reshape(h, w, 3)
+
+
+def decode_hdr_rgbe(path):
+    """Minimal Radiance .hdr reader -> (H, W, 4) uint8 RGBE (-Y h +X w; new-style RLE or flat scanlines)."""
+    data = open(path, "rb").read()
+    assert data.startswith(b"#?RADIANCE") or data.startswith(b"#?RGBE"), "not a Radiance file"
+    end = data.index(b"\n\n")
+    assert b"FORMAT=32-bit_rle_rgbe" in data[:end], "expected 32-bit_rle_rgbe"
+    nl = data.index(b"\n", end + 2)
+    dims = data[end + 2:nl].split()
+    assert dims[0] == b"-Y" and dims[2] == b"+X", dims
+    h, w = int(dims[1]), int(dims[3])
+    pos = nl + 1
+    out = np.zeros((h, w, 4), np.uint8)
+    for y in range(h):
+        rle = 8 <= w < 32768 and data[pos] == 2 and data[pos + 1] == 2 and ((data[pos + 2] << 8) | data[pos + 3]) == w
+        if not rle:
+            out[y] = np.frombuffer(data, np.uint8, w * 4, pos).reshape(w, 4)
+            pos += w * 4
+            continue
+        pos += 4
+        for c in range(4):
+            x = 0
+            while x < w:
+                n = data[pos]
+                pos += 1
+                if n > 128:
+                    n -= 128
+                    out[y, x:x + n, c] = data[pos]
+                    pos += 1
+                else:
+                    out[y, x:x + n, c] = np.frombuffer(data, np.uint8, n, pos)
+                    pos += n
+                x += n
+            assert x == w, "RLE run crosses the scanline"
+    assert pos == len(data), f"{len(data) - pos} trailing bytes"
+    return out
