@@ -20,6 +20,7 @@
 #include <cstring>
 #include <fstream>
 #include <sstream>
+#include <limits>
 #include <string>
 #include <vector>
 
@@ -190,9 +191,21 @@ bool parse_index(const std::string& tok, int nv, int nvt, int nvn, ObjIndex* out
   return out->v >= 0 && out->v < nv;
 }
 
+// Crossing-number test of (tx, ty) against the triangle (px, py) (the pnpoly test tinyobjloader uses,
+// apps/src/tiny_obj_loader.h:1414-1426), in single precision and in the same order of operations.
+static bool crossing_inside3(const float* px, const float* py, float tx, float ty) {
+  bool in = false;
+  for (int i = 0, j = 2; i < 3; j = i++) {
+    if (((py[i] > ty) != (py[j] > ty)) && (tx < (px[j] - px[i]) * (ty - py[i]) / (py[j] - py[i]) + px[i])) in = !in;
+  }
+  return in;
+}
+
 // loadObj, apps/src/scene.cpp:38-234.  Faces are emitted in file order; quads
 // are split along the shorter diagonal as tinyobjloader 2.0.0 does
-// (apps/src/tiny_obj_loader.h:1509-1553); larger polygons are fanned.
+// (apps/src/tiny_obj_loader.h:1509-1553); polygons with more corners go through
+// its ear clipping, restated below (tiny_obj_loader.h:1569-1845), so that concave
+// polygons come out as the same triangles in the same order (tests/golden/hardobj.obj).
 int load_obj(B2ptLoadedScene* S, const std::string& obj_path, const std::vector<std::string>& search, B2ptGeom* g) {
   std::string path = find_file(slashes(obj_path), search);
   if (path.empty()) return fail(B2PT_ERR_IO, "cannot open OBJ file " + obj_path);
@@ -265,7 +278,70 @@ int load_obj(B2ptLoadedScene* S, const std::string& obj_path, const std::vector<
           emit(idx[1], idx[2], idx[3]);
         }
       } else {
-        for (size_t k = 1; k + 1 < idx.size(); ++k) emit(idx[0], idx[k], idx[k + 1]);
+        // Projection plane: the first corner that is not degenerate decides which coordinate is dropped
+        // (the one along which its normal is strictly largest; x is kept on ties).
+        int ax0 = 1, ax1 = 2;
+        const size_t n0 = idx.size();
+        for (size_t k = 0; k < n0; ++k) {
+          const float* p0 = &v[3 * (size_t)idx[k].v];
+          const float* p1 = &v[3 * (size_t)idx[(k + 1) % n0].v];
+          const float* p2 = &v[3 * (size_t)idx[(k + 2) % n0].v];
+          const float e0x = p1[0] - p0[0], e0y = p1[1] - p0[1], e0z = p1[2] - p0[2];
+          const float e1x = p2[0] - p1[0], e1y = p2[1] - p1[1], e1z = p2[2] - p1[2];
+          const float nx = std::fabs(e0y * e1z - e0z * e1y);
+          const float ny = std::fabs(e0z * e1x - e0x * e1z);
+          const float nz = std::fabs(e0x * e1y - e0y * e1x);
+          const float eps = std::numeric_limits<float>::epsilon();
+          if (nx > eps || ny > eps || nz > eps) {
+            if (!(nx > ny && nx > nz)) {
+              ax0 = 0;
+              if (nz > nx && nz > ny) ax1 = 1;
+            }
+            break;
+          }
+        }
+        // Ear clipping: walk a candidate corner around the remaining polygon; a corner is cut off when it turns
+        // the way the sign test says and no other remaining vertex lies inside its triangle.  The walk gives up
+        // after a full round without progress (what is left is then dropped, as the reference's loader does).
+        std::vector<ObjIndex> rest = idx;
+        size_t corner = 0, budget = rest.size(), seen = rest.size();
+        while (rest.size() > 3 && budget > 0) {
+          const size_t n = rest.size();
+          if (corner >= n) corner -= n;
+          if (seen != n) {
+            seen = n;
+            budget = n;
+          } else {
+            --budget;
+          }
+          ObjIndex t[3];
+          float px[3], py[3];
+          for (int k = 0; k < 3; ++k) {
+            t[k] = rest[(corner + k) % n];
+            px[k] = v[3 * (size_t)t[k].v + ax0];
+            py[k] = v[3 * (size_t)t[k].v + ax1];
+          }
+          const float e0x = px[1] - px[0], e0y = py[1] - py[0];
+          const float e1x = px[2] - px[1], e1y = py[2] - py[1];
+          const float turn = e0x * e1y - e0y * e1x;
+          const float sign_ref = (px[0] * py[1] - py[0] * px[1]) * 0.5f;
+          if (turn * sign_ref < 0.0f) {
+            ++corner;
+            continue;
+          }
+          bool blocked = false;
+          for (size_t o = 3; o < n && !blocked; ++o) {
+            const ObjIndex& q = rest[(corner + o) % n];
+            blocked = crossing_inside3(px, py, v[3 * (size_t)q.v + ax0], v[3 * (size_t)q.v + ax1]);
+          }
+          if (blocked) {
+            ++corner;
+            continue;
+          }
+          emit(t[0], t[1], t[2]);
+          rest.erase(rest.begin() + (long)((corner + 1) % n));
+        }
+        if (rest.size() == 3) emit(rest[0], rest[1], rest[2]);
       }
     } else if (strncmp(p, "mtllib", 6) == 0) {
       mtllib = trim(std::string(p + 6));

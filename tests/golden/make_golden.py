@@ -30,20 +30,22 @@ CASES = {
     "cornellGlass_noaa_24x32": ("cornellGlass", 24, 32, ["--no-aa"]),
     "sphere_16x16": ("sphere", 16, 16, []),
     "quadbox_32x32": ("quadbox", 32, 32, []),
+    # OBJ syntax corner cases and concave polygons (tinyobjloader's ear clipping), see hardobj.obj
+    "hardobj_16x16": ("hardobj", 16, 16, []),
 }
 
 
 def main():
     assert harness.have("ref_cpu"), "build oracle/_ref first: make -C oracle ref"
-    for f in ("quadbox.obj",):
-        shutil.copyfile(os.path.join(HERE, f), os.path.join(harness.RUN_MODELS, f))
-    shutil.copyfile(os.path.join(HERE, "quadbox.mtl"), os.path.join(harness.RUN_MODELS, "materials", "quadbox.mtl"))
+    for f in ("quadbox", "hardobj"):
+        shutil.copyfile(os.path.join(HERE, f + ".obj"), os.path.join(harness.RUN_MODELS, f + ".obj"))
+        shutil.copyfile(os.path.join(HERE, f + ".mtl"), os.path.join(harness.RUN_MODELS, "materials", f + ".mtl"))
     for case, (scene, w, h, extra) in CASES.items():
         d = harness.tmpdir()
         txt = os.path.join(d, "s.txt")
-        if scene == "quadbox":
+        if scene in ("quadbox", "hardobj"):
             with open(txt, "w") as f:
-                f.write(scenes.scene_text("cornellObj", width=w, height=h, obj_path="../models/quadbox.obj"))
+                f.write(scenes.scene_text("cornellObj", width=w, height=h, obj_path=f"../models/{scene}.obj"))
         else:
             harness.scene_variant(scene, txt, w, h)
         b2s = os.path.join(HERE, case + ".b2s")

@@ -52,6 +52,24 @@ def test_obj_with_quads_and_no_texture_maps(tmp_path):
     assert mine.geoms["material_id"][6] == 6  # appended material (scene.cpp:221-231)
 
 
+def test_obj_syntax_corner_cases_and_concave_polygons(tmp_path):
+    """tests/golden/hardobj.obj: CRLF lines, tabs, exponents and signs, three-component vt, negative
+    (relative) indices, several o / g / usemtl / s statements, two MTL materials (the reference uses the
+    first of the file for every face) and polygons with 5 - 8 corners, concave, non-planar and with
+    collinear corners, which tinyobjloader 2.0.0 ear-clips: same triangles, same order, same bits as the
+    reference's loader."""
+    ref = PodScene.load(os.path.join(GOLDEN, "hardobj_16x16.b2s"))
+    (tmp_path / "models" / "materials").mkdir(parents=True)
+    shutil.copy(os.path.join(GOLDEN, "hardobj.obj"), tmp_path / "models")
+    shutil.copy(os.path.join(GOLDEN, "hardobj.mtl"), tmp_path / "models" / "materials")
+    path = scenes.write_scene("cornellObj", str(tmp_path / "scenes" / "s.txt"), width=16, height=16,
+                              obj_path="../models/hardobj.obj")
+    mine = api.Scene(path).pod
+    assert_same_scene(ref, mine)
+    assert len(mine.face_pos) == 34
+    assert abs(float(mine.materials["index_of_refraction"][-1]) - 1.33) < 1e-6  # `newmtl first`, not `second`
+
+
 def test_crlf_and_comments_are_tolerated(tmp_path):
     txt = scenes.scene_text("cornell", width=8, height=8)
     p = tmp_path / "crlf.txt"
