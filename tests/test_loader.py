@@ -70,6 +70,20 @@ def test_obj_syntax_corner_cases_and_concave_polygons(tmp_path):
     assert abs(float(mine.materials["index_of_refraction"][-1]) - 1.33) < 1e-6  # `newmtl first`, not `second`
 
 
+@pytest.mark.parametrize("name", ["camera", "tabs_numbers", "permuted_transform", "no_trailing_newline", "triangle_geom",
+                                  "rot_scale", "both_refl_refr", "iter_depth"])
+def test_scene_format_variants_match_the_reference_loader(name):
+    """tests/golden/variants: one property of the scene text format each (see make_scene_variants.py), the
+    .b2s written by the reference's own scene.cpp + the camera recompute of main.cpp."""
+    ref = PodScene.load(os.path.join(GOLDEN, "variants", name + ".b2s"))
+    mine = api.Scene(os.path.join(GOLDEN, "variants", name + ".txt")).pod
+    assert_same_scene(ref, mine)
+    if name == "triangle_geom":
+        assert int(mine.geoms["type"][-1]) == 2 and len(mine.geoms) == 8
+    if name == "iter_depth":
+        assert (mine.trace_depth, mine.iterations) == (3, 17)
+
+
 def test_crlf_and_comments_are_tolerated(tmp_path):
     txt = scenes.scene_text("cornell", width=8, height=8)
     p = tmp_path / "crlf.txt"
