@@ -32,6 +32,10 @@ CASES = {
     "quadbox_32x32": ("quadbox", 32, 32, []),
     # OBJ syntax corner cases and concave polygons (tinyobjloader's ear clipping), see hardobj.obj
     "hardobj_16x16": ("hardobj", 16, 16, []),
+    # scene-format variants (make_scene_variants.py) whose geometry / materials differ from the shipped scenes:
+    # rotated geoms with a non-uniform scale (an ellipsoid), a material that is reflective AND refractive
+    "rot_scale_48x20": ("variant:rot_scale", 48, 20, []),
+    "both_refl_refr_48x20": ("variant:both_refl_refr", 48, 20, []),
 }
 
 
@@ -43,7 +47,9 @@ def main():
     for case, (scene, w, h, extra) in CASES.items():
         d = harness.tmpdir()
         txt = os.path.join(d, "s.txt")
-        if scene in ("quadbox", "hardobj"):
+        if scene.startswith("variant:"):
+            shutil.copyfile(os.path.join(HERE, "variants", scene.split(":")[1] + ".txt"), txt)
+        elif scene in ("quadbox", "hardobj"):
             with open(txt, "w") as f:
                 f.write(scenes.scene_text("cornellObj", width=w, height=h, obj_path=f"../models/{scene}.obj"))
         else:

@@ -55,7 +55,7 @@ def compare_iteration(pod: PodScene, optkw: dict, iters=(1, 2), what=""):
 @pytest.mark.parametrize("case,optkw", [
     ("cornell_32x32", {}), ("cornellGlass_32x32", {}), ("cornellGlass_dof_32x24", {"depth_of_field": 1}),
     ("cornellGlass_noaa_24x32", {"antialiasing": 0}), ("sphere_16x16", {}), ("quadbox_32x32", {}),
-    ("hardobj_16x16", {}),
+    ("hardobj_16x16", {}), ("rot_scale_48x20", {}), ("both_refl_refr_48x20", {}),
     ("cornell_32x32", {"sort_by_material": 0}),
 ])
 def test_golden_scenes_every_stage_bitexact(case, optkw):
