@@ -125,7 +125,7 @@ std::string find_file(const std::string& name, const std::vector<std::string>& d
 }
 
 struct MtlInfo {
-  float kd[3] = {0.6f, 0.6f, 0.6f}, ks[3] = {0, 0, 0}, ke[3] = {0, 0, 0};
+  float kd[3] = {0, 0, 0}, ks[3] = {0, 0, 0}, ke[3] = {0, 0, 0};  // tinyobjloader 2.0.0 starts every material at zero
   float ior = 1.0f;
   std::string map_kd, map_ks, map_ke, map_bump;
   bool found = false;

@@ -84,6 +84,22 @@ def test_scene_format_variants_match_the_reference_loader(name):
         assert (mine.trace_depth, mine.iterations) == (3, 17)
 
 
+@pytest.mark.parametrize("name", ["minimal", "no_ni", "ke", "tabs_crlf", "comments_unknown", "second_first"])
+def test_mtl_variants_match_the_reference_loader(tmp_path, name):
+    """tests/golden/mtl_variants (see make_mtl_variants.py): the material the reference appends for an OBJ
+    geom, byte for byte -- tinyobjloader's zero defaults, Ke[0] as emittance, only the first `newmtl` counts."""
+    want = np.load(os.path.join(GOLDEN, "mtl_variants", name + "_material.npy")).tobytes()
+    (tmp_path / "models" / "materials").mkdir(parents=True)
+    obj = open(os.path.join(GOLDEN, "quadbox.obj")).read()
+    obj = obj.replace("mtllib quadbox.mtl", f"mtllib mv_{name}.mtl").replace("usemtl plain", "usemtl a")
+    (tmp_path / "models" / f"mv_{name}.obj").write_text(obj)
+    shutil.copy(os.path.join(GOLDEN, "mtl_variants", name + ".mtl"), tmp_path / "models" / "materials" / f"mv_{name}.mtl")
+    path = scenes.write_scene("cornellObj", str(tmp_path / "scenes" / "s.txt"), width=16, height=16,
+                              obj_path=f"../models/mv_{name}.obj")
+    mine = api.Scene(path).pod
+    assert mine.materials[-1:].tobytes() == want, mine.materials[-1]
+
+
 def test_crlf_and_comments_are_tolerated(tmp_path):
     txt = scenes.scene_text("cornell", width=8, height=8)
     p = tmp_path / "crlf.txt"
