@@ -10,10 +10,12 @@
 //     (apps/src/stb_image.h:2392-2489);
 //   * the 20-bit fixed-point YCbCr->RGB conversion with the 0xffff0000 mask on
 //     the Cb term of green (apps/src/stb_image.h:3598-3623).
-// For non-subsampled files -- all seven shipped 4096x4096 textures are 4:4:4 --
-// the output is byte-identical to stbi_load (tests/test_loader.py checks this
-// against texels dumped by the reference loader).  Chroma-subsampled files are
-// upsampled by replication (stb interpolates), progressive files are rejected.
+//   * the "JFIF-centred" chroma upsampling (tent filters for 2x1, 1x2 and 2x2, replication otherwise,
+//     apps/src/stb_image.h:3388-3468, 3836-3880).
+// The output is byte-identical to stbi_load for baseline files -- the seven shipped 4096x4096
+// textures (4:4:4) and the 4:2:0 / 4:2:2 / grey / restart-interval files of
+// tests/golden/jpeg (tests/test_loader.py checks both against texels dumped by the reference
+// loader).  Progressive files are rejected.
 #pragma once
 
 #include <cstdint>
@@ -375,19 +377,90 @@ inline bool decode(const uint8_t* data, size_t size, int* w, int* h, int* channe
   *h = D.height;
   *channels = D.ncomp;
   out->assign((size_t)D.width * D.height * D.ncomp, 0);
-  auto sample = [&](const Component& c, int x, int y) -> int {
-    const int sx = x * c.h / D.hmax, sy = y * c.v / D.vmax;
-    return c.plane[(size_t)sy * c.w_blocks * 8 + sx];
+  // Chroma upsampling as stb_image does it (apps/src/stb_image.h:3388-3468, 3836-3880): "JFIF-centred" tent
+  // filters for the factors 2x1, 1x2 and 2x2, plain replication for everything else, and per component a
+  // little state machine that picks the nearer and the farther source row of every output row.
+  struct Upsampler {
+    int hs = 1, vs = 1, w_lores = 0, rows = 0, ystep = 0, row0 = 0, row1 = 0, ypos = 0;
+    std::vector<uint8_t> line;
   };
+  Upsampler up[3];
+  for (int k = 0; k < D.ncomp; ++k) {
+    const Component& c = D.comp[k];
+    Upsampler& u = up[k];
+    u.hs = D.hmax / c.h;
+    u.vs = D.vmax / c.v;
+    u.ystep = u.vs >> 1;
+    u.w_lores = (D.width + u.hs - 1) / u.hs;
+    u.rows = (D.height * c.v + D.vmax - 1) / D.vmax;
+    u.line.assign((size_t)u.w_lores * u.hs + 8, 0);
+  }
   for (int y = 0; y < D.height; ++y) {
+    const uint8_t* row[3] = {nullptr, nullptr, nullptr};
+    for (int k = 0; k < D.ncomp; ++k) {
+      const Component& c = D.comp[k];
+      Upsampler& u = up[k];
+      const size_t stride = (size_t)c.w_blocks * 8;
+      const bool lower = u.ystep >= (u.vs >> 1);
+      const uint8_t* near = c.plane.data() + stride * (size_t)(lower ? u.row1 : u.row0);
+      const uint8_t* far = c.plane.data() + stride * (size_t)(lower ? u.row0 : u.row1);
+      uint8_t* o = u.line.data();
+      const int w = u.w_lores;
+      if (u.hs == 1 && u.vs == 1) {
+        row[k] = near;
+      } else if (u.hs == 1 && u.vs == 2) {
+        for (int i = 0; i < w; ++i) o[i] = (uint8_t)((3 * near[i] + far[i] + 2) >> 2);
+        row[k] = o;
+      } else if (u.hs == 2 && u.vs == 1) {
+        if (w == 1) {
+          o[0] = o[1] = near[0];
+        } else {
+          o[0] = near[0];
+          o[1] = (uint8_t)((near[0] * 3 + near[1] + 2) >> 2);
+          int i = 1;
+          for (; i < w - 1; ++i) {
+            const int n = 3 * near[i] + 2;
+            o[2 * i] = (uint8_t)((n + near[i - 1]) >> 2);
+            o[2 * i + 1] = (uint8_t)((n + near[i + 1]) >> 2);
+          }
+          o[2 * i] = (uint8_t)((near[w - 2] * 3 + near[w - 1] + 2) >> 2);
+          o[2 * i + 1] = near[w - 1];
+        }
+        row[k] = o;
+      } else if (u.hs == 2 && u.vs == 2) {
+        if (w == 1) {
+          o[0] = o[1] = (uint8_t)((3 * near[0] + far[0] + 2) >> 2);
+        } else {
+          int t1 = 3 * near[0] + far[0];
+          o[0] = (uint8_t)((t1 + 2) >> 2);
+          for (int i = 1; i < w; ++i) {
+            const int t0 = t1;
+            t1 = 3 * near[i] + far[i];
+            o[2 * i - 1] = (uint8_t)((3 * t0 + t1 + 8) >> 4);
+            o[2 * i] = (uint8_t)((3 * t1 + t0 + 8) >> 4);
+          }
+          o[2 * w - 1] = (uint8_t)((t1 + 2) >> 2);
+        }
+        row[k] = o;
+      } else {
+        for (int i = 0; i < w; ++i)
+          for (int j = 0; j < u.hs; ++j) o[i * u.hs + j] = near[i];
+        row[k] = o;
+      }
+      if (++u.ystep >= u.vs) {
+        u.ystep = 0;
+        u.row0 = u.row1;
+        if (++u.ypos < u.rows) u.row1 += 1;
+      }
+    }
     uint8_t* o = out->data() + (size_t)y * D.width * D.ncomp;
     if (D.ncomp == 1) {
-      for (int x = 0; x < D.width; ++x) o[x] = (uint8_t)sample(D.comp[0], x, y);
+      for (int x = 0; x < D.width; ++x) o[x] = row[0][x];
     } else {
       for (int x = 0; x < D.width; ++x) {
         // 20-bit fixed point: (int)(c * 4096.0f + 0.5f) << 8
-        const int yf = (sample(D.comp[0], x, y) << 20) + (1 << 19);
-        const int cb = sample(D.comp[1], x, y) - 128, cr = sample(D.comp[2], x, y) - 128;
+        const int yf = ((int)row[0][x] << 20) + (1 << 19);
+        const int cb = (int)row[1][x] - 128, cr = (int)row[2][x] - 128;
         int r = yf + cr * (5743 << 8);
         int g = yf + (cr * -(2925 << 8)) + ((cb * -(1410 << 8)) & 0xffff0000);
         int b = yf + cb * (7258 << 8);

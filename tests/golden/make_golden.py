@@ -66,5 +66,29 @@ def main():
         shutil.rmtree(d)
 
 
+def texture_crc():
+    """texture_crc.txt: CRC-32 of the four 4096x4096 spaceship textures as the reference's loader (stb_image)
+    holds them, for tests/test_loader.py::test_jpeg_decoder_matches_reference_texels."""
+    import zlib
+
+    from mygpuraytracer_b200 import assets, standin_mesh
+    from mygpuraytracer_b200.podscene import PodScene
+
+    root = assets.prepare()
+    harness.install_spaceship_obj(standin_mesh.ensure_obj(os.path.join(root, "models"), 1000))
+    d = harness.tmpdir()
+    txt = os.path.join(d, "s.txt")
+    harness.scene_variant("cornellObj", txt, 16, 16)
+    b2s = os.path.join(d, "s.b2s")
+    harness.run("ref_cpu", txt, os.path.join(d, "out"), b2s, iters=1, dump_iter=1)
+    ref = PodScene.load(b2s)
+    with open(os.path.join(HERE, "texture_crc.txt"), "w") as f:
+        for name, tex in zip(["kd", "ks", "bump", "ke"], ref.textures):
+            f.write(f"{name} {zlib.crc32(tex.tobytes()):08x}\n")
+    shutil.rmtree(d)
+    print(open(os.path.join(HERE, "texture_crc.txt")).read())
+
+
 if __name__ == "__main__":
     main()
+    texture_crc()

@@ -147,6 +147,26 @@ def test_standin_mesh_properties(tmp_path):
     assert sc.materials["index_of_refraction"][-1] == 2.0  # Ni of the spaceship MTL
 
 
+@pytest.mark.parametrize("name", ["s420_64x48", "s420_37x29", "s422_50x20", "s444_33x17", "s420_2x2", "s420_1x5",
+                                  "s420_restart_40x40", "grey_21x13"])
+def test_jpeg_sampling_layouts_match_stb_image(tmp_path, name):
+    """tests/golden/jpeg (see make_jpeg_golden.py): chroma-subsampled, odd-sized, restart-interval and grey
+    baseline files come out byte-identical to what the reference's loader (stb_image) holds."""
+    want = np.load(os.path.join(GOLDEN, "jpeg", name + ".npy"))
+    for d in ("models/materials", "textures"):
+        (tmp_path / d).mkdir(parents=True)
+    shutil.copy(os.path.join(GOLDEN, "jpeg", name + ".jpg"), tmp_path / "textures" / f"jg_{name}.jpg")
+    obj = open(os.path.join(GOLDEN, "quadbox.obj")).read()
+    (tmp_path / "models" / f"jg_{name}.obj").write_text(obj.replace("mtllib quadbox.mtl", f"mtllib jg_{name}.mtl"))
+    (tmp_path / "models" / "materials" / f"jg_{name}.mtl").write_text(
+        f"newmtl plain\nKd 0.5 0.5 0.5\nmap_Kd ../textures/jg_{name}.jpg\n")
+    path = scenes.write_scene("cornellObj", str(tmp_path / "scenes" / "s.txt"), width=16, height=16,
+                              obj_path=f"../models/jg_{name}.obj")
+    mine = api.Scene(path).pod
+    assert len(mine.textures) == 1
+    assert mine.textures[0].shape == want.shape and np.array_equal(mine.textures[0], want)
+
+
 def test_jpeg_decoder_matches_reference_texels():
     """4:4:4 baseline JPEG -> the same bytes stb_image produces.  The golden
     is a CRC of texels dumped by the reference loader (see make_golden.py);
