@@ -131,6 +131,37 @@ struct MtlInfo {
   bool found = false;
 };
 
+// The file name of a map_* / bump statement.  tinyobjloader 2.0.0 accepts the MTL texture options in front
+// of it and lets each swallow a fixed number of blank-separated arguments, numeric or not
+// (apps/src/tiny_obj_loader.h:1235-1325); whatever follows the last option, blanks included, is the name.
+static std::string texture_name_of(const std::string& args) {
+  static const struct {
+    const char* name;
+    int nargs;
+  } opts[] = {{"-blendu", 1}, {"-blendv", 1}, {"-clamp", 1}, {"-boost", 1}, {"-bm", 1},      {"-o", 3},         {"-s", 3},
+              {"-t", 3},      {"-type", 1},   {"-texres", 1}, {"-imfchan", 1}, {"-mm", 2},    {"-colorspace", 1}};
+  auto blank = [](char c) { return c == ' ' || c == '\t'; };
+  size_t i = 0;
+  for (;;) {
+    while (i < args.size() && blank(args[i])) ++i;
+    if (i >= args.size()) return std::string();
+    int nargs = -1;
+    for (const auto& o : opts) {
+      const size_t n = strlen(o.name);
+      if (args.compare(i, n, o.name) == 0 && i + n < args.size() && blank(args[i + n])) {
+        nargs = o.nargs;
+        i += n;
+        break;
+      }
+    }
+    if (nargs < 0) return args.substr(i);
+    for (int k = 0; k < nargs; ++k) {
+      while (i < args.size() && blank(args[i])) ++i;
+      while (i < args.size() && !blank(args[i])) ++i;
+    }
+  }
+}
+
 // First material of an MTL file (the reference uses objMaterials[0] only, scene.cpp:68,134).
 MtlInfo parse_first_mtl(const std::string& path) {
   MtlInfo m;
@@ -148,7 +179,7 @@ MtlInfo parse_first_mtl(const std::string& path) {
       continue;
     }
     if (count != 1) continue;
-    auto rest = [&]() { return slashes(trim(t.substr(k.size()))); };
+    auto rest = [&]() { return slashes(trim(texture_name_of(t.substr(k.size())))); };
     auto f3 = [&](float* o) {
       for (int i = 0; i < 3 && i + 1 < (int)tk.size(); ++i) o[i] = (float)atof(tk[i + 1].c_str());
     };

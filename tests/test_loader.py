@@ -167,6 +167,31 @@ def test_jpeg_sampling_layouts_match_stb_image(tmp_path, name):
     assert mine.textures[0].shape == want.shape and np.array_equal(mine.textures[0], want)
 
 
+@pytest.mark.parametrize("name", ["options_s", "bump_bm", "bump_kw", "map_bump_lower", "all_four", "clamp_blend",
+                                  "swallowed_name", "mm_type", "missing_file", "name_with_blanks"])
+def test_mtl_texture_statements_match_the_reference_loader(tmp_path, name):
+    """tests/golden/mtl_textures (see make_mtl_texture_golden.py): which texture slots of the geom are filled
+    and with which texels, for MTL texture options, the bump spellings, names with blanks and missing files."""
+    import zlib
+
+    exp = np.load(os.path.join(GOLDEN, "mtl_textures", "expected.npz"))
+    for d in ("models/materials", "textures"):
+        (tmp_path / d).mkdir(parents=True)
+    for dst, src in {"opt tex a.png": "rgb_93x71.png", "opt_b.png": "rgba_85x77.png", "opt_c.png": "palette_90x80.png",
+                     "opt_d.png": "stored_70x60.png"}.items():
+        shutil.copy(os.path.join(GOLDEN, "png", src), tmp_path / "textures" / dst)
+    obj = open(os.path.join(GOLDEN, "quadbox.obj")).read()
+    (tmp_path / "models" / f"mo_{name}.obj").write_text(obj.replace("mtllib quadbox.mtl", f"mtllib mo_{name}.mtl"))
+    shutil.copy(os.path.join(GOLDEN, "mtl_textures", name + ".mtl"), tmp_path / "models" / "materials" / f"mo_{name}.mtl")
+    path = scenes.write_scene("cornellObj", str(tmp_path / "scenes" / "s.txt"), width=16, height=16,
+                              obj_path=f"../models/mo_{name}.obj")
+    mine = api.Scene(path).pod
+    slots = [int(mine.geoms[k][6]) for k in ("tex_kd", "tex_ks", "tex_bump", "tex_ke")]
+    crcs = [zlib.crc32(np.ascontiguousarray(t).tobytes()) for t in mine.textures]
+    assert slots == exp[name + "_slots"].tolist()
+    assert crcs == exp[name + "_crcs"].tolist()
+
+
 def _png_names():
     z = os.path.join(GOLDEN, "png", "texels.npz")
     return sorted(np.load(z).files) if os.path.exists(z) else []
