@@ -386,10 +386,16 @@ int load_obj(B2ptLoadedScene* S, const std::string& obj_path, const std::vector<
   if (!mtllib.empty()) {
     std::vector<std::string> mdirs = {dir_of(path) + "/materials", dir_of(path), "../models/materials"};
     for (const std::string& d : search) mdirs.push_back(d);
-    std::string mp = find_file(slashes(mtllib), mdirs);
-    if (!mp.empty()) {
+    // `mtllib a.mtl b.mtl`: tinyobjloader splits the statement at blanks and takes the first file that loads
+    // (apps/src/tiny_obj_loader.h, "mtllib"); a name that exists as written (blanks and all) is tried first
+    std::vector<std::string> names = {mtllib};
+    for (const std::string& n : tokens_of(mtllib)) names.push_back(n);
+    for (const std::string& n : names) {
+      const std::string mp = find_file(slashes(n), mdirs);
+      if (mp.empty()) continue;
       mtl = parse_first_mtl(mp);
       tex_dirs.push_back(dir_of(mp));
+      break;
     }
   }
   tex_dirs.push_back(dir_of(path));

@@ -192,6 +192,22 @@ def test_mtl_texture_statements_match_the_reference_loader(tmp_path, name):
     assert crcs == exp[name + "_crcs"].tolist()
 
 
+@pytest.mark.parametrize("name", ["vertex_colors", "v_w", "vt_one", "lines_points", "trailing_ws", "no_newline_end",
+                                  "vp_and_unknown", "usemtl_unknown", "two_mtllibs", "face_v_vt", "two_corner_face"])
+def test_obj_statement_variants_match_the_reference_loader(tmp_path, name):
+    """tests/golden/obj_variants (see make_obj_variants.py): faces and the appended material, bit for bit."""
+    want = np.load(os.path.join(GOLDEN, "obj_variants", name + ".npz"))
+    (tmp_path / "models" / "materials").mkdir(parents=True)
+    shutil.copy(os.path.join(GOLDEN, "obj_variants", name + ".obj"), tmp_path / "models" / f"ov_{name}.obj")
+    shutil.copy(os.path.join(GOLDEN, "quadbox.mtl"), tmp_path / "models" / "materials")
+    path = scenes.write_scene("cornellObj", str(tmp_path / "scenes" / "s.txt"), width=16, height=16,
+                              obj_path=f"../models/ov_{name}.obj")
+    mine = api.Scene(path).pod
+    assert_same_bits(want["face_pos"], mine.face_pos, "face_pos")
+    assert_same_bits(want["face_uv"], mine.face_uv, "face_uv")
+    assert mine.materials[-1:].tobytes() == want["material"].tobytes()
+
+
 def _png_names():
     z = os.path.join(GOLDEN, "png", "texels.npz")
     return sorted(np.load(z).files) if os.path.exists(z) else []
