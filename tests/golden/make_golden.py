@@ -36,20 +36,26 @@ CASES = {
     # rotated geoms with a non-uniform scale (an ellipsoid), a material that is reflective AND refractive
     "rot_scale_48x20": ("variant:rot_scale", 48, 20, []),
     "both_refl_refr_48x20": ("variant:both_refl_refr", 48, 20, []),
+    # quadbox with all four texture maps (texquad.mtl, PNG fixtures in texquad/): bump mapping, emission texels, kd / ks
+    "texquad_32x32": ("texquad", 32, 32, []),
 }
 
 
 def main():
     assert harness.have("ref_cpu"), "build oracle/_ref first: make -C oracle ref"
-    for f in ("quadbox", "hardobj"):
+    for f in ("quadbox", "hardobj", "texquad"):
         shutil.copyfile(os.path.join(HERE, f + ".obj"), os.path.join(harness.RUN_MODELS, f + ".obj"))
         shutil.copyfile(os.path.join(HERE, f + ".mtl"), os.path.join(harness.RUN_MODELS, "materials", f + ".mtl"))
+    tex_dir = os.path.join(os.path.dirname(harness.RUN_MODELS), "textures")
+    os.makedirs(tex_dir, exist_ok=True)
+    for f in os.listdir(os.path.join(HERE, "texquad")):
+        shutil.copyfile(os.path.join(HERE, "texquad", f), os.path.join(tex_dir, f))
     for case, (scene, w, h, extra) in CASES.items():
         d = harness.tmpdir()
         txt = os.path.join(d, "s.txt")
         if scene.startswith("variant:"):
             shutil.copyfile(os.path.join(HERE, "variants", scene.split(":")[1] + ".txt"), txt)
-        elif scene in ("quadbox", "hardobj"):
+        elif scene in ("quadbox", "hardobj", "texquad"):
             with open(txt, "w") as f:
                 f.write(scenes.scene_text("cornellObj", width=w, height=h, obj_path=f"../models/{scene}.obj"))
         else:
