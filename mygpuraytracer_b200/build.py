@@ -8,7 +8,9 @@ context / C ABI (``csrc/b2pt.cu``) and the host-side scene loader
   other architectures, no multi-backend dispatch;
 * ``-fmad=false``: no FMA contraction, so the kernels round exactly as the
   reference's expressions are written (see ``csrc/pt_math.cuh``);
-* ``-lineinfo``: ncu source pages map to these files.
+* ``-lineinfo``: ncu source pages map to these files;
+* ``-fwrapv`` (host code): the integer IDCT of the JPEG decoder overflows on damaged files exactly as
+  stb_image's does; wrapping makes that defined behaviour.
 """
 from __future__ import annotations
 
@@ -22,7 +24,7 @@ LIB = os.path.join(HERE, "libb2pt.so")
 NVCC_FLAGS = [
     "-std=c++17", "-O3", "-fmad=false", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",
-    "-Xcompiler", "-fPIC,-O2,-ffp-contract=off,-Wall",
+    "-Xcompiler", "-fPIC,-O2,-ffp-contract=off,-fwrapv,-Wall",
     "--shared",
 ]
 

@@ -36,13 +36,16 @@ struct Huff {
   uint8_t vals[256];
   uint16_t fast[512];  // 9-bit lookahead: (len << 8) | symbol, 0 = slow path
   bool ok = false;
-  void build(const uint8_t counts[16], const uint8_t* symbols, int n) {
+  bool build(const uint8_t counts[16], const uint8_t* symbols, int n) {
+    ok = false;
+    if (n < 0 || n > 256) return false;
     memcpy(vals, symbols, (size_t)n);
     int code = 0, k = 0;
     memset(fast, 0, sizeof fast);
     for (int len = 1; len <= 16; ++len) {
       valptr[len] = k;
       mincode[len] = code;
+      if (code + counts[len - 1] > (1 << len)) return false;  // more codes of this length than the prefix code has room for
       for (int i = 0; i < counts[len - 1]; ++i, ++k, ++code) {
         if (len <= 9) {
           const int base = code << (9 - len);
@@ -54,6 +57,7 @@ struct Huff {
     }
     maxcode[17] = 0x7fffffff;
     ok = true;
+    return true;
   }
 };
 
@@ -259,6 +263,7 @@ inline bool decode(const uint8_t* data, size_t size, int* w, int* h, int* channe
     if (m == 0x00) continue;  // a stuffed 0xff00 left over from entropy-coded data
     if (m == 0x01 || (m >= 0xd0 && m <= 0xd7)) continue;
     int len = D.word();
+    if (len < 2) { *err = "bad JPEG segment length"; return false; }
     const uint8_t* seg_end = D.p + len - 2;
     if (seg_end > D.end) { *err = "truncated JPEG segment"; return false; }
     if (m == 0xdb) {  // DQT
@@ -277,7 +282,7 @@ inline bool decode(const uint8_t* data, size_t size, int* w, int* h, int* channe
         if (n > 256 || (tc & 15) > 3) { *err = "bad DHT"; return false; }
         uint8_t syms[256];
         for (int i = 0; i < n; ++i) syms[i] = (uint8_t)D.byte();
-        ((tc >> 4) ? D.ac : D.dc)[tc & 15].build(counts, syms, n);
+        if ((tc >> 4) > 1 || !((tc >> 4) ? D.ac : D.dc)[tc & 15].build(counts, syms, n)) { *err = "bad DHT"; return false; }
       }
     } else if (m == 0xc0 || m == 0xc1 || m == 0xc2) {  // SOF0/1/2
       if (m == 0xc2) { *err = "progressive JPEG is not supported"; return false; }
@@ -286,6 +291,9 @@ inline bool decode(const uint8_t* data, size_t size, int* w, int* h, int* channe
       D.width = D.word();
       D.ncomp = D.byte();
       if ((D.ncomp != 1 && D.ncomp != 3) || D.width <= 0 || D.height <= 0) { *err = "unsupported JPEG frame"; return false; }
+      if (have_frame) { *err = "more than one JPEG frame"; return false; }
+      if ((uint64_t)D.width * (uint64_t)D.height > (1ull << 28)) { *err = "JPEG image too large"; return false; }
+      D.hmax = D.vmax = 1;
       for (int i = 0; i < D.ncomp; ++i) {
         D.comp[i].id = D.byte();
         const int hv = D.byte();
@@ -296,6 +304,8 @@ inline bool decode(const uint8_t* data, size_t size, int* w, int* h, int* channe
         D.hmax = D.comp[i].h > D.hmax ? D.comp[i].h : D.hmax;
         D.vmax = D.comp[i].v > D.vmax ? D.comp[i].v : D.vmax;
       }
+      for (int i = 0; i < D.ncomp; ++i)
+        if (D.hmax % D.comp[i].h != 0 || D.vmax % D.comp[i].v != 0) { *err = "bad JPEG sampling factors"; return false; }
       const int mcux = (D.width + 8 * D.hmax - 1) / (8 * D.hmax), mcuy = (D.height + 8 * D.vmax - 1) / (8 * D.vmax);
       for (int i = 0; i < D.ncomp; ++i) {
         D.comp[i].w_blocks = mcux * D.comp[i].h;
@@ -317,6 +327,7 @@ inline bool decode(const uint8_t* data, size_t size, int* w, int* h, int* channe
         D.comp[which].td = tt >> 4;
         D.comp[which].ta = tt & 15;
         if (D.comp[which].td > 3 || D.comp[which].ta > 3) { *err = "bad SOS table"; return false; }
+        if (!D.dc[D.comp[which].td].ok || !D.ac[D.comp[which].ta].ok) { *err = "JPEG scan uses a Huffman table that was never defined"; return false; }
         scan_comps[i] = which;
       }
       D.p = seg_end;
