@@ -109,7 +109,7 @@ class Scene:
             _check(lib.b2pt_scene_load(os.fsencode(filename), C.byref(ov), C.byref(h)))
             try:
                 pod = PodScene.from_ctypes(lib.b2pt_scene_view(h).contents)
-                name = lib.b2pt_scene_image_name(h).decode()
+                name = lib.b2pt_scene_image_name(h).decode("utf-8", "replace")
             finally:
                 lib.b2pt_scene_free(h)
         else:

@@ -500,6 +500,16 @@ extern "C" int b2pt_scene_load(const char* path, const B2ptLoadOverrides* ov, B2
         if (ov->iterations > 0) iterations = ov->iterations;
         if (ov->depth > 0) trace_depth = ov->depth;
       }
+      // the reference allocates resolution.x * resolution.y pixels without looking (scene.cpp:379-381); a
+      // library refuses what b2pt_create would refuse, here, with the file name in the message
+      if (cam.resolution[0] <= 0 || cam.resolution[1] <= 0 || (long long)cam.resolution[0] * cam.resolution[1] >= (1ll << 30)) {
+        rc = fail(B2PT_ERR_INVALID, "CAMERA: RES must be positive and below 2^30 pixels");
+        break;
+      }
+      if (trace_depth < 0 || trace_depth > 62) {
+        rc = fail(B2PT_ERR_RANGE, "CAMERA: DEPTH must be in [0, 62]");
+        break;
+      }
       const float kPi = 3.1415926535897932384626422832795028841971f;
       // yscaled = tan(fovy * (PI / 180)): the FULL angle
       const float yscaled = std::tan(fovy * (kPi / 180));
