@@ -233,6 +233,30 @@ def test_png_layouts_match_stb_image(tmp_path, name):
     assert mine.textures[0].shape == want.shape and np.array_equal(mine.textures[0], want)
 
 
+def _tga_names():
+    z = os.path.join(GOLDEN, "tga", "texels.npz")
+    return sorted(np.load(z).files) if os.path.exists(z) else []
+
+
+@pytest.mark.parametrize("name", _tga_names())
+def test_tga_layouts_match_stb_image(tmp_path, name):
+    """tests/golden/tga (see make_tga_golden.py): grey / RGB / RGBA / colour-mapped / RGB555 files, raw and
+    run-length encoded, bottom-up and top-down: channel count and texels byte-identical to the reference's loader."""
+    want = np.load(os.path.join(GOLDEN, "tga", "texels.npz"))[name]
+    for d in ("models/materials", "textures"):
+        (tmp_path / d).mkdir(parents=True)
+    shutil.copy(os.path.join(GOLDEN, "tga", name + ".tga"), tmp_path / "textures" / f"tg_{name}.tga")
+    obj = open(os.path.join(GOLDEN, "quadbox.obj")).read()
+    (tmp_path / "models" / f"tg_{name}.obj").write_text(obj.replace("mtllib quadbox.mtl", f"mtllib tg_{name}.mtl"))
+    (tmp_path / "models" / "materials" / f"tg_{name}.mtl").write_text(
+        f"newmtl plain\nKd 0.5 0.5 0.5\nmap_Kd ../textures/tg_{name}.tga\n")
+    path = scenes.write_scene("cornellObj", str(tmp_path / "scenes" / "s.txt"), width=16, height=16,
+                              obj_path=f"../models/tg_{name}.obj")
+    mine = api.Scene(path).pod
+    assert len(mine.textures) == 1
+    assert mine.textures[0].shape == want.shape and np.array_equal(mine.textures[0], want)
+
+
 def test_png_decoder_rejects_damaged_files(tmp_path):
     """Truncated and corrupted PNG data never crashes the loader and never yields a partial texture."""
     data = open(os.path.join(GOLDEN, "png", "rgb_93x71.png"), "rb").read()
