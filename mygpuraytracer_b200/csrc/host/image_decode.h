@@ -24,6 +24,7 @@
 #include <string>
 #include <vector>
 
+#include "bmp_decode.h"
 #include "png_decode.h"
 #include "tga_decode.h"
 
@@ -540,6 +541,7 @@ inline bool decode_image_file(const std::string& path, bool flip_vertically, int
   bool ok = false;
   if (buf.size() > 2 && buf[0] == 0xff && buf[1] == 0xd8) ok = jpg::decode(buf.data(), buf.size(), w, h, c, texels, &err);
   else if (buf.size() > 8 && buf[0] == 0x89 && buf[1] == 'P' && buf[2] == 'N' && buf[3] == 'G') ok = png::decode(buf.data(), buf.size(), w, h, c, texels, &err);
+  else if (buf.size() > 2 && buf[0] == 'B' && buf[1] == 'M') ok = bmp::decode(buf.data(), buf.size(), w, h, c, texels, &err);
   else ok = decode_pnm(buf, w, h, c, texels);
   if (!ok && tga::looks_like_tga(buf.data(), buf.size())) ok = tga::decode(buf.data(), buf.size(), w, h, c, texels, &err);  // no signature: last
   if (!ok) return false;

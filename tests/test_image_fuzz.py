@@ -1,5 +1,5 @@
 """The texture decoders of the scene loader under mutation fuzzing (tools/fuzz_image_decoders.cpp), built with
-AddressSanitizer + UndefinedBehaviorSanitizer: damaged JPEG / PNG / TGA files are rejected or decoded, never a crash,
+AddressSanitizer + UndefinedBehaviorSanitizer: damaged JPEG / PNG / TGA / BMP files are rejected or decoded, never a crash,
 an out-of-bounds access or a hang.  (A longer run of the same harness, 4000 mutations of each of the 27 fixtures,
 was clean when the decoders were hardened.)"""
 import glob
@@ -11,7 +11,8 @@ import pytest
 from util import GOLDEN, ROOT
 
 FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "jpeg", "*.jpg")) + glob.glob(os.path.join(GOLDEN, "png", "*.png")) +
-                  glob.glob(os.path.join(GOLDEN, "texquad", "*.png")) + glob.glob(os.path.join(GOLDEN, "tga", "*.tga")))
+                  glob.glob(os.path.join(GOLDEN, "texquad", "*.png")) + glob.glob(os.path.join(GOLDEN, "tga", "*.tga")) +
+                  glob.glob(os.path.join(GOLDEN, "bmp", "*.bmp")))
 
 
 @pytest.fixture(scope="module")

@@ -257,6 +257,31 @@ def test_tga_layouts_match_stb_image(tmp_path, name):
     assert mine.textures[0].shape == want.shape and np.array_equal(mine.textures[0], want)
 
 
+def _bmp_names():
+    z = os.path.join(GOLDEN, "bmp", "texels.npz")
+    return sorted(np.load(z).files) if os.path.exists(z) else []
+
+
+@pytest.mark.parametrize("name", _bmp_names())
+def test_bmp_layouts_match_stb_image(tmp_path, name):
+    """tests/golden/bmp (see make_bmp_golden.py): 1 / 4 / 8-bit palettes, RGB555, RGB565 bit fields, 24- and 32-bit,
+    top-down rows, the OS/2 header, an all-zero alpha channel: channel count and texels byte-identical to the
+    reference's loader."""
+    want = np.load(os.path.join(GOLDEN, "bmp", "texels.npz"))[name]
+    for d in ("models/materials", "textures"):
+        (tmp_path / d).mkdir(parents=True)
+    shutil.copy(os.path.join(GOLDEN, "bmp", name + ".bmp"), tmp_path / "textures" / f"bm_{name}.bmp")
+    obj = open(os.path.join(GOLDEN, "quadbox.obj")).read()
+    (tmp_path / "models" / f"bm_{name}.obj").write_text(obj.replace("mtllib quadbox.mtl", f"mtllib bm_{name}.mtl"))
+    (tmp_path / "models" / "materials" / f"bm_{name}.mtl").write_text(
+        f"newmtl plain\nKd 0.5 0.5 0.5\nmap_Kd ../textures/bm_{name}.bmp\n")
+    path = scenes.write_scene("cornellObj", str(tmp_path / "scenes" / "s.txt"), width=16, height=16,
+                              obj_path=f"../models/bm_{name}.bmp".replace(".bmp", ".obj"))
+    mine = api.Scene(path).pod
+    assert len(mine.textures) == 1
+    assert mine.textures[0].shape == want.shape and np.array_equal(mine.textures[0], want)
+
+
 def test_png_decoder_rejects_damaged_files(tmp_path):
     """Truncated and corrupted PNG data never crashes the loader and never yields a partial texture."""
     data = open(os.path.join(GOLDEN, "png", "rgb_93x71.png"), "rb").read()

@@ -1,7 +1,7 @@
 // fuzz_image_decoders.cpp -- mutation fuzzer for the texture decoders of the scene loader (csrc/host/image_decode.h,
-// png_decode.h, tga_decode.h): a library must reject a damaged texture file, never crash or hang on it.
+// png_decode.h, tga_decode.h, bmp_decode.h): a library must reject a damaged texture file, never crash or hang on it.
 //   g++ -std=c++17 -O1 -g -fwrapv -fsanitize=address,undefined -fno-sanitize=signed-integer-overflow \
-//       -I mygpuraytracer_b200/csrc/host tools/fuzz_image_decoders.cpp -o fuzz && ./fuzz file.jpg|png|tga iterations seed
+//       -I mygpuraytracer_b200/csrc/host tools/fuzz_image_decoders.cpp -o fuzz && ./fuzz file.jpg|png|tga|bmp iterations seed
 // Bit flips, truncations, 4-byte overwrites and injected 0xff bytes; tests/test_image_fuzz.py runs it on every fixture.
 #include "image_decode.h"
 #include <random>
@@ -23,6 +23,7 @@ int main(int argc, char** argv) {
     bool r;
     if (data[0] == 0xff) r = b2host::jpg::decode(b.data(), b.size(), &w, &h, &c, &out, &err);
     else if (data[0] == 0x89) r = b2host::png::decode(b.data(), b.size(), &w, &h, &c, &out, &err);
+    else if (data[0] == 'B' && data[1] == 'M') r = b2host::bmp::decode(b.data(), b.size(), &w, &h, &c, &out, &err);
     else r = b2host::tga::decode(b.data(), b.size(), &w, &h, &c, &out, &err);
     if (r) ++ok; else ++bad;
     if (argc > 4) fprintf(stderr, "%d %d\n", i, (int)r);
