@@ -15,7 +15,8 @@
 // The output is byte-identical to stbi_load for baseline files -- the seven shipped 4096x4096
 // textures (4:4:4) and the 4:2:0 / 4:2:2 / grey / restart-interval files of
 // tests/golden/jpeg (tests/test_loader.py checks both against texels dumped by the reference
-// loader).  Progressive files are rejected.
+// loader).  Progressive files (spectral selection and successive approximation, T.81 Annex G) are decoded
+// into a coefficient store first and transformed when the last scan is in, like stb_image does.
 #pragma once
 
 #include <cstdint>
@@ -68,6 +69,7 @@ struct Component {
   int dc_pred = 0;
   int w_blocks = 0, h_blocks = 0;  // allocated size in 8x8 blocks
   std::vector<uint8_t> plane;      // w_blocks*8 x h_blocks*8 samples
+  std::vector<short> coef;         // progressive files: 64 coefficients per block, w_blocks x h_blocks blocks
 };
 
 struct Decoder {
@@ -83,6 +85,7 @@ struct Decoder {
   Component comp[4];
   int restart_interval = 0;
   bool progressive = false;
+  int ss = 0, se = 63, ah = 0, al = 0, eobrun = 0;  // spectral selection / successive approximation of the scan
 
   int byte() { return p < end ? *p++ : 0; }
   int word() { int a = byte(); return (a << 8) | byte(); }
@@ -249,6 +252,92 @@ inline bool decode_block(Decoder& D, Component& c, short blk[64]) {
   return true;
 }
 
+// Progressive scans (T.81 Annex G): a DC scan sets or refines coefficient 0 of every block of its components,
+// an AC scan sets or refines the band ss..se of one component; end-of-band runs span blocks.
+inline bool prog_block_dc(Decoder& D, Component& c, short* blk) {
+  if (D.ah == 0) {
+    const int t = D.decode(D.dc[c.td]);
+    if (t < 0 || t > 15) return false;
+    const int diff = t ? D.receive_extend(t) : 0;
+    c.dc_pred += diff;
+    blk[0] = (short)(c.dc_pred * (1 << D.al));
+  } else if (D.bits(1)) {
+    blk[0] = (short)(blk[0] + (1 << D.al));
+  }
+  return true;
+}
+
+inline bool prog_block_ac(Decoder& D, Component& c, short* blk) {
+  const Huff& h = D.ac[c.ta];
+  if (D.ah == 0) {
+    if (D.eobrun) {
+      --D.eobrun;
+      return true;
+    }
+    for (int k = D.ss; k <= D.se;) {
+      const int rs = D.decode(h);
+      if (rs < 0) return false;
+      const int s = rs & 15, r = rs >> 4;
+      if (s == 0) {
+        if (r < 15) {
+          D.eobrun = 1 << r;
+          if (r) D.eobrun += D.bits(r);
+          --D.eobrun;
+          break;
+        }
+        k += 16;
+      } else {
+        k += r;
+        if (k > 63) return false;
+        blk[kZigzag[k++]] = (short)(D.receive_extend(s) * (1 << D.al));
+      }
+    }
+    return true;
+  }
+  const short bit = (short)(1 << D.al);
+  auto refine = [&](short* p) {
+    if (D.bits(1) && (*p & bit) == 0) *p = (short)(*p > 0 ? *p + bit : *p - bit);
+  };
+  if (D.eobrun) {
+    --D.eobrun;
+    for (int k = D.ss; k <= D.se; ++k) {
+      short* p = &blk[kZigzag[k]];
+      if (*p != 0) refine(p);
+    }
+    return true;
+  }
+  int k = D.ss;
+  do {
+    const int rs = D.decode(h);
+    if (rs < 0) return false;
+    int s = rs & 15, r = rs >> 4;
+    if (s == 0) {
+      if (r < 15) {
+        D.eobrun = (1 << r) - 1;
+        if (r) D.eobrun += D.bits(r);
+        r = 64;  // the rest of the band only gets refinement bits
+      }
+      // r == 15: sixteen zero coefficients, handled by the run below
+    } else {
+      if (s != 1) return false;
+      s = D.bits(1) ? bit : -bit;
+    }
+    while (k <= D.se) {
+      short* p = &blk[kZigzag[k++]];
+      if (*p != 0) {
+        refine(p);
+      } else {
+        if (r == 0) {
+          *p = (short)s;
+          break;
+        }
+        --r;
+      }
+    }
+  } while (k <= D.se);
+  return true;
+}
+
 inline bool decode(const uint8_t* data, size_t size, int* w, int* h, int* channels, std::vector<uint8_t>* out, std::string* err) {
   Decoder D;
   D.p = data;
@@ -287,7 +376,7 @@ inline bool decode(const uint8_t* data, size_t size, int* w, int* h, int* channe
         if ((tc >> 4) > 1 || !((tc >> 4) ? D.ac : D.dc)[tc & 15].build(counts, syms, n)) { *err = "bad DHT"; return false; }
       }
     } else if (m == 0xc0 || m == 0xc1 || m == 0xc2) {  // SOF0/1/2
-      if (m == 0xc2) { *err = "progressive JPEG is not supported"; return false; }
+      D.progressive = m == 0xc2;
       if (D.byte() != 8) { *err = "only 8-bit JPEG is supported"; return false; }
       D.height = D.word();
       D.width = D.word();
@@ -313,6 +402,7 @@ inline bool decode(const uint8_t* data, size_t size, int* w, int* h, int* channe
         D.comp[i].w_blocks = mcux * D.comp[i].h;
         D.comp[i].h_blocks = mcuy * D.comp[i].v;
         D.comp[i].plane.assign((size_t)D.comp[i].w_blocks * 8 * D.comp[i].h_blocks * 8, 0);
+        if (D.progressive) D.comp[i].coef.assign((size_t)D.comp[i].w_blocks * D.comp[i].h_blocks * 64, 0);
       }
       have_frame = true;
     } else if (m == 0xdd) {  // DRI
@@ -329,9 +419,33 @@ inline bool decode(const uint8_t* data, size_t size, int* w, int* h, int* channe
         D.comp[which].td = tt >> 4;
         D.comp[which].ta = tt & 15;
         if (D.comp[which].td > 3 || D.comp[which].ta > 3) { *err = "bad SOS table"; return false; }
-        if (!D.dc[D.comp[which].td].ok || !D.ac[D.comp[which].ta].ok) { *err = "JPEG scan uses a Huffman table that was never defined"; return false; }
         scan_comps[i] = which;
       }
+      D.ss = D.byte();
+      D.se = D.byte();
+      {
+        const int aa = D.byte();
+        D.ah = aa >> 4;
+        D.al = aa & 15;
+      }
+      if (D.progressive) {
+        if (D.ss > 63 || D.se > 63 || D.ss > D.se || D.ah > 13 || D.al > 13) { *err = "bad SOS"; return false; }
+        if (D.ss == 0 && D.se != 0) { *err = "JPEG scan mixes DC and AC coefficients"; return false; }
+        if (D.ss != 0 && n_scan != 1) { *err = "interleaved AC scan"; return false; }
+      } else {
+        D.ss = 0;
+        D.se = 63;
+        D.ah = D.al = 0;
+      }
+      for (int i = 0; i < n_scan; ++i) {
+        const Component& sc = D.comp[scan_comps[i]];
+        const bool need_dc = !D.progressive || (D.ss == 0 && D.ah == 0), need_ac = !D.progressive || D.ss != 0;
+        if ((need_dc && !D.dc[sc.td].ok) || (need_ac && !D.ac[sc.ta].ok)) {
+          *err = "JPEG scan uses a Huffman table that was never defined";
+          return false;
+        }
+      }
+      D.eobrun = 0;
       D.p = seg_end;
       // entropy-coded segment
       D.bitbuf = 0; D.bitcnt = 0; D.hit_marker = false;
@@ -352,6 +466,7 @@ inline bool decode(const uint8_t* data, size_t size, int* w, int* h, int* channe
           D.p += 2;
           D.hit_marker = false;
           for (int i = 0; i < D.ncomp; ++i) D.comp[i].dc_pred = 0;
+          D.eobrun = 0;
           todo = D.restart_interval;
         }
         return true;
@@ -361,8 +476,13 @@ inline bool decode(const uint8_t* data, size_t size, int* w, int* h, int* channe
         const int bw = (((D.width * c.h + D.hmax - 1) / D.hmax) + 7) / 8, bh = (((D.height * c.v + D.vmax - 1) / D.vmax) + 7) / 8;
         for (int by = 0; by < bh; ++by)
           for (int bx = 0; bx < bw; ++bx) {
-            if (!decode_block(D, c, blk)) { *err = "corrupt JPEG data"; return false; }
-            idct_block(&c.plane[((size_t)by * 8) * c.w_blocks * 8 + (size_t)bx * 8], c.w_blocks * 8, blk);
+            if (D.progressive) {
+              short* cb = &c.coef[((size_t)by * c.w_blocks + bx) * 64];
+              if (!(D.ss == 0 ? prog_block_dc(D, c, cb) : prog_block_ac(D, c, cb))) { *err = "corrupt JPEG data"; return false; }
+            } else {
+              if (!decode_block(D, c, blk)) { *err = "corrupt JPEG data"; return false; }
+              idct_block(&c.plane[((size_t)by * 8) * c.w_blocks * 8 + (size_t)bx * 8], c.w_blocks * 8, blk);
+            }
             restart_if_needed();
           }
       } else {
@@ -373,6 +493,11 @@ inline bool decode(const uint8_t* data, size_t size, int* w, int* h, int* channe
               Component& c = D.comp[scan_comps[i]];
               for (int y = 0; y < c.v; ++y)
                 for (int x = 0; x < c.h; ++x) {
+                  if (D.progressive) {  // only DC scans are interleaved (checked above)
+                    short* cb = &c.coef[(((size_t)my * c.v + y) * c.w_blocks + ((size_t)mx * c.h + x)) * 64];
+                    if (!prog_block_dc(D, c, cb)) { *err = "corrupt JPEG data"; return false; }
+                    continue;
+                  }
                   if (!decode_block(D, c, blk)) { *err = "corrupt JPEG data"; return false; }
                   const size_t px = ((size_t)mx * c.h + x) * 8, py = ((size_t)my * c.v + y) * 8;
                   idct_block(&c.plane[py * c.w_blocks * 8 + px], c.w_blocks * 8, blk);
@@ -388,6 +513,18 @@ inline bool decode(const uint8_t* data, size_t size, int* w, int* h, int* channe
     D.p = seg_end;
   }
   if (!have_frame) { *err = "JPEG has no frame"; return false; }
+  if (D.progressive) {
+    // all scans are in: dequantise (16-bit, as stb_image does) and transform every block
+    for (int k = 0; k < D.ncomp; ++k) {
+      Component& c = D.comp[k];
+      for (int by = 0; by < c.h_blocks; ++by)
+        for (int bx = 0; bx < c.w_blocks; ++bx) {
+          short* cb = &c.coef[((size_t)by * c.w_blocks + bx) * 64];
+          for (int i = 0; i < 64; ++i) cb[i] = (short)(cb[i] * D.quant[c.tq][i]);
+          idct_block(&c.plane[((size_t)by * 8) * c.w_blocks * 8 + (size_t)bx * 8], c.w_blocks * 8, cb);
+        }
+    }
+  }
   *w = D.width;
   *h = D.height;
   *channels = D.ncomp;

@@ -3,7 +3,7 @@ stb_image, oracle/_ref/ref_cpu --b2s).
 
 The seven textures the reference ships are 4:4:4; textures of other assets usually are not.  PIL writes small
 baseline files with 4:2:0, 4:2:2, 4:4:4 sampling, odd sizes (partial MCUs, a chroma plane of width 1), restart
-intervals and a greyscale one; each becomes the map_Kd of tests/golden/quadbox.obj and goes through the
+intervals, a greyscale one and progressive files of each kind; each becomes the map_Kd of tests/golden/quadbox.obj and goes through the
 reference's loader.  jpeg/<name>.jpg is the input, jpeg/<name>.npy the texels the reference holds after loading
 (H x W x C, rows flipped as scene.cpp:133 does).
 Needs /root/reference (through oracle/_ref) and PIL; the outputs are committed.
@@ -30,6 +30,12 @@ CASES = {
     "s420_1x5": (1, 5, dict(subsampling=2, quality=90), False),
     "s420_restart_40x40": (40, 40, dict(subsampling=2, quality=80, restart_marker_blocks=2), False),
     "grey_21x13": (21, 13, dict(quality=90), True),
+    # progressive files (spectral selection + successive approximation); large enough for scene.cpp:148
+    "prog420_90x70": (90, 70, dict(subsampling=2, quality=88, progressive=True), False),
+    "prog444_57x43": (57, 43, dict(subsampling=0, quality=93, progressive=True), False),
+    "prog422_70x50": (70, 50, dict(subsampling=1, quality=75, progressive=True, optimize=True), False),
+    "prog_grey_95x77": (95, 77, dict(quality=85, progressive=True), True),
+    "prog420_restart_88x72": (88, 72, dict(subsampling=2, quality=80, progressive=True, restart_marker_blocks=3), False),
 }
 
 

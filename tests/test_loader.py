@@ -148,10 +148,12 @@ def test_standin_mesh_properties(tmp_path):
 
 
 @pytest.mark.parametrize("name", ["s420_64x48", "s420_37x29", "s422_50x20", "s444_33x17", "s420_2x2", "s420_1x5",
-                                  "s420_restart_40x40", "grey_21x13"])
+                                  "s420_restart_40x40", "grey_21x13", "prog420_90x70", "prog444_57x43", "prog422_70x50",
+                                  "prog_grey_95x77", "prog420_restart_88x72"])
 def test_jpeg_sampling_layouts_match_stb_image(tmp_path, name):
     """tests/golden/jpeg (see make_jpeg_golden.py): chroma-subsampled, odd-sized, restart-interval and grey
-    baseline files come out byte-identical to what the reference's loader (stb_image) holds."""
+    baseline files and progressive files of each kind come out byte-identical to what the reference's loader
+    (stb_image) holds."""
     want = np.load(os.path.join(GOLDEN, "jpeg", name + ".npy"))
     for d in ("models/materials", "textures"):
         (tmp_path / d).mkdir(parents=True)
