@@ -38,6 +38,23 @@ struct BitReader {
     n -= k;
     return v;
   }
+  uint32_t peek(int k) {  // up to k <= 16 bits without consuming them; fewer are valid at the very end of the data
+    while (n < k && p < end) {
+      acc |= (uint32_t)*p++ << n;
+      n += 8;
+    }
+    return acc & ((1u << k) - 1u);
+  }
+  void drop(int k) {
+    if (k > n) {
+      fail = true;
+      acc = 0;
+      n = 0;
+    } else {
+      acc >>= k;
+      n -= k;
+    }
+  }
   void to_byte_boundary() {  // drop the rest of the current byte, give whole buffered bytes back
     p -= n / 8;
     acc = 0;
@@ -45,11 +62,14 @@ struct BitReader {
   }
 };
 
+constexpr int kFastBits = 9;
 struct Huffman {  // canonical code: how many codes of each length, symbols ordered by (length, value)
   uint16_t count[16];
   uint16_t symbol[288];
+  uint16_t fast[1 << kFastBits];  // codes of up to kFastBits bits, indexed by the next bits of the stream: (length << 9) | symbol
   bool build(const uint8_t* len, int n) {
     memset(count, 0, sizeof count);
+    memset(fast, 0, sizeof fast);
     for (int i = 0; i < n; ++i) ++count[len[i]];
     uint16_t offs[16];
     offs[1] = 0;
@@ -62,9 +82,31 @@ struct Huffman {  // canonical code: how many codes of each length, symbols orde
       if (left < 0) return false;
     }
     count[0] = 0;
+    // the short codes once more, as a table over the next kFastBits bits of the stream (which delivers a code's
+    // bits most significant first, so the index is the code reversed, with every combination of the bits behind it)
+    int next_code[16];
+    next_code[0] = 0;
+    for (int l = 1, code = 0; l <= 15; ++l) {
+      code = (code + (l > 1 ? count[l - 1] : 0)) << 1;
+      next_code[l] = code;
+    }
+    for (int i = 0; i < n; ++i) {
+      const int l = len[i];
+      if (!l) continue;
+      const int code = next_code[l]++;
+      if (l > kFastBits) continue;
+      int rev = 0;
+      for (int k = 0; k < l; ++k) rev |= ((code >> k) & 1) << (l - 1 - k);
+      for (int hi = 0; hi < (1 << (kFastBits - l)); ++hi) fast[rev | (hi << l)] = (uint16_t)((l << 9) | i);
+    }
     return true;
   }
   int decode(BitReader& b) const {
+    const uint16_t e = fast[b.peek(kFastBits)];
+    if (e) {
+      b.drop(e >> 9);
+      return b.fail ? -1 : (e & 511);
+    }
     int code = 0, first = 0, index = 0;
     for (int l = 1; l <= 15; ++l) {
       code |= (int)b.get(1);
