@@ -160,7 +160,17 @@ typedef struct B2ptOptions {
                                  grids to a share of the SMs so that the
                                  contexts' kernels co-reside: lower latency
                                  per context is traded for throughput (def 1) */
-  int32_t reserved[7];
+  int32_t persistent_host_albedo; /* b2pt_pathtrace / b2pt_pipe_pathtrace copy the
+                                 albedo AOV to the host on EVERY call, as the
+                                 reference does (apps/src/pathtrace.cu:666-668)
+                                 (def 0).  1 = the caller asserts that the
+                                 albedo_host buffer it passes is persistent and
+                                 that nobody else writes it between calls (the
+                                 reference's scene->state.albedo is such a
+                                 buffer): the copy is then made only when the
+                                 AOV changed (iteration 1, reset, camera) or
+                                 the pointer is new                            */
+  int32_t reserved[6];
 } B2ptOptions;
 
 /* Fills `opt` with the defaults above (the reference's compile-time macros). */
@@ -212,10 +222,10 @@ int b2pt_read_accum(B2ptCtx* ctx, float* image_host, float* albedo_host);
 
 /* Exactly one reference pathtrace(pbo, frame, iter) call: render `iter`, then
  * copy image and albedo to the host buffers (scene->state.image / .albedo).
- * The albedo AOV only changes on iteration 1 and on a reset, so the copy into
- * `albedo_host` is skipped when the previous b2pt_pathtrace call already wrote
- * the current albedo to the SAME pointer (the reference's state.albedo is one
- * persistent vector); b2pt_read_accum always copies. */
+ * Both are copied on every call.  With B2ptOptions.persistent_host_albedo = 1
+ * the copy into `albedo_host` is skipped when the previous call already wrote
+ * the current albedo to the SAME pointer (the AOV only changes on iteration 1
+ * and on a reset); b2pt_read_accum always copies. */
 int b2pt_pathtrace(B2ptCtx* ctx, int32_t iter, float* image_host, float* albedo_host);
 
 /* ---- pipelined pathtrace() --------------------------------------------------------
@@ -242,8 +252,9 @@ void b2pt_pipe_destroy(B2ptPipe* pipe);
 
 /* One reference pathtrace(pbo, frame, iter) call: on return image_host holds
  * the running sum including iteration `iter`, albedo_host the iteration-1
- * albedo AOV (copied only when it changed or the pointer is new; either may be
- * NULL).  Synchronous for the caller; the lanes keep rendering ahead. */
+ * albedo AOV (every call; with persistent_host_albedo = 1 only when it changed
+ * or the pointer is new; either may be NULL).  Synchronous for the caller; the
+ * lanes keep rendering ahead. */
 int b2pt_pipe_pathtrace(B2ptPipe* pipe, int32_t iter, float* image_host, float* albedo_host);
 
 /* Zero the running sum, the albedo and every lane (Free + Init of
@@ -256,6 +267,13 @@ int b2pt_pipe_reset(B2ptPipe* pipe, const B2ptCamera* cam);
 float* b2pt_pipe_device_image(B2ptPipe* pipe);
 float* b2pt_pipe_device_albedo(B2ptPipe* pipe);
 
+/* sendImageToPBO / sendDenosiedImageToPBO for a pipelined host: as
+ * b2pt_tonemap_rgba8, `src_dev` NULL = the running sum.  Runs on the pipe's
+ * copy stream (never behind the iterations the lanes render ahead) and
+ * returns when rgba8_dev is written, so the caller may unmap / draw the PBO
+ * and overwrite `src_dev` at once (apps/src/main.cpp:270-271). */
+int b2pt_pipe_tonemap_rgba8(B2ptPipe* pipe, const float* src_dev, int32_t iter, uint8_t* rgba8_dev);
+
 /* Introspection: number of lanes, the context of lane k (statistics, BVH
  * info, tonemap), kernel launches of all lanes + merges, and how often a call
  * did not continue the predicted sequence. */
@@ -263,6 +281,12 @@ int32_t b2pt_pipe_lanes(B2ptPipe* pipe);
 B2ptCtx* b2pt_pipe_lane(B2ptPipe* pipe, int32_t k);
 int64_t b2pt_pipe_launch_count(B2ptPipe* pipe);
 int64_t b2pt_pipe_misses(B2ptPipe* pipe);
+
+/* timer().getGpuElapsedTimeForPreviousOperation() for a pipelined host
+ * (apps/src/main.cpp:263): milliseconds of the depth loop
+ * (apps/src/pathtrace.cu:583-653) of the iteration the last
+ * b2pt_pipe_pathtrace call consumed. */
+float b2pt_pipe_last_loop_ms(B2ptPipe* pipe);
 
 /* Device pointers of the accumulators (W*H*3 floats), for zero-copy hand-off
  * to a collective or a device-side denoiser. */

@@ -103,6 +103,9 @@ void pathtraceInit(Scene* scene) {
   s.iterations = (int)scene->state.iterations;
   B2ptOptions opt;
   b2pt_default_options(&opt);  // = the macros of apps/src/pathtrace.cu:36-42
+  // scene->state.albedo is one vector sized by the loader and written by nobody but pathtrace(): the library
+  // may skip the copy of an albedo AOV that has not changed since the previous call (it changes on iteration 1)
+  opt.persistent_host_albedo = 1;
   int lanes = 4;
   if (const char* e = getenv("B2PT_PIPE_LANES")) lanes = atoi(e) > 0 ? atoi(e) : 1;
   b2pt_check(b2pt_pipe_create(&s, &opt, lanes, &pipe), "pathtraceInit");
@@ -141,5 +144,7 @@ void pathtrace(uchar4* /*pbo*/, int /*frame*/, int iter) {  // pbo and frame are
 void sendToGPU(uchar4* pbo, int /*iter*/) {  // apps/src/pathtrace.cu:673-685
   cudaMemcpy(dev_denoised, hst_scene->state.output.data(), sizeof(glm::vec3) * hst_scene->state.output.size(),
              cudaMemcpyHostToDevice);
-  b2pt_check(b2pt_tonemap_rgba8(b2pt_pipe_lane(pipe, 0), dev_denoised, 0, reinterpret_cast<uint8_t*>(pbo)), "sendToGPU");
+  // synchronous for the caller: main.cpp unmaps the PBO right after this call (main.cpp:270-271) and the next
+  // frame overwrites dev_denoised
+  b2pt_check(b2pt_pipe_tonemap_rgba8(pipe, dev_denoised, 0, reinterpret_cast<uint8_t*>(pbo)), "sendToGPU");
 }

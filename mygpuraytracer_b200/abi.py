@@ -123,7 +123,8 @@ class Options(C.Structure):
         ("record_stages", C.c_int32),
         ("use_graph", C.c_int32),
         ("concurrent_contexts", C.c_int32),
-        ("reserved", C.c_int32 * 7),
+        ("persistent_host_albedo", C.c_int32),
+        ("reserved", C.c_int32 * 6),
     ]
 
 
@@ -146,6 +147,7 @@ def default_options(**kw) -> Options:
     o.record_stages = 0
     o.use_graph = 1
     o.concurrent_contexts = 1
+    o.persistent_host_albedo = 0
     for k, v in kw.items():
         if not hasattr(o, k):
             raise AttributeError(f"B2ptOptions has no field {k!r}")
@@ -194,10 +196,12 @@ SYMBOLS = {
     "b2pt_pipe_reset": (C.c_int, [_vp, C.POINTER(Camera)]),
     "b2pt_pipe_device_image": (_vp, [_vp]),
     "b2pt_pipe_device_albedo": (_vp, [_vp]),
+    "b2pt_pipe_tonemap_rgba8": (C.c_int, [_vp, _vp, _i32, _vp]),
     "b2pt_pipe_lanes": (_i32, [_vp]),
     "b2pt_pipe_lane": (_vp, [_vp, _i32]),
     "b2pt_pipe_launch_count": (_i64, [_vp]),
     "b2pt_pipe_misses": (_i64, [_vp]),
+    "b2pt_pipe_last_loop_ms": (C.c_float, [_vp]),
     "b2pt_device_image": (_vp, [_vp]),
     "b2pt_device_albedo": (_vp, [_vp]),
     "b2pt_set_device_image": (C.c_int, [_vp, _vp]),

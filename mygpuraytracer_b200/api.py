@@ -183,6 +183,9 @@ class Renderer:
         return image, albedo
 
     def pathtrace(self, iteration: int, image: np.ndarray, albedo: Optional[np.ndarray]) -> None:
+        """One reference ``pathtrace()`` call.  ``albedo`` is written on every call unless the context was created
+        with ``persistent_host_albedo=1``: then the caller vouches that it passes the same, otherwise untouched
+        array every time, and an unchanged AOV is not copied again."""
         _check(self.lib.b2pt_pathtrace(self._h, iteration, image.ctypes.data,
                                        albedo.ctypes.data if albedo is not None else None))
 
@@ -354,12 +357,14 @@ class Pipeline:
         return int(self.lib.b2pt_pipe_misses(self._h))
 
     def last_loop_ms(self) -> float:
-        return float(self.lib.b2pt_last_loop_ms(self.lib.b2pt_pipe_lane(self._h, 0)))
+        """Depth-loop time of the iteration the last call consumed; -1 until the call after the first query
+        (the pipe only pays for the measurement once a host asks for it)."""
+        return float(self.lib.b2pt_pipe_last_loop_ms(self._h))
 
     def tonemap_rgba8(self, dst_ptr: int, iteration: int, src_ptr: int = 0) -> None:
-        """``sendImageToPBO`` of the running sum (or of ``src_ptr``)."""
-        _check(self.lib.b2pt_tonemap_rgba8(self.lib.b2pt_pipe_lane(self._h, 0),
-                                           C.c_void_p(src_ptr or self.device_image_ptr()), iteration, C.c_void_p(dst_ptr)))
+        """``sendImageToPBO`` of the running sum (or of ``src_ptr``); returns when ``dst_ptr`` is written."""
+        _check(self.lib.b2pt_pipe_tonemap_rgba8(self._h, C.c_void_p(src_ptr) if src_ptr else None, iteration,
+                                                C.c_void_p(dst_ptr)))
 
 
 # ---------------------------------------------------------------------------------------
@@ -440,10 +445,15 @@ def pathtraceInit(scene: Scene) -> None:
     if _renderer is not None:
         _renderer.close()
     _hst_scene = scene
+    opt = _options_for_next_init
+    if opt is None:
+        # scene.state.albedo is one array owned by the Scene and written only by pathtrace(), like the reference's
+        # state.albedo vector: the unchanged AOV need not be copied again after iteration 1
+        opt = abi.default_options(persistent_host_albedo=1)
     if _lanes_for_next_init > 1:
-        _renderer = Pipeline(scene, _options_for_next_init, lanes=_lanes_for_next_init)
+        _renderer = Pipeline(scene, opt, lanes=_lanes_for_next_init)
     else:
-        _renderer = Renderer(scene, _options_for_next_init)
+        _renderer = Renderer(scene, opt)
 
 
 def pathtraceFree() -> None:

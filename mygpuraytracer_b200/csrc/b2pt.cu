@@ -92,6 +92,7 @@ extern "C" void b2pt_default_options(B2ptOptions* o) {
   o->record_stages = 0;
   o->use_graph = 1;
   o->concurrent_contexts = 1;
+  o->persistent_host_albedo = 0;  // copy the albedo AOV every call, like pathtrace.cu:666-668
 }
 
 // ---------------------------------------------------------------------------------
@@ -276,6 +277,19 @@ static DevCamera to_dev_camera(const B2ptCamera& c) {
 // ---------------------------------------------------------------------------------
 // radix sort of pairs (device arrays), used by the LBVH build and exported
 // ---------------------------------------------------------------------------------
+struct Scratch {  // frees everything on scope exit
+  std::vector<void*> p;
+  ~Scratch() { for (void* q : p) cudaFree(q); }
+  template <typename T>
+  cudaError_t get(T** out, size_t count) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess) p.push_back(q);
+    *out = (T*)q;
+    return e;
+  }
+};
+
 struct RadixTemps {
   unsigned int* hist = nullptr;     // [4][256]
   unsigned int* tickets = nullptr;  // [4]
@@ -303,6 +317,17 @@ static void radix_temps_free(RadixTemps* t) {
   cudaFree(t->val_alt);
   *t = RadixTemps();
 }
+struct RadixTempsGuard {  // frees on every return path
+  RadixTemps t;
+  ~RadixTempsGuard() { radix_temps_free(&t); }
+};
+struct EventPair {
+  cudaEvent_t a = nullptr, b = nullptr;
+  ~EventPair() {
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+  }
+};
 
 // Sorts n pairs in place (result ends in key/val after four passes).  Asynchronous on `s`; the temporaries
 // must stay alive until the stream has run the passes.
@@ -367,26 +392,29 @@ static int build_mesh(B2ptCtx* c, const float* pos_host, const float* uv_host, i
   // ray origin in this mesh's object space); origin_radius bounds that coordinate (pad = 2^-19 * it)
   const float pad = 4e-6f * std::max(ext, 1.0f) + 1.9073486328125e-6f * origin_radius;
 
+  // temporaries, events and the radix buffers are released on every return path
+  Scratch tmp;
   TriBounds* bounds = nullptr;
   uint32_t *code = nullptr, *val = nullptr;
   float4 *leaf_box = nullptr, *node_box = nullptr;
   int2* children = nullptr;
   int *parent = nullptr, *visit = nullptr;
-  CK(cudaMalloc(&bounds, sizeof(TriBounds)));
-  CK(cudaMalloc(&code, (size_t)n * 4));
-  CK(cudaMalloc(&val, (size_t)n * 4));
-  CK(cudaMalloc(&leaf_box, (size_t)n * 2 * sizeof(float4)));
-  CK(cudaMalloc(&node_box, (size_t)std::max(n - 1, 1) * 2 * sizeof(float4)));
-  CK(cudaMalloc(&children, (size_t)std::max(n - 1, 1) * sizeof(int2)));
-  CK(cudaMalloc(&parent, (size_t)(2 * n) * sizeof(int)));
-  CK(cudaMalloc(&visit, (size_t)std::max(n - 1, 1) * sizeof(int)));
-  RadixTemps rtemps;  // allocated up front: build_ms below is device time, not cudaMalloc latency
+  CK(tmp.get(&bounds, 1));
+  CK(tmp.get(&code, (size_t)n));
+  CK(tmp.get(&val, (size_t)n));
+  CK(tmp.get(&leaf_box, (size_t)n * 2));
+  CK(tmp.get(&node_box, (size_t)std::max(n - 1, 1) * 2));
+  CK(tmp.get(&children, (size_t)std::max(n - 1, 1)));
+  CK(tmp.get(&parent, (size_t)(2 * n)));
+  CK(tmp.get(&visit, (size_t)std::max(n - 1, 1)));
+  RadixTempsGuard rguard;  // allocated up front: build_ms below is device time, not cudaMalloc latency
+  RadixTemps& rtemps = rguard.t;
   if ((rc = radix_temps_alloc(&rtemps, n))) return rc;
 
-  cudaEvent_t e0, e1;
-  CK(cudaEventCreate(&e0));
-  CK(cudaEventCreate(&e1));
-  CK(cudaEventRecord(e0, s));
+  EventPair ev;
+  CK(cudaEventCreate(&ev.a));
+  CK(cudaEventCreate(&ev.b));
+  CK(cudaEventRecord(ev.a, s));
   const int blocks = (n + 255) / 256;
   k_bounds_init<<<1, 32, 0, s>>>(bounds);
   k_centroid_bounds<<<std::min(blocks, 1184), 256, 0, s>>>(out->face_pos, n, bounds);
@@ -395,6 +423,8 @@ static int build_mesh(B2ptCtx* c, const float* pos_host, const float* uv_host, i
   if ((rc = radix_sort_pairs_dev(code, val, n, s, &c->launches, rtemps))) return rc;
   k_leaves<<<blocks, 256, 0, s>>>(out->face_pos, val, n, pad, out->tris, leaf_box);
   c->launches += 1;
+  TriBounds hb;
+  memset(&hb, 0, sizeof hb);
   if (n >= 2) {
     CK(cudaMemsetAsync(visit, 0, (size_t)(n - 1) * sizeof(int), s));
     const int iblocks = (n - 1 + 255) / 256;
@@ -405,35 +435,26 @@ static int build_mesh(B2ptCtx* c, const float* pos_host, const float* uv_host, i
     k_emit_wide4<<<iblocks, 256, 0, s>>>(n, children, visit, leaf_box, node_box, out->nodes);
     c->launches += 5;
     // depth of the wide tree (visit[] is free again): one level per launch until nothing is reached any more;
-    // a binary tree of depth D gives at most D wide levels
+    // a binary tree of depth D gives at most D wide levels, and D is known by now (one small read-back)
     CK(cudaMemsetAsync(visit, 0, (size_t)(n - 1) * sizeof(int), s));
     const int one = 1;
     CK(cudaMemcpyAsync(visit, &one, sizeof(int), cudaMemcpyHostToDevice, s));
-    for (int level = 1; level <= 64; ++level) k_wide_levels<<<iblocks, 256, 0, s>>>(n, out->nodes, visit, level, bounds);
-    c->launches += 64;
+    CK(cudaMemcpyAsync(&hb, bounds, sizeof hb, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const int levels = std::max(1, std::min(hb.max_depth, 64));
+    for (int level = 1; level <= levels; ++level) k_wide_levels<<<iblocks, 256, 0, s>>>(n, out->nodes, visit, level, bounds);
+    c->launches += levels;
   }
-  CK(cudaEventRecord(e1, s));
+  CK(cudaEventRecord(ev.b, s));
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(s));
-  CK(cudaEventElapsedTime(&out->info.build_ms, e0, e1));
-  TriBounds hb;
+  CK(cudaEventElapsedTime(&out->info.build_ms, ev.a, ev.b));
   CK(cudaMemcpy(&hb, bounds, sizeof hb, cudaMemcpyDeviceToHost));
   out->info.max_depth = n >= 2 ? hb.max_depth : 1;
   const int wide_depth = n >= 2 ? hb.wide_depth : 0;
   if (getenv("B2PT_TRAVERSAL_STATS"))
     fprintf(stderr, "[b2pt bvh] %d triangles: binary depth %d, 4-wide depth %d (stack bound %d of %d entries)\n", n,
             out->info.max_depth, wide_depth, 3 * wide_depth, kWalkShort + kWalkSpill);
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
-  cudaFree(bounds);
-  cudaFree(code);
-  cudaFree(val);
-  cudaFree(leaf_box);
-  cudaFree(node_box);
-  cudaFree(children);
-  cudaFree(parent);
-  cudaFree(visit);
-  radix_temps_free(&rtemps);
   // a walk's stack holds at most three entries per inner wide node on its path (nearest child first, the other
   // hits pushed); k_mesh_walk_long's depth-first fallback relies on the same bound
   if (out->info.max_depth > 64 || 3 * wide_depth > kWalkShort + kWalkSpill)
@@ -1144,8 +1165,13 @@ extern "C" int b2pt_render(B2ptCtx* c, int32_t iter_first, int32_t iter_count, i
     CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
     int rc = enqueue_iteration(c, false, true, true);
     cudaError_t e = cudaStreamEndCapture(c->stream, &c->graph);
-    if (rc) return rc;
-    if (e != cudaSuccess) return fail(B2PT_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    if (rc || e != cudaSuccess) {  // do not keep a half-captured graph
+      if (c->graph) cudaGraphDestroy(c->graph);
+      c->graph = nullptr;
+      c->launches = before;
+      if (rc) return rc;
+      return fail(B2PT_ERR_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+    }
     c->graph_kernels = (int)(c->launches - before);
     c->launches = before;
     CK(cudaGraphInstantiate(&c->graph_exec, c->graph, 0));
@@ -1178,7 +1204,9 @@ extern "C" int b2pt_read_accum(B2ptCtx* c, float* image_host, float* albedo_host
 extern "C" int b2pt_pathtrace(B2ptCtx* c, int32_t iter, float* image_host, float* albedo_host) {
   int rc = b2pt_render(c, iter, 1, 1);
   if (rc) return rc;
-  const bool albedo_current = albedo_host && albedo_host == c->albedo_host_last && c->albedo_host_version == c->albedo_version;
+  // only a caller that vouches for its buffer (persistent_host_albedo) may skip the copy of an unchanged AOV
+  const bool albedo_current = c->opt.persistent_host_albedo && albedo_host && albedo_host == c->albedo_host_last &&
+                              c->albedo_host_version == c->albedo_version;
   rc = b2pt_read_accum(c, image_host, albedo_current ? nullptr : albedo_host);
   if (rc == 0 && albedo_host) {
     c->albedo_host_last = albedo_host;
@@ -1315,6 +1343,16 @@ __global__ void k_tonemap(const float* __restrict__ src, int n, int iter, uchar4
   o.z = (unsigned char)min(max(cb, 0), 255);
   o.w = 0;
   dst[i] = o;
+}
+
+// used by pipe.cu: the same kernel on a stream of the caller's choice
+extern "C" int b2pt_tonemap_on_stream_(B2ptCtx* c, const float* src_dev, int32_t iter, uint8_t* rgba8_dev, void* stream) {
+  if (!c || !rgba8_dev || !src_dev) return fail(B2PT_ERR_INVALID, "ctx, src_dev and rgba8_dev must not be NULL");
+  CK(cudaSetDevice(c->device));
+  k_tonemap<<<(c->P + 255) / 256, 256, 0, (cudaStream_t)stream>>>(src_dev, c->P, iter, (uchar4*)rgba8_dev);
+  c->launches += 1;
+  CK(cudaGetLastError());
+  return 0;
 }
 
 extern "C" int b2pt_tonemap_rgba8(B2ptCtx* c, const float* src_dev, int32_t iter, uint8_t* rgba8_dev) {
@@ -1501,18 +1539,6 @@ extern "C" int b2pt_bvh_info(B2ptCtx* c, int32_t geom, B2ptBvhInfo* info) {
 // ---------------------------------------------------------------------------------
 // standalone primitives on host arrays
 // ---------------------------------------------------------------------------------
-struct Scratch {  // frees everything on scope exit
-  std::vector<void*> p;
-  ~Scratch() { for (void* q : p) cudaFree(q); }
-  template <typename T>
-  cudaError_t get(T** out, size_t count) {
-    void* q = nullptr;
-    cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
-    if (e == cudaSuccess) p.push_back(q);
-    *out = (T*)q;
-    return e;
-  }
-};
 
 template <int MODE>
 static int scan_family_host(int n, const int* in_host, const uint8_t* flags_host, int* out_host, int* count_out) {

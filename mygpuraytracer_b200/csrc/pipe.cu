@@ -30,6 +30,7 @@
 #include "../../include/b2pt.h"
 
 extern "C" void b2pt_set_last_error_(const char* msg);
+extern "C" int b2pt_tonemap_on_stream_(B2ptCtx* c, const float* src_dev, int32_t iter, uint8_t* rgba8_dev, void* stream);
 
 namespace {
 
@@ -74,6 +75,7 @@ struct Lane {
   cudaEvent_t merged = nullptr;    // its contribution has been folded into the sum
   int iter = 0;
   bool busy = false;
+  bool rendered_valid = false;     // `rendered` has been recorded at least once
 };
 
 }  // namespace
@@ -90,11 +92,14 @@ struct B2ptPipe {
   cudaStream_t copy = nullptr;
   int sm_count = 148;
   int albedo_lane = 0;
+  bool albedo_skip_unchanged = false;  // B2ptOptions.persistent_host_albedo
   uint64_t albedo_version = 1, albedo_host_version = 0;
   const float* albedo_host_last = nullptr;
   int64_t merges = 0;
   int64_t misses = 0;
   int last_lane = 0;
+  bool track_loop_ms = false;  // switched on by the first b2pt_pipe_last_loop_ms call
+  float last_loop_ms = -1.0f;
 };
 
 static int pipe_enqueue(B2ptPipe* p, Lane& L, int lane_index, int iter, bool after_merge) {
@@ -102,9 +107,10 @@ static int pipe_enqueue(B2ptPipe* p, Lane& L, int lane_index, int iter, bool aft
   int rc = b2pt_render(L.ctx, iter, 1, 1);
   if (rc) return rc;
   PCK(cudaEventRecord(L.rendered, L.stream));
+  L.rendered_valid = true;
   L.iter = iter;
   L.busy = true;
-  if (iter <= 1) {  // iteration 1 writes the albedo AOV (apps/src/pathtrace.cu:412)
+  if (iter == 1) {  // iteration 1, and only it, writes the albedo AOV (apps/src/pathtrace.cu:412)
     p->albedo_lane = lane_index;
     p->albedo_version += 1;
   }
@@ -162,6 +168,7 @@ extern "C" int b2pt_pipe_create(const B2ptScene* scene, const B2ptOptions* opt, 
   o.concurrent_contexts = lanes;
   B2ptPipe* p = new (std::nothrow) B2ptPipe();
   if (!p) return pipe_fail(B2PT_ERR_NOMEM, "out of host memory");
+  p->albedo_skip_unchanged = o.persistent_host_albedo != 0;
   p->device = o.device;
   p->floats = (size_t)scene->camera.resolution[0] * (size_t)scene->camera.resolution[1] * 3;
   p->lanes.resize((size_t)lanes);
@@ -219,13 +226,22 @@ extern "C" int b2pt_pipe_pathtrace(B2ptPipe* p, int32_t iter, float* image_host,
   p->merges += 1;
   const size_t bytes = p->floats * sizeof(float);
   if (image_host) PCK(cudaMemcpyAsync(image_host, p->sum, bytes, cudaMemcpyDeviceToHost, p->copy));
-  if (albedo_host && !(albedo_host == p->albedo_host_last && p->albedo_host_version == p->albedo_version)) {
-    // the albedo AOV lives in the context that rendered iteration 1; that render is complete: either it is
-    // the one just waited for, or an earlier call consumed it
+  if (albedo_host && !(p->albedo_skip_unchanged && albedo_host == p->albedo_host_last &&
+                       p->albedo_host_version == p->albedo_version)) {
+    // the albedo AOV lives in the context that rendered (or is rendering) iteration 1: wait for that render,
+    // which need not be the one this call consumes (a host that starts at iteration 0 finds iteration 1 one
+    // lane ahead)
+    Lane& A = p->lanes[(size_t)p->albedo_lane];
+    if (A.rendered_valid) PCK(cudaStreamWaitEvent(p->copy, A.rendered, 0));
     PCK(cudaMemcpyAsync(albedo_host, b2pt_device_albedo(p->lanes[(size_t)p->albedo_lane].ctx), bytes, cudaMemcpyDeviceToHost,
                         p->copy));
     p->albedo_host_last = albedo_host;
     p->albedo_host_version = p->albedo_version;
+  }
+  if (p->track_loop_ms) {
+    // the lane's loop events are recorded again by its next render: read them before it is re-armed
+    PCK(cudaEventSynchronize(L.rendered));
+    p->last_loop_ms = b2pt_last_loop_ms(L.ctx);
   }
   // the lane moves on to the iteration `lanes` steps ahead as soon as its contribution has been consumed
   L.busy = false;
@@ -261,6 +277,16 @@ extern "C" int b2pt_pipe_reset(B2ptPipe* p, const B2ptCamera* cam) {
   return 0;
 }
 
+extern "C" int b2pt_pipe_tonemap_rgba8(B2ptPipe* p, const float* src_dev, int32_t iter, uint8_t* rgba8_dev) {
+  if (!p || !rgba8_dev) return pipe_fail(B2PT_ERR_INVALID, "pipe and rgba8_dev must not be NULL");
+  PCK(cudaSetDevice(p->device));
+  // the copy stream holds only merges and copies, never the iterations the lanes render ahead
+  int rc = b2pt_tonemap_on_stream_(p->lanes[0].ctx, src_dev ? src_dev : p->sum, iter, rgba8_dev, (void*)p->copy);
+  if (rc) return rc;
+  PCK(cudaStreamSynchronize(p->copy));
+  return 0;
+}
+
 extern "C" float* b2pt_pipe_device_image(B2ptPipe* p) { return p ? p->sum : nullptr; }
 extern "C" float* b2pt_pipe_device_albedo(B2ptPipe* p) {
   return p ? b2pt_device_albedo(p->lanes[(size_t)p->albedo_lane].ctx) : nullptr;
@@ -276,3 +302,11 @@ extern "C" int64_t b2pt_pipe_launch_count(B2ptPipe* p) {
   return n;
 }
 extern "C" int64_t b2pt_pipe_misses(B2ptPipe* p) { return p ? p->misses : 0; }
+extern "C" float b2pt_pipe_last_loop_ms(B2ptPipe* p) {
+  if (!p) return -1.0f;
+  if (!p->track_loop_ms) {  // costs one host wait per call, so it is only paid by hosts that ask
+    p->track_loop_ms = true;
+    return -1.0f;
+  }
+  return p->last_loop_ms;
+}
