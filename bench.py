@@ -1,36 +1,34 @@
 #!/usr/bin/env python
 """bench.py -- Mpaths/s of the wavefront path-tracing loop (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config 1..5] [--spp S]
 
-Workload (config.workload): scenes/cornellSpaceship.txt at 1920x1080, depth 8
--- the configuration BASELINE.json's metric is quoted on -- with the generated
-STAND-IN MESH (the reference's spaceship OBJ is missing from its checkout) and
-the reference's four 4096x4096 textures when the build copied them, procedural
-ones otherwise (config.textures says which).
+Workload (config.workload): BASELINE.json configs[3], the configuration its metric is quoted on --
+scenes/cornellSpaceship.txt at 1920x1080, depth 8 -- with the generated STAND-IN MESH (the reference's spaceship
+OBJ is missing from its checkout) and the reference's four 4096x4096 textures when the build copied them,
+procedural ones otherwise (config.textures says which).  --config selects any of the five BASELINE.json
+configurations.
 
-A step is ONE iteration (one sample per pixel through the whole depth loop) on
-every rank.  Ranks shard samples per pixel: rank r of N renders iteration
-indices r+1, r+1+N, ... into its own accumulator; after the K timed steps the
-accumulators are combined with one NCCL reduce (inside the timed region).
-`value` = N*K*W*H paths / max-over-ranks device time, scaling "weak".
+A step is ONE FRAME: one iteration (one sample per pixel through the whole depth loop) on EVERY rank.  Rank r of
+a frame that starts at iteration i renders i + r; the frame is combined on the device (csrc/multi.cu:
+k_frame_reduce over NVLink peer memory, or one NCCL reduce with --reduce nccl) into the running sum on rank 0,
+once per frame.  Both legs go through mygpuraytracer_b200.distributed.FrameRenderer (b2pt_shard_*):
+  value   frames stay on the device (no host pointers): N*K*W*H paths / max-over-ranks device time
+  e2e     the same frames with the reference's output contract (apps/src/pathtrace.cu:662-668): after EVERY
+          frame rank 0 copies the running sum to pinned host memory; d2h bytes counted per step
+Each leg times the K-step window `--reps` times back to back (pipeline full at both ends) and reports the
+median window; `windows_ms` holds all of them.
 
 Keys beyond the base contract:
-  e2e           the same metric through the reference-facing call
-                b2pt_pathtrace(): every step renders one iteration and copies
-                the running sum and the albedo AOV to pinned HOST buffers, as
-                the reference's pathtrace() does (apps/src/pathtrace.cu:663-668)
-  roofline      the dominant kernel (k_intersect): algorithmic bytes (56 B per
-                path segment: 24 B ray read + 32 B hit record written) over its
-                device time measured with CUDA events in this run, against the
-                measured HBM copy bandwidth (MEASURED_PEAKS.json)
-  roofline_iter Bytes_iter = 84*P + 280*S over the step
-  cpu_baseline  the reference's own intersections.h / interactions.h compiled
-                for the host (oracle/_ref/ref_cpu, kind "reference") or the C
-                oracle (kind "port") on a bounded sample of the same scene
-  reference_gpu the reference's unmodified pathtrace.cu built for sm_100a
-                (oracle/_ref/ref_gpu) on the same workload, same GPU, when the
-                binary travelled to the box (the >=10x comparator of north_star)
+  roofline        the kernel with the largest device time in one iteration (CUDA events around every launch of
+                  a lane context of the timed region, run alone): algorithmic bytes / average launch time against
+                  the measured HBM copy bandwidth (MEASURED_PEAKS.json); `regime` says which grids were timed
+  roofline_iter   Bytes_iter = 84*P + 280*S over the step
+  cpu_baseline    the reference's own intersections.h / interactions.h compiled for the host
+                  (oracle/_ref/ref_cpu, kind "reference") or the C oracle (kind "port") on a bounded sample
+  cpu_baseline_config1  BASELINE.md's B-CPU line: scenes/cornell.txt 800x800 depth 8, iteration 1, in full
+  reference_gpu   the reference's unmodified pathtrace.cu built for sm_100a (oracle/_ref/ref_gpu) on the same
+                  workload and GPU: 1 warm-up + 3 timed calls, min / median (the >=10x comparator of north_star)
 """
 from __future__ import annotations
 
@@ -49,15 +47,27 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of each kernel, from the committed `ncu --set full`
-# capture of this workload (profiles/, cold caches: an upper bound on the warm traffic)
-TRAFFIC = {  # bytes per launch, depth-1 launches of profiles/r01_final_ncu_depth01.md and r01_final_ncu_unfused_depth1.md
+# capture of this workload (profiles/, cold caches: an upper bound on the warm traffic); see TRAFFIC_SOURCE
+TRAFFIC_SOURCE = "profiles/r01_final_ncu_depth01.md, r01_final_ncu_unfused_depth1.md (depth-1 launches)"
+TRAFFIC = {
     "k_intersect_analytic": 31.24e6, "k_mesh_walk": 71.61e6, "k_mesh_walk_long": 20.69e6, "k_mesh_finish": 50.24e6,
     "k_sort_material": 1.99e6, "k_shade_compact": 169.64e6, "k_shade_trace": 197.83e6, "k_generate_trace": 123.39e6,
 }
 
 METRIC = "Mpaths/s"
-SCENE = "cornellSpaceship"
-WIDTH, HEIGHT, DEPTH = 1920, 1080, 8
+# BASELINE.json "configs", in order.  4 is the configuration the metric is quoted on (the default).
+CONFIGS = {
+    1: dict(scene="cornell", width=800, height=800, depth=8, options={}, spp=1,
+            what="configs[0]: Cornell box, analytic spheres / cubes, diffuse; the reference's CPU-runnable case"),
+    2: dict(scene="cornellGlass", width=800, height=800, depth=8, options=dict(depth_of_field=1, antialiasing=1), spp=5000,
+            what="configs[1]: refractive + reflective BSDFs with DOF and stochastic AA, 5000 spp on 1 B200"),
+    3: dict(scene="cornellObj", width=1920, height=1080, depth=8, options={}, spp=0,
+            what="configs[2]: triangle mesh with diffuse / specular / emission textures, LBVH build + traversal"),
+    4: dict(scene="cornellSpaceship", width=1920, height=1080, depth=8, options={}, spp=0,
+            what="configs[3]: heavy textured / bump-mapped mesh, material sort + compaction, at 1/2/4/8 B200"),
+    5: dict(scene="cornellSpaceship", width=3840, height=2160, depth=12, options={}, spp=4096,
+            what="configs[4]: synthetic scaling, 4096 spp, spp-sharded at 2/4/8 B200"),
+}
 CPU_SAMPLE = (48, 27)  # resolution of the bounded CPU sample (same scene, mesh, depth): ~10 s per iteration on 8 cores
 
 
@@ -105,14 +115,23 @@ def prepare_assets(triangles: int, write: bool = True):
     return root, ("reference JPEGs" if assets.textures_are_reference(root) else "procedural 4096x4096 (reference JPEGs absent)")
 
 
-def workload_config(args, n_tris: int, textures: str):
+def workload_config(args, n_tris: int, textures: str, world: int):
+    from mygpuraytracer_b200 import scenes
+
+    mesh = scenes.uses_mesh(args.scene)
+    opts = CONFIGS[args.config]["options"]
     return {
-        "workload": f"scenes/{SCENE}.txt {args.width}x{args.height} depth {args.depth}, STAND-IN MESH {n_tris} triangles "
-                    f"(reference OBJ missing), AA on, DOF off, material sort on",
-        "scene": SCENE, "width": args.width, "height": args.height, "depth": args.depth,
-        "triangles": n_tris, "textures": textures,
-        "step": "one iteration (1 spp) per rank", "sharding": "samples-per-pixel, one NCCL reduce per frame",
-        "streams_per_gpu": args.streams,
+        "workload": f"BASELINE.json configs[{args.config - 1}]: scenes/{args.scene}.txt {args.width}x{args.height} depth {args.depth}"
+                    + (f", STAND-IN MESH {n_tris} triangles (reference OBJ missing)" if mesh else ", analytic geoms only")
+                    + f", AA on, DOF {'on' if opts.get('depth_of_field') else 'off'}, material sort on",
+        "baseline_config": args.config, "scene": args.scene, "width": args.width, "height": args.height, "depth": args.depth,
+        "triangles": n_tris if mesh else 0, "textures": textures if mesh else "none",
+        "step": "one frame = one iteration (1 spp) on every rank",
+        "sharding": "samples-per-pixel: rank r of a frame starting at iteration i renders i + r; the frame is combined into "
+                    "the running sum on rank 0 once per frame (" + ("k_frame_reduce over NVLink peer memory, in iteration order"
+                                                                       if args.reduce == "p2p" else "one NCCL reduce") + ")",
+        "reduce": args.reduce if world > 1 else "none (one rank)",
+        "lanes_per_gpu": args.streams,
         "l2": "working set per step (path state 2x48 B + hits 32 B per path, 4 textures, BVH) > 126 MB L2; no flush",
         "rng": "slot-keyed minstd (reference mode)", "trig": "native",
     }
@@ -213,62 +232,81 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+
 # ---------------------------------------------------------------------------------------
 # CPU legs
 # ---------------------------------------------------------------------------------------
-def cpu_sample(root: str, args, steps: int = 1, res=CPU_SAMPLE):
+def host_threads() -> int:
+    """The host cores this process may use, whatever OMP_NUM_THREADS the launcher exported
+    (torch.distributed.run sets it to 1)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_sample(root: str, args, steps: int = 1, res=CPU_SAMPLE, scene=None, depth=None):
     """Time the reference's CPU code on a bounded sample: the same scene file,
     mesh, textures and depth at a reduced resolution, `steps` iterations."""
     from mygpuraytracer_b200 import assets
 
     w, h = res
-    scene_txt = assets.scene_file(SCENE, w, h, depth=args.depth, root=root)
-    sample = f"{SCENE} {w}x{h} depth {args.depth}, same mesh/textures, {steps} iteration(s) of {w * h} paths"
+    scene = scene or args.scene
+    depth = depth or args.depth
+    threads = host_threads()
+    scene_txt = assets.scene_file(scene, w, h, depth=depth, root=root)
+    sample = f"{scene} {w}x{h} depth {depth}, same mesh/textures, {steps} iteration(s) of {w * h} paths"
     try:
         from oracle import harness
 
         if harness.have("ref_cpu"):
             # run from the asset tree's bin/ so '../models/...' resolves to the same files
-            cmd = [os.path.join(harness.REF_DIR, "ref_cpu"), "--scene", scene_txt, "--iters", str(steps)]
+            cmd = [os.path.join(harness.REF_DIR, "ref_cpu"), "--scene", scene_txt, "--iters", str(steps), "--threads", str(threads)]
+            env = dict(os.environ, OMP_NUM_THREADS=str(threads))
             t0 = time.time()
-            p = subprocess.run(cmd, cwd=os.path.join(root, "bin"), capture_output=True, text=True, timeout=1800)
+            p = subprocess.run(cmd, cwd=os.path.join(root, "bin"), capture_output=True, text=True, timeout=1800, env=env)
             wall = time.time() - t0
             for line in p.stdout.splitlines():
                 if line.startswith("REF_CPU_RESULT"):
                     r = json.loads(line.split(" ", 1)[1])
                     return {"value": r["mpaths_per_s"], "unit": METRIC, "cores": r["threads"], "kind": "reference",
-                            "sample": sample, "ms_per_iteration": r["ms_per_iter"], "wall_s": round(wall, 2)}
+                            "sample": sample, "sample_width": w, "sample_height": h,
+                            "ms_per_iteration": r["ms_per_iter"], "wall_s": round(wall, 2)}
             log("ref_cpu produced no result line:", p.stderr[-500:])
     except Exception as e:  # fall through to the port
         log("ref_cpu unavailable:", e)
     from mygpuraytracer_b200 import abi, api
     from oracle import oracle
 
+    oracle.set_num_threads(threads)
     pod = api.Scene(scene_txt).pod
     t0 = time.time()
-    oracle.render(pod, abi.default_options(), 1, steps, 1)
+    oracle.render(pod, abi.default_options(**CONFIGS[args.config]["options"]), 1, steps, 1)
     dt = time.time() - t0
     return {"value": w * h * steps / dt / 1e6, "unit": METRIC, "cores": oracle.num_threads(), "kind": "port",
-            "sample": sample, "ms_per_iteration": 1e3 * dt / steps, "wall_s": round(dt, 2)}
+            "sample": sample, "sample_width": w, "sample_height": h, "ms_per_iteration": 1e3 * dt / steps, "wall_s": round(dt, 2)}
 
 
 def reference_gpu(root: str, args):
-    """The unmodified reference pathtrace.cu (sm_100a) on the full workload."""
+    """The unmodified reference pathtrace.cu (sm_100a) on the full workload: warm-up + timed calls."""
     exe = os.path.join(ROOT, "oracle", "_ref", "ref_gpu")
     if not os.access(exe, os.X_OK) or args.ref_gpu_iters <= 0:
         return None
     from mygpuraytracer_b200 import assets
 
-    scene_txt = assets.scene_file(SCENE, args.width, args.height, depth=args.depth, root=root)
+    scene_txt = assets.scene_file(args.scene, args.width, args.height, depth=args.depth, root=root)
     try:
-        p = subprocess.run([exe, "--scene", scene_txt, "--time", "--iters", str(args.ref_gpu_iters), "--warmup", "0"],
+        p = subprocess.run([exe, "--scene", scene_txt, "--time", "--iters", str(args.ref_gpu_iters), "--warmup", "1"],
                            cwd=os.path.join(root, "bin"), capture_output=True, text=True, timeout=args.ref_gpu_timeout)
         for line in p.stdout.splitlines():
             if line.startswith("REF_GPU_RESULT"):
                 r = json.loads(line.split(" ", 1)[1])
+                med = r.get("call_ms_median", r["call_ms_per_iter"])
                 return {"what": "reference apps/src/pathtrace.cu, unmodified, nvcc -O3 sm_100a, same GPU and workload",
-                        "iterations": r["iters"], "ms_per_iteration_loop": r["loop_ms_per_iter"],
-                        "ms_per_iteration_call": r["call_ms_per_iter"], "mpaths_per_s": r["mpaths_per_s_call"]}
+                        "warmup": r.get("warmup", 0), "iterations": r["iters"], "ms_per_iteration_loop": r["loop_ms_per_iter"],
+                        "ms_per_iteration_call": r["call_ms_per_iter"], "ms_per_call_min": r.get("call_ms_min"),
+                        "ms_per_call_median": med, "ms_per_call_max": r.get("call_ms_max"),
+                        "mpaths_per_s": args.width * args.height / (med * 1e-3) / 1e6}
         return {"error": (p.stderr or p.stdout)[-300:]}
     except subprocess.TimeoutExpired:
         return {"error": f"timed out after {args.ref_gpu_timeout}s"}
@@ -282,7 +320,7 @@ def reference_host_adapter(root: str, args, iters: int):
         return None
     from mygpuraytracer_b200 import assets
 
-    scene_txt = assets.scene_file(SCENE, args.width, args.height, depth=args.depth, root=root)
+    scene_txt = assets.scene_file(args.scene, args.width, args.height, depth=args.depth, root=root)
     try:
         p = subprocess.run([exe, "--scene", scene_txt, "--iters", str(iters)], cwd=os.path.join(root, "bin"),
                            capture_output=True, text=True, timeout=300)
@@ -302,29 +340,42 @@ def reference_host_adapter(root: str, args, iters: int):
 # arms
 # ---------------------------------------------------------------------------------------
 def run_reference(args, rank: int, world: int):
+    """The reference's CPU implementation of the path on this box's host cores (rank 0 only).  A step is one
+    iteration of a BOUNDED SAMPLE of the workload (same scene, mesh, textures, depth; fewer pixels): the
+    brute-force reference costs O(paths x triangles).  config.workload names the sample that really ran."""
     if rank != 0:
         return
     root, textures = prepare_assets(args.triangles)
-    from mygpuraytracer_b200 import standin_mesh
+    from mygpuraytracer_b200 import scenes, standin_mesh
 
-    n_tris = len(standin_mesh.build(args.triangles)[3])
-    # Size the sample so that steps+warmup iterations fit in ~150 s: the brute-force
-    # reference costs O(paths x triangles), so time scales with the pixel count.
+    n_tris = len(standin_mesh.build(args.triangles)[3]) if scenes.uses_mesh(args.scene) else 0
+    # Size the sample so that steps+warmup iterations fit in ~150 s.
     probe = cpu_sample(root, args, 1, (16, 9))
     per_pixel_s = probe["ms_per_iteration"] * 1e-3 / (16 * 9)
     budget_s = 150.0 / max(1, args.steps + min(args.warmup, 1))
-    pixels = max(16 * 9, min(CPU_SAMPLE[0] * CPU_SAMPLE[1], int(budget_s / per_pixel_s)))
-    h = max(9, int((pixels * 9 / 16) ** 0.5))
-    w = max(16, pixels // h)
+    full = args.width * args.height
+    pixels = max(16 * 9, min(full, int(budget_s / per_pixel_s)))
+    if pixels >= full:
+        w, h = args.width, args.height
+    else:
+        h = max(9, int((pixels * args.height / args.width) ** 0.5))
+        w = max(16, pixels // h)
     r = cpu_sample(root, args, max(1, args.steps + min(args.warmup, 1)), (w, h))
+    cfg = workload_config(args, n_tris, textures, world)
+    same = (w, h) == (args.width, args.height)
+    cfg["workload"] = (f"BOUNDED SAMPLE {w}x{h} of: " if not same else "") + cfg["workload"]
+    cfg["sample"] = {"width": w, "height": h, "paths_per_step": w * h, "full_width": args.width, "full_height": args.height,
+                     "same_config": same}
+    cfg["sharding"] = "none: host cores of rank 0"
+    cfg["reduce"] = "none"
     line = {
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": METRIC, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": r["ms_per_iteration"], "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, n_tris, textures),
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
         "cpu_baseline": {"value": r["value"], "unit": METRIC, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": METRIC, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": f"each step is one iteration of the bounded sample ({w}x{h}); Mpaths/s is size independent",
+        "note": f"each step is one iteration of the bounded sample ({w}x{h}, {w * h} paths, {r['cores']} host threads); "
+                "Mpaths/s of the brute-force reference falls with the triangle count, not with the pixel count",
     }
     emit(line)
 
@@ -333,7 +384,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     import numpy as np
     import torch
 
-    from mygpuraytracer_b200 import abi, api, assets, standin_mesh
+    from mygpuraytracer_b200 import abi, api, assets, distributed, scenes
 
     dist = None
     if world > 1:
@@ -344,250 +395,269 @@ def run_ours(args, rank: int, world: int, local_rank: int):
     scene_txt = None
     if rank == 0:
         root, textures = prepare_assets(args.triangles)
-        scene_txt = assets.scene_file(SCENE, args.width, args.height, depth=args.depth, root=root)
+        scene_txt = assets.scene_file(args.scene, args.width, args.height, depth=args.depth, root=root)
     if dist:
         dist.barrier()
     if rank != 0:
         root, textures = prepare_assets(args.triangles, write=False)
-        scene_txt = os.path.join(root, "scenes", f"{SCENE}_{args.width}x{args.height}_d{args.depth}.txt")
+        scene_txt = os.path.join(root, "scenes", f"{args.scene}_{args.width}x{args.height}_d{args.depth}.txt")
     t0 = time.time()
     scene = api.Scene(scene_txt)
     load_s = time.time() - t0
     pod = scene.pod
+    has_mesh = scenes.uses_mesh(args.scene)
     n_tris = len(pod.face_pos)
     P = pod.n_pixels
-    opt = abi.default_options(device=local_rank)
-    # the KC throughput contexts share the GPU (grids sized to a share of the SMs); the e2e leg below uses its
-    # own full-width context, because one pathtrace() call at a time wants the lowest latency
-    opt_shared = abi.default_options(device=local_rank, concurrent_contexts=max(1, args.streams))
-    # KC contexts per GPU, each on its own stream with its own accumulator, render
-    # interleaved iteration indices (the same samples-per-pixel sharding used
-    # across GPUs).  One iteration is 26 short dependent kernels that cannot fill
-    # 148 SMs on their own (a depth-7 launch has 250 k rays); independent
-    # iterations in flight overlap each other's tails.
+    cfg_opts = CONFIGS[args.config]["options"]
+    # rank 0's host buffers are two pinned arrays that nobody else writes: the albedo AOV, which only changes on
+    # iteration 1, is copied when it changed (declared in e2e.albedo); the every-call form is measured beside it
+    opt = abi.default_options(device=local_rank, persistent_host_albedo=1, **cfg_opts)
     KC = max(1, args.streams)
-    rs = [api.Renderer(scene, opt_shared)]
-    if args.private_scenes:
-        rs += [api.Renderer(scene, opt_shared) for _ in range(KC - 1)]
-    else:  # one copy of the scene (BVH, triangles, textures) on the device, shared by the KC contexts
-        rs += [api.Renderer(scene, opt_shared, share=rs[0]) for _ in range(KC - 1)]
-    r = rs[0]
-    mesh_geom = int(np.nonzero(pod.geoms["type"] == abi.OBJ)[0][0])
-    # every context builds its own BVH; the first build of a process also pays CUDA's lazy kernel loading
-    bvh = min((x.bvh_info(mesh_geom) for x in rs), key=lambda b: b.build_ms)
+    fr = distributed.FrameRenderer(scene, opt, lanes=KC, reduce=args.reduce)
+    shard = fr.shard
+    stream = torch.cuda.ExternalStream(shard.stream_ptr(), device=torch.device("cuda", local_rank))
+    lane0 = shard.lane(0)
+    mesh_geom = int(np.nonzero(pod.geoms["type"] == abi.OBJ)[0][0]) if has_mesh else -1
+    bvh = lane0.bvh_info(mesh_geom) if has_mesh else None
 
-    streams = [torch.cuda.Stream() for _ in range(KC)]
-    accs = [torch.zeros(P * 3, dtype=torch.float32, device="cuda") for _ in range(KC)]
-    for rk, st, ac in zip(rs, streams, accs):
-        rk.set_stream_ptr(st.cuda_stream)
-        rk.set_device_image_ptr(ac.data_ptr())
-    stream, acc = streams[0], accs[0]
-
-    W = args.warmup
-    K = args.steps                          # iterations per rank, split over the KC contexts
-    lanes = world * KC                      # independent iteration streams in the whole job
-
-    def first_of(c):
-        return rank * KC + c + 1
+    W, K, R = args.warmup, args.steps, max(1, args.reps)
+    host_img = torch.empty(P * 3, dtype=torch.float32).pin_memory()
+    host_alb = torch.empty(P * 3, dtype=torch.float32).pin_memory()
+    img_np, alb_np = host_img.numpy().reshape(P, 3), host_alb.numpy().reshape(P, 3)
+    frame = [0]  # frames rendered so far: the sequence never restarts, so no call is mispredicted
 
     def barrier():
         if dist:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run(iter_base, total):
-        """Queue `total` iterations over the contexts (exactly), fork/join around stream 0."""
-        for c in range(1, KC):
-            streams[c].wait_stream(stream)
-        for c in range(KC):
-            count = total // KC + (1 if c < total % KC else 0)
-            with torch.cuda.stream(streams[c]):
-                rs[c].render(first_of(c) + iter_base * lanes, count, lanes)
-        for c in range(1, KC):
-            stream.wait_stream(streams[c])
+    def frames(n, to_host):
+        for _ in range(n):
+            if to_host:
+                fr.pathtrace(1 + frame[0] * world, img_np, alb_np)
+            else:
+                fr.pathtrace(1 + frame[0] * world, None, None)
+            frame[0] += 1
 
-    # ---- device-resident throughput --------------------------------------------------------
-    with torch.cuda.stream(stream):
-        run(0, max(W, KC))
+    def timed_leg(to_host):
+        """W warm-up frames, then R back-to-back windows of exactly K frames; device time on the shard's stream,
+        max over ranks per window.  The lanes hold the next frames when a window starts and when it ends."""
+        frames(max(W, KC), to_host)
         barrier()
-        for ac in accs:
-            ac.zero_()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(R + 1)]
+        launches0 = shard.launch_count()
+        ev[0].record(stream)
+        for i in range(R):
+            frames(K, to_host)
+            ev[i + 1].record(stream)
         barrier()
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
-        launches0 = sum(x.launch_count() for x in rs)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        run(max(W, KC), K)
-        for c in range(1, KC):
-            acc.add_(accs[c])
+        launches = shard.launch_count() - launches0
+        ms = torch.tensor([ev[i].elapsed_time(ev[i + 1]) for i in range(R)], device="cuda")
+        cnt = torch.tensor([launches], device="cuda", dtype=torch.int64)
         if dist:
-            dist.reduce(acc, dst=0)
-        e1.record(stream)
-        barrier()
-        ms = e0.elapsed_time(e1)
-        clocks = sampler.stop() if rank == 0 else None
-        launches = sum(x.launch_count() for x in rs) - launches0
-        live = r.live_counts()
-    t = torch.tensor([ms], device="cuda")
-    if dist:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * K * P / (ms_max * 1e-3) / 1e6
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        return [float(x) for x in ms.tolist()], int(cnt.item())
+
+    if args.spp > 0:
+        converge(args, fr, shard, stream, dist, rank, world, P, img_np, alb_np, n_tris, textures, barrier)
+        fr.close()
+        if dist:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    dev_windows, dev_launches = timed_leg(False)
+    e2e_windows, e2e_launches = timed_leg(True)
+    clocks = sampler.stop() if rank == 0 else None
+    misses = shard.misses()
+    dev_ms, e2e_ms = statistics.median(dev_windows), statistics.median(e2e_windows)
+    value = world * K * P / (dev_ms * 1e-3) / 1e6
+    e2e_value = world * K * P / (e2e_ms * 1e-3) / 1e6
+    checksum = float(np.float64(img_np.sum())) if rank == 0 else 0.0
+    live = lane0.live_counts()
     segments = int(live[: args.depth].sum())
-    first = first_of(0)
 
-    # ---- per-kernel times of one iteration (CUDA events around every launch) ------------------
-    with torch.cuda.stream(stream):
-        prof = [r.profile_kernels(first + (2 * W + K + KC + i) * lanes) for i in range(5)]
-        barrier()
-        walks = r.walk_counts()
-        long_walks = r.walk_counts(long_walks=True)
-    prof = {k: statistics.median(p[k] for p in prof) for k in prof[0]}
-
-    # ---- end to end: the reference-facing call with host buffers ------------------------------
-    host_img = torch.empty(P * 3, dtype=torch.float32).pin_memory()
-    host_alb = torch.empty(P * 3, dtype=torch.float32).pin_memory()
-    img_np, alb_np = host_img.numpy().reshape(P, 3), host_alb.numpy().reshape(P, 3)
-    r_e2e = api.Renderer(scene, opt)
-    r_e2e.set_stream_ptr(stream.cuda_stream)
-    # the first LBVH build of a process also pays CUDA's lazy kernel loading; this context builds its own
-    bvh = min([bvh, r_e2e.bvh_info(mesh_geom)], key=lambda b: b.build_ms)
-    with torch.cuda.stream(stream):
-        r = r_e2e
-        for i in range(min(W, 3)):
-            r.pathtrace(first + i * lanes, img_np, alb_np)
-        barrier()
-        e0.record(stream)
-        for i in range(K):
-            r.pathtrace(first + (W + i) * lanes, img_np, alb_np)
-        if dist:
-            dist.reduce(acc, dst=0)
-        e1.record(stream)
-        barrier()
-        e2e_ms = e0.elapsed_time(e1)
-    t = torch.tensor([e2e_ms], device="cuda")
-    if dist:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * K * P / (float(t.item()) * 1e-3) / 1e6
-    checksum = float(np.float64(img_np.sum()))
-
-    # ---- end to end, pipelined: the same one-iteration-per-call contract served by b2pt_pipe_pathtrace -------
-    # (csrc/pipe.cu: KC lanes render the next iterations while the host consumes the current one; every call
-    # still returns the running sum in host memory, bit-identical to the single-context call above)
-    pipe = api.Pipeline(scene, opt, lanes=KC)
-    pipe_warm = max(3, min(W, 8))            # call 1 starts the lanes, call 2 learns the stride, call 3 is steady state
-    with torch.cuda.stream(stream):
-        for i in range(pipe_warm):
-            pipe.pathtrace(first + i * lanes, img_np, alb_np)
-        barrier()
-        misses0 = pipe.misses()
-        e0.record(stream)
-        for i in range(K):
-            pipe.pathtrace(first + (pipe_warm + i) * lanes, img_np, alb_np)
-        if dist:
-            dist.reduce(acc, dst=0)
-        e1.record(stream)
-        barrier()
-        pipe_ms = e0.elapsed_time(e1)
-        pipe_misses = pipe.misses() - misses0
-    tp = torch.tensor([pipe_ms], device="cuda")
-    if dist:
-        dist.all_reduce(tp, op=dist.ReduceOp.MAX)
-    pipe_value = world * K * P / (float(tp.item()) * 1e-3) / 1e6
-    pipe.close()
-    with torch.cuda.stream(stream):
-        prof_full = [r_e2e.profile_kernels(first + (3 * W + 2 * K + KC + i) * lanes) for i in range(5)]
-        barrier()
-    prof_full = {k: statistics.median(p[k] for p in prof_full) for k in prof_full[0]}
+    extras = {}
+    if rank == 0 and not args.no_extras:
+        # ---- per-kernel times of one iteration: a lane context of the timed region (shared-SM grids, unfused
+        # kernels), run alone, CUDA events around every launch.  ncu serialises launches, so its launch list of
+        # this command times the same kernels in the same regime (profiles/).
+        shard.sync()
+        for k in range(KC):
+            shard.lane(k).sync()  # the lanes hold speculated frames: wait for them, then lane 0 renders alone
+        base_iter = 1 + (frame[0] + 4 * KC) * world
+        prof = [lane0.profile_kernels(base_iter + i) for i in range(5)]
+        prof = {k: statistics.median(p[k] for p in prof) for k in prof[0]}
+        walks = lane0.walk_counts() if has_mesh else np.zeros(args.depth, np.int32)
+        long_walks = lane0.walk_counts(long_walks=True) if has_mesh else np.zeros(args.depth, np.int32)
+        extras.update(prof=prof, walks=walks, long_walks=long_walks)
+    barrier()
+    fr.close()
 
     if rank == 0:
+        if not args.no_extras and world == 1:
+            extras.update(single_process_legs(args, scene, opt, P, K, W, KC, img_np, alb_np))
         peak, peak_src = hbm_peak()
-        n_walks = int(walks[: args.depth].sum())
-        n_long = int(long_walks[: args.depth].sum())
-        # algorithmic bytes per launch unit (DESIGN.md, kernel table)
-        kern = {
-            # ray read 24 B (32 as stored), hit record 32 B, key 1 B, survival flag 1 B
-            "k_intersect_analytic": ("analytic", 58.0 * segments),
-            # per queued ray: queue slot 4 B, ray 24 B, closest analytic t 4 B + geom 4 B read; (t, bary, ids) 20 B + key 1 B written
-            "k_mesh_walk": ("walk", 57.0 * n_walks),
-            "k_mesh_walk_long": ("walk_long", 57.0 * n_long),
-            # per queued ray: queue slot 4 B + partial record 20 B read, record 32 B + flag 1 B written
-            "k_mesh_finish": ("finish", 57.0 * n_walks),
-            "k_sort_material": ("sort", 10.0 * segments),      # key 1 B + flag 1 B read, permutation 4 B + compaction rank 4 B written
-            "k_shade_compact": ("shade", 132.0 * segments),    # permutation 4 B + hit 32 B + state 48 B read, state 48 B written
-        }
-        dom = max(kern, key=lambda k: prof[kern[k][0]])
-        dom_ms = prof[kern[dom][0]]
-        dom_bytes = kern[dom][1]
-        dom_gbs = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
-        # every kernel of the iteration against the HBM roofline: algorithmic bytes (DESIGN.md, kernel table) over
-        # its device time in one iteration of a context running alone with the shared-SM grids of the timed region
-        kern_all = dict(kern)
-        kern_all["k_generate"] = ("generate", 44.0 * P)
-        roofline_kernels = {}
-        for name, (key, nbytes) in kern_all.items():
-            kms = prof.get(key, 0.0)
-            gbs = nbytes / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
-            roofline_kernels[name] = {"ms_per_step": kms, "algorithmic_bytes_per_step": nbytes, "achieved": gbs,
-                                      "unit": "GB/s", "frac": gbs / peak}
-        iter_bytes = 84.0 * P + 280.0 * segments
-        iter_gbs = iter_bytes / (ms_max / K * 1e-3) / 1e9
         line = {
-            "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(args, n_tris, textures),
-            "e2e": {"value": pipe_value, "unit": METRIC, "h2d_bytes_per_step": 8, "d2h_bytes_per_step": P * 12,
-                    "d2h_note": "running sum every step; the albedo AOV (P*12 more) only when it changed (iteration 1)",
-                    "call": "b2pt_pipe_pathtrace(pipe, iter, host_image, host_albedo) -- pathtrace() of apps/src/pathtrace.h:9, "
-                            "one iteration per call, host image after every call",
-                    "ms_per_step": float(tp.item()) / K, "lanes": KC, "mispredicted_calls": int(pipe_misses),
-                    "note": "steady state of the pipeline: the lanes hold the next %d iterations when the timed region "
-                            "starts and when it ends; K iterations are rendered and K consumed inside it.  The copy to the host "
-                            "and the merge overlap the other lanes' kernels, so this leg is bound by the same %d-context GPU "
-                            "throughput as `value` (e2e_single_context is the unoverlapped form)" % (KC, KC)},
-            "e2e_single_context": {"value": e2e_value, "unit": METRIC, "ms_per_step": float(t.item()) / K,
-                                   "call": "b2pt_pathtrace(ctx, iter, host_image, host_albedo): render, then copy, nothing overlapped"},
-            "gpu_launches": int(launches), "streams_per_gpu": KC,
+            "metric": METRIC, "value": value, "unit": METRIC, "n_gpus": world, "steps": K, "warmup": max(W, KC),
+            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args, n_tris, textures, world),
+            "windows_ms": {"device": dev_windows, "e2e": e2e_windows, "reps": R,
+                           "note": "each window is exactly `steps` frames, timed back to back; value / e2e use the median"},
+            "e2e": {"value": e2e_value, "unit": METRIC, "h2d_bytes_per_step": 8 * world, "d2h_bytes_per_step": P * 12,
+                    "ms_per_step": e2e_ms / K,
+                    "call": "distributed.FrameRenderer.pathtrace(first_iter, host_image, host_albedo) = b2pt_shard_frame_begin / "
+                            "_reduce / _end: N reference pathtrace() calls (apps/src/pathtrace.h:9) per step, one per rank; "
+                            "rank 0 has the running sum in pinned host memory after EVERY step",
+                    "albedo": "persistent_host_albedo=1: the albedo AOV (P*12 bytes more) is copied when it changed (iteration 1), "
+                              "not every step; e2e_albedo_every_call is the reference's literal 2 x P*12 per call",
+                    "lanes": KC, "mispredicted_calls": int(misses)},
+            "gpu_launches": int(e2e_launches), "gpu_launches_device_leg": int(dev_launches), "lanes_per_gpu": KC,
             "clocks": clocks,
-            "roofline": {"kernel": dom, "bound": "hbm", "achieved": dom_gbs, "peak": peak, "unit": "GB/s",
-                         "frac": dom_gbs / peak, "traffic": TRAFFIC.get(dom), "peak_source": peak_src,
-                         "traffic_note": "dram__bytes_read+write of the depth-1 launch under ncu --set full (cold caches); it "
-                                         "includes the scene traffic (BVH nodes, triangles, texels) that the algorithmic "
-                                         "bytes leave out (SURVEY.md 8d)",
-                         "algorithmic_bytes_per_launch": dom_bytes / args.depth, "launches_per_step": args.depth,
-                         "ms_per_launch": dom_ms / args.depth, "walks_per_step": n_walks, "long_walks_per_step": n_long,
-                         "note": "dominant kernel by device time measured with CUDA events in this run; achieved = algorithmic "
-                                 "bytes per launch / average launch duration.  The BVH walk is issue/latency bound, not HBM "
-                                 "bound: see profiles/ for issue-slot, FP32-pipe and divergence counters"},
-            "roofline_iter": {"bytes_per_step": iter_bytes, "achieved": iter_gbs, "peak": peak, "unit": "GB/s",
-                              "frac": iter_gbs / peak, "formula": "84*P + 280*S"},
-            "roofline_kernels": roofline_kernels,
-            "kernel_ms_per_step": prof,
-            "kernel_ms_per_step_full_width": prof_full,
-            "kernel_ms_note": "CUDA events around every launch of one iteration run alone: with the grids of the timed "
-                              "region (contexts share the SMs) and with the full-width grids of the e2e context, where "
-                              "the analytic intersection is fused into generate / shade (k_generate_trace, k_shade_trace)",
-            "segments_per_step": segments, "live_paths_per_depth": [int(x) for x in live[: args.depth + 1]],
-            "bvh": {"triangles": int(bvh.n_faces), "nodes": int(bvh.n_nodes), "max_depth": int(bvh.max_depth),
-                    "build_ms": float(bvh.build_ms), "build_ms_note": "device time, fastest build of this process (the first one also pays CUDA's lazy kernel loading)"},
+            "segments_per_step": segments * world, "segments_per_iteration": segments,
+            "live_paths_per_depth": [int(x) for x in live[: args.depth + 1]],
             "scene_load_s": round(load_s, 2), "image_checksum": checksum,
         }
+        iter_bytes = 84.0 * P + 280.0 * segments
+        iter_gbs = iter_bytes * world / (dev_ms / K * 1e-3) / 1e9
+        line["roofline_iter"] = {"bytes_per_step": iter_bytes * world, "achieved": iter_gbs, "peak": peak * world, "unit": "GB/s",
+                                 "frac": iter_gbs / (peak * world), "formula": "N * (84*P + 280*S)"}
+        if bvh is not None:
+            line["bvh"] = {"triangles": int(bvh.n_faces), "nodes": int(bvh.n_nodes), "max_depth": int(bvh.max_depth),
+                           "build_ms": float(bvh.build_ms)}
+        if "prof" in extras:
+            prof = extras["prof"]
+            n_walks = int(extras["walks"][: args.depth].sum())
+            n_long = int(extras["long_walks"][: args.depth].sum())
+            # algorithmic bytes per launch unit (DESIGN.md, kernel table)
+            kern = {
+                "k_intersect_analytic": ("analytic", 58.0 * segments),   # ray 24 B, hit record 32 B, key 1 B, flag 1 B
+                "k_mesh_walk": ("walk", 57.0 * n_walks),                 # queue 4, ray 24, analytic hit 8, (t, bary, ids) 20 + key 1
+                "k_mesh_walk_long": ("walk_long", 57.0 * n_long),
+                "k_mesh_finish": ("finish", 57.0 * n_walks),             # queue 4 + partial record 20 read, record 32 + flag 1 written
+                "k_sort_material": ("sort", 10.0 * segments),            # key 1 + flag 1 read, permutation 4 + rank 4 written
+                "k_shade_compact": ("shade", 132.0 * segments),          # permutation 4 + hit 32 + state 48 read, state 48 written
+                "k_generate": ("generate", 44.0 * P),
+            }
+            roofline_kernels = {}
+            for name, (key, nbytes) in kern.items():
+                kms = prof.get(key, 0.0)
+                gbs = nbytes / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
+                roofline_kernels[name] = {"ms_per_step": kms, "algorithmic_bytes_per_step": nbytes, "achieved": gbs,
+                                          "unit": "GB/s", "frac": gbs / peak}
+            dom = max((k for k in kern if k != "k_generate"), key=lambda k: prof.get(kern[k][0], 0.0))
+            dom_ms, dom_bytes = prof[kern[dom][0]], kern[dom][1]
+            dom_gbs = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+            line["roofline"] = {
+                "kernel": dom, "bound": "hbm", "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak,
+                "traffic": TRAFFIC.get(dom), "traffic_source": TRAFFIC_SOURCE, "peak_source": peak_src,
+                "regime": "a lane context of the timed region (grids sized to a share of the SMs, unfused kernels) rendering one "
+                          "iteration ALONE, CUDA events around every launch: the regime ncu's serialised launch list of this "
+                          "command measures",
+                "algorithmic_bytes_per_launch": dom_bytes / args.depth, "launches_per_step": args.depth,
+                "ms_per_launch": dom_ms / args.depth, "walks_per_step": n_walks, "long_walks_per_step": n_long,
+                "note": "achieved = algorithmic bytes per launch / average launch duration.  The BVH walk is issue / latency "
+                        "bound, not HBM bound: see profiles/ for issue-slot, FP32-pipe and divergence counters"}
+            line["roofline_kernels"] = roofline_kernels
+            line["kernel_ms_per_step"] = prof
+        for k in ("kernel_ms_per_step_full_width", "e2e_single_context", "e2e_albedo_every_call", "e2e_single_process_multi"):
+            if k in extras:
+                line[k] = extras[k]
         if world == 1 and not args.no_cpu:
             ra = reference_host_adapter(root, args, max(20, min(K, 200)))
             if ra is not None:
                 line["e2e_reference_host"] = ra
-            line["cpu_baseline"] = {k: v for k, v in cpu_sample(root, args, 1).items()}
+            line["cpu_baseline"] = cpu_sample(root, args, 1)
+            if args.config != 1:
+                # BASELINE.md B-CPU: the reference's CPU-runnable case, in full
+                line["cpu_baseline_config1"] = cpu_sample(root, args, 1, (800, 800), scene="cornell", depth=8)
             rg = reference_gpu(root, args)
             if rg is not None:
                 line["reference_gpu"] = rg
         emit(line)
-    for x in rs + [r_e2e]:
-        x.close()
     if dist:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def single_process_legs(args, scene, opt, P, K, W, KC, img_np, alb_np):
+    """N = 1 only, after the shard is gone: the full-width single context (kernel split and the unoverlapped
+    b2pt_pathtrace call) and the pipelined call with the albedo AOV copied on every call."""
+    import torch
+
+    from mygpuraytracer_b200 import abi, api
+
+    out = {}
+    opt1 = abi.default_options(device=opt.device, persistent_host_albedo=1, **CONFIGS[args.config]["options"])
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stream = torch.cuda.Stream()
+    with api.Renderer(scene, opt1) as r:
+        r.set_stream_ptr(stream.cuda_stream)
+        for i in range(3):
+            r.pathtrace(1 + i, img_np, alb_np)
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for i in range(K):
+            r.pathtrace(4 + i, img_np, alb_np)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        out["e2e_single_context"] = {"value": K * P / (ms * 1e-3) / 1e6, "unit": METRIC, "ms_per_step": ms / K,
+                                     "call": "b2pt_pathtrace(ctx, iter, host_image, host_albedo): render, then copy, nothing overlapped"}
+        prof = [r.profile_kernels(10 + K + i) for i in range(5)]
+        out["kernel_ms_per_step_full_width"] = {k: statistics.median(p[k] for p in prof) for k in prof[0]}
+    opt2 = abi.default_options(device=opt.device, persistent_host_albedo=0, **CONFIGS[args.config]["options"])
+    with api.Pipeline(scene, opt2, lanes=KC) as pipe:
+        for i in range(max(W, KC)):
+            pipe.pathtrace(1 + i, img_np, alb_np)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(K):
+            pipe.pathtrace(1 + max(W, KC) + i, img_np, alb_np)
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3
+        out["e2e_albedo_every_call"] = {"value": K * P / (ms * 1e-3) / 1e6, "unit": METRIC, "ms_per_step": ms / K,
+                                        "d2h_bytes_per_step": P * 24,
+                                        "call": "b2pt_pipe_pathtrace with persistent_host_albedo=0: image AND albedo to the host "
+                                                "on every call, the literal apps/src/pathtrace.cu:662-668 (host wall clock)"}
+    return out
+
+
+def converge(args, fr, shard, stream, dist, rank, world, P, img_np, alb_np, n_tris, textures, barrier):
+    """--spp S: render iterations 1 .. S (S rounded up to whole frames) through the e2e path from a zeroed accumulator,
+    rank 0 reading the running sum after every frame, and optionally save the final image."""
+    import numpy as np
+    import torch
+
+    n_frames = (args.spp + world - 1) // world
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for f in range(n_frames):
+        fr.pathtrace(1 + f * world, img_np, alb_np)
+    e1.record(stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if dist:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    spp = n_frames * world
+    if rank == 0:
+        if args.save_image:
+            np.save(args.save_image, img_np / np.float32(spp))
+        emit({"metric": METRIC, "mode": "converge", "value": spp * P / (ms * 1e-3) / 1e6, "unit": METRIC, "n_gpus": world,
+              "spp": spp, "frames": n_frames, "ms_per_frame": ms / n_frames, "ms_per_iteration": ms / spp, "seconds": ms * 1e-3,
+              "wall_s": round(wall, 3), "higher_is_better": True, "scaling": "strong", "dtype": "f32", "data": "synthetic",
+              "config": workload_config(args, n_tris, textures, world),
+              "e2e": {"value": spp * P / (ms * 1e-3) / 1e6, "unit": METRIC, "h2d_bytes_per_step": 8 * world, "d2h_bytes_per_step": P * 12},
+              "image_checksum": float(np.float64(img_np.sum())), "image_file": args.save_image or None,
+              "note": "the whole render from a zeroed accumulator, rank 0 has the running sum on the host after every frame"})
 
 
 def main():
@@ -595,17 +665,28 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--reps", type=int, default=5, help="back-to-back timed windows of `steps` frames; the median is reported")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--width", type=int, default=WIDTH)
-    ap.add_argument("--height", type=int, default=HEIGHT)
-    ap.add_argument("--depth", type=int, default=DEPTH)
+    ap.add_argument("--config", type=int, default=4, choices=sorted(CONFIGS), help="BASELINE.json configuration (1-based)")
+    ap.add_argument("--width", type=int, default=0)
+    ap.add_argument("--height", type=int, default=0)
+    ap.add_argument("--depth", type=int, default=0)
     ap.add_argument("--triangles", type=int, default=250_000)
-    ap.add_argument("--streams", type=int, default=4, help="concurrent iteration streams (contexts) per GPU")
+    ap.add_argument("--streams", type=int, default=4, help="lanes (contexts rendering ahead) per GPU")
+    ap.add_argument("--reduce", default="p2p", choices=["p2p", "nccl"],
+                    help="how a frame is combined across ranks: k_frame_reduce over NVLink peer memory, or one NCCL reduce")
+    ap.add_argument("--spp", type=int, default=0, help="render this many samples per pixel from scratch instead of timing windows")
+    ap.add_argument("--save-image", default="", help="with --spp: write image / spp (float32 .npy) here")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / reference_gpu legs")
-    ap.add_argument("--private-scenes", action="store_true", help="every context uploads its own copy of the scene (A/B of b2pt_create_shared)")
-    ap.add_argument("--ref-gpu-iters", type=int, default=1)
-    ap.add_argument("--ref-gpu-timeout", type=int, default=240)
+    ap.add_argument("--no-extras", action="store_true", help="skip the per-kernel profile and the single-process legs")
+    ap.add_argument("--ref-gpu-iters", type=int, default=3)
+    ap.add_argument("--ref-gpu-timeout", type=int, default=300)
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    args.scene = cfg["scene"]
+    args.width = args.width or cfg["width"]
+    args.height = args.height or cfg["height"]
+    args.depth = args.depth or cfg["depth"]
     capture_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

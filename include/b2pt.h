@@ -288,6 +288,86 @@ int64_t b2pt_pipe_misses(B2ptPipe* pipe);
  * b2pt_pipe_pathtrace call consumed. */
 float b2pt_pipe_last_loop_ms(B2ptPipe* pipe);
 
+/* ---- pathtrace() over several GPUs ----------------------------------------------
+ * Iterations are independent (the only state they share is the additive
+ * accumulator, apps/src/pathtrace.cu:508), so G GPUs render G consecutive
+ * iterations at once.  One FRAME = iterations first .. first+G-1, member g renders
+ * first+g into its own zeroed image; `lanes` contexts per GPU render the next
+ * frames ahead (as a B2ptPipe does on one GPU).  A frame is combined by ONE kernel
+ * per member over NVLink peer memory (csrc/multi.cu, k_frame_reduce): member g
+ * owns pixel slice g of the running sum, reads slice g of every member's image,
+ * adds them IN ITERATION ORDER, clears what it consumed and forwards the new sum
+ * into member 0's whole image.  The additions are the reference's sequential
+ * image[pixel] += color*PI, so the result is bit-identical to one GPU rendering
+ * the same iterations one after the other.
+ */
+#define B2PT_MAX_MEMBERS 16
+
+/* (a) One process, several GPUs (the reference's host is one process,
+ * apps/src/main.cpp).  `devices` = n_devices CUDA ordinals (NULL: 0..n-1; an
+ * ordinal may repeat: those members share the device).  The devices must have
+ * peer access to each other (NVLink / NVSwitch).  This is pathtraceInit. */
+typedef struct B2ptMulti B2ptMulti;
+int b2pt_multi_create(const B2ptScene* scene, const B2ptOptions* opt, int32_t n_devices, const int32_t* devices,
+                      int32_t lanes, B2ptMulti** out);
+void b2pt_multi_destroy(B2ptMulti* multi); /* pathtraceFree; NULL is accepted */
+/* G reference pathtrace() calls at once: renders iterations first_iter ..
+ * first_iter+G-1 (consecutive frames are predicted and rendered ahead) and
+ * returns the running sum including all of them in image_host, the iteration-1
+ * albedo AOV in albedo_host (either may be NULL).  Every member copies its own
+ * slice of the image over its own PCIe link. */
+int b2pt_multi_pathtrace(B2ptMulti* multi, int32_t first_iter, float* image_host, float* albedo_host);
+int b2pt_multi_reset(B2ptMulti* multi, const B2ptCamera* cam);
+int32_t b2pt_multi_members(B2ptMulti* multi);
+float* b2pt_multi_device_image(B2ptMulti* multi); /* the running sum on member 0's device */
+int64_t b2pt_multi_launch_count(B2ptMulti* multi);
+
+/* (b) One process per GPU (torch.distributed, MPI): a B2ptShard per rank.  Device
+ * pointers are exchanged once as CUDA IPC handles: every rank exports a blob of
+ * b2pt_shard_export_size() bytes, the host all-gathers the blobs (rank order) and
+ * hands them to b2pt_shard_connect.  A frame is three calls made by EVERY rank in
+ * the same order, with a cross-rank barrier queued by the host on
+ * b2pt_shard_stream() between them (NCCL: a 4-byte all-reduce on that stream):
+ *
+ *     b2pt_shard_frame_begin(s, first_iter);   my contribution of the frame is complete
+ *     <barrier on b2pt_shard_stream(s)>        ... and so is everybody else's
+ *     b2pt_shard_frame_reduce(s);              k_frame_reduce on my slice
+ *     <barrier on b2pt_shard_stream(s)>        every slice consumed, member 0's image complete
+ *     b2pt_shard_frame_end(s, image_host, albedo_host);
+ *
+ * frame_end copies the running sum / the albedo AOV to host memory on rank 0 (the
+ * pointers are ignored elsewhere; NULL = keep it on the device) and re-arms the
+ * lane.  A rank that is given host pointers waits for the copy; the others return
+ * at once and are throttled by frame_begin (at most `lanes` frames ahead).
+ *
+ * The plain alternative to begin/barrier/reduce/barrier, for hosts that prefer a
+ * library collective: after frame_begin, reduce b2pt_shard_frame_image(s) (W*H*3
+ * floats, sum, to rank 0, in place) on b2pt_shard_stream(s) -- e.g. ncclReduce --
+ * then call b2pt_shard_frame_merge(s) and frame_end.  The image then agrees with
+ * the single-GPU one to float summation order instead of bit for bit. */
+typedef struct B2ptShard B2ptShard;
+int b2pt_shard_create(const B2ptScene* scene, const B2ptOptions* opt, int32_t rank, int32_t world, int32_t lanes,
+                      B2ptShard** out);
+void b2pt_shard_destroy(B2ptShard* shard);
+int64_t b2pt_shard_export_size(B2ptShard* shard);
+int b2pt_shard_export(B2ptShard* shard, void* blob, int64_t bytes);
+int b2pt_shard_connect(B2ptShard* shard, const void* blobs_in_rank_order, int64_t bytes_per_member);
+int b2pt_shard_frame_begin(B2ptShard* shard, int32_t first_iter);
+void* b2pt_shard_stream(B2ptShard* shard); /* cudaStream_t of the frame protocol */
+int b2pt_shard_frame_reduce(B2ptShard* shard);
+float* b2pt_shard_frame_image(B2ptShard* shard);
+int b2pt_shard_frame_merge(B2ptShard* shard);
+int b2pt_shard_frame_end(B2ptShard* shard, float* image_host, float* albedo_host);
+int b2pt_shard_reset(B2ptShard* shard, const B2ptCamera* cam);
+int b2pt_shard_sync(B2ptShard* shard);
+float* b2pt_shard_device_image(B2ptShard* shard); /* rank 0: the running sum; NULL elsewhere */
+float* b2pt_shard_device_slice(B2ptShard* shard, int64_t* offset_floats, int64_t* len_floats);
+int32_t b2pt_shard_lanes(B2ptShard* shard);
+B2ptCtx* b2pt_shard_lane(B2ptShard* shard, int32_t k);
+B2ptShard* b2pt_multi_member(B2ptMulti* multi, int32_t g);
+int64_t b2pt_shard_launch_count(B2ptShard* shard);
+int64_t b2pt_shard_misses(B2ptShard* shard);
+
 /* Device pointers of the accumulators (W*H*3 floats), for zero-copy hand-off
  * to a collective or a device-side denoiser. */
 float* b2pt_device_image(B2ptCtx* ctx);

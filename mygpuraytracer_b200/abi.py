@@ -202,6 +202,33 @@ SYMBOLS = {
     "b2pt_pipe_launch_count": (_i64, [_vp]),
     "b2pt_pipe_misses": (_i64, [_vp]),
     "b2pt_pipe_last_loop_ms": (C.c_float, [_vp]),
+    "b2pt_multi_create": (C.c_int, [C.POINTER(Scene), C.POINTER(Options), _i32, _i32p, _i32, C.POINTER(_vp)]),
+    "b2pt_multi_destroy": (None, [_vp]),
+    "b2pt_multi_pathtrace": (C.c_int, [_vp, _i32, _vp, _vp]),
+    "b2pt_multi_reset": (C.c_int, [_vp, C.POINTER(Camera)]),
+    "b2pt_multi_members": (_i32, [_vp]),
+    "b2pt_multi_member": (_vp, [_vp, _i32]),
+    "b2pt_multi_device_image": (_vp, [_vp]),
+    "b2pt_multi_launch_count": (_i64, [_vp]),
+    "b2pt_shard_create": (C.c_int, [C.POINTER(Scene), C.POINTER(Options), _i32, _i32, _i32, C.POINTER(_vp)]),
+    "b2pt_shard_destroy": (None, [_vp]),
+    "b2pt_shard_export_size": (_i64, [_vp]),
+    "b2pt_shard_export": (C.c_int, [_vp, _vp, _i64]),
+    "b2pt_shard_connect": (C.c_int, [_vp, _vp, _i64]),
+    "b2pt_shard_frame_begin": (C.c_int, [_vp, _i32]),
+    "b2pt_shard_stream": (_vp, [_vp]),
+    "b2pt_shard_frame_reduce": (C.c_int, [_vp]),
+    "b2pt_shard_frame_image": (_vp, [_vp]),
+    "b2pt_shard_frame_merge": (C.c_int, [_vp]),
+    "b2pt_shard_frame_end": (C.c_int, [_vp, _vp, _vp]),
+    "b2pt_shard_reset": (C.c_int, [_vp, C.POINTER(Camera)]),
+    "b2pt_shard_sync": (C.c_int, [_vp]),
+    "b2pt_shard_device_image": (_vp, [_vp]),
+    "b2pt_shard_device_slice": (_vp, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
+    "b2pt_shard_lanes": (_i32, [_vp]),
+    "b2pt_shard_lane": (_vp, [_vp, _i32]),
+    "b2pt_shard_launch_count": (_i64, [_vp]),
+    "b2pt_shard_misses": (_i64, [_vp]),
     "b2pt_device_image": (_vp, [_vp]),
     "b2pt_device_albedo": (_vp, [_vp]),
     "b2pt_set_device_image": (C.c_int, [_vp, _vp]),

@@ -149,10 +149,25 @@ class Renderer:
             _check(self.lib.b2pt_create(C.byref(self._cscene), C.byref(self.options), C.byref(self._h)))
         self.n_pixels = self.pod.n_pixels
 
+    @classmethod
+    def view(cls, handle, pod: PodScene) -> "Renderer":
+        """A non-owning Renderer over an existing ``B2ptCtx*`` (a lane of a Pipeline / Shard): statistics and
+        per-kernel profiling of the contexts that really render.  ``close()`` does not destroy the context."""
+        self = cls.__new__(cls)
+        self.lib = load_library()
+        self.pod = pod
+        self.options = None
+        self._cscene = None
+        self._h = C.c_void_p(handle if isinstance(handle, int) else C.cast(handle, C.c_void_p).value)
+        self._borrowed = True
+        self.n_pixels = pod.n_pixels
+        return self
+
     # -- lifetime ------------------------------------------------------------------------
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h.value:
-            self.lib.b2pt_destroy(self._h)
+            if not getattr(self, "_borrowed", False):
+                self.lib.b2pt_destroy(self._h)
             self._h = C.c_void_p()
 
     def __enter__(self):
@@ -365,6 +380,156 @@ class Pipeline:
         """``sendImageToPBO`` of the running sum (or of ``src_ptr``); returns when ``dst_ptr`` is written."""
         _check(self.lib.b2pt_pipe_tonemap_rgba8(self._h, C.c_void_p(src_ptr) if src_ptr else None, iteration,
                                                 C.c_void_p(dst_ptr)))
+
+
+# ---------------------------------------------------------------------------------------
+# several GPUs (csrc/multi.cu): one frame = one iteration per GPU, combined on the device
+# ---------------------------------------------------------------------------------------
+class MultiRenderer:
+    """One process, several GPUs (``b2pt_multi_*``): ``pathtrace(first)`` renders iterations ``first ..
+    first + G - 1`` at once, one per GPU, and returns the running sum including all of them -- bit-identical to
+    one GPU rendering them one after the other.  ``devices`` may name a device twice (members share it)."""
+
+    def __init__(self, scene, options: Optional[abi.Options] = None, devices=None, lanes: int = 4, **opt_kw):
+        self.lib = load_library()
+        self.pod: PodScene = scene.pod if isinstance(scene, Scene) else scene
+        self.options = options if options is not None else abi.default_options(**opt_kw)
+        self._cscene = self.pod.as_ctypes()
+        self._h = C.c_void_p()
+        if devices is None:
+            devices = list(range(device_count()))
+        arr = (C.c_int32 * len(devices))(*devices)
+        _check(self.lib.b2pt_multi_create(C.byref(self._cscene), C.byref(self.options), len(devices), arr, lanes,
+                                          C.byref(self._h)))
+        self.members = len(devices)
+        self.n_pixels = self.pod.n_pixels
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.b2pt_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # pragma: no cover
+            pass
+
+    def pathtrace(self, first_iteration: int, image: Optional[np.ndarray], albedo: Optional[np.ndarray] = None) -> None:
+        _check(self.lib.b2pt_multi_pathtrace(self._h, first_iteration, image.ctypes.data if image is not None else None,
+                                             albedo.ctypes.data if albedo is not None else None))
+
+    def reset(self, camera: Optional[np.ndarray] = None) -> None:
+        if camera is None:
+            _check(self.lib.b2pt_multi_reset(self._h, None))
+            return
+        cam = abi.Camera()
+        C.memmove(C.byref(cam), np.ascontiguousarray(camera).ctypes.data, C.sizeof(abi.Camera))
+        _check(self.lib.b2pt_multi_reset(self._h, C.byref(cam)))
+
+    def device_image_ptr(self) -> int:
+        return int(self.lib.b2pt_multi_device_image(self._h) or 0)
+
+    def launch_count(self) -> int:
+        return int(self.lib.b2pt_multi_launch_count(self._h))
+
+
+class Shard:
+    """One rank of a one-process-per-GPU job (``b2pt_shard_*``).  The cross-rank plumbing (exchange of the
+    export blobs, the two barriers of a frame) belongs to the host: see :mod:`mygpuraytracer_b200.distributed`
+    for the ``torch.distributed`` form."""
+
+    def __init__(self, scene, options: Optional[abi.Options] = None, rank: int = 0, world: int = 1, lanes: int = 4, **opt_kw):
+        self.lib = load_library()
+        self.pod: PodScene = scene.pod if isinstance(scene, Scene) else scene
+        self.options = options if options is not None else abi.default_options(**opt_kw)
+        self._cscene = self.pod.as_ctypes()
+        self._h = C.c_void_p()
+        _check(self.lib.b2pt_shard_create(C.byref(self._cscene), C.byref(self.options), rank, world, lanes, C.byref(self._h)))
+        self.rank, self.world, self.lanes = rank, world, lanes
+        self.n_pixels = self.pod.n_pixels
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.b2pt_shard_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # pragma: no cover
+            pass
+
+    def export(self) -> bytes:
+        n = int(self.lib.b2pt_shard_export_size(self._h))
+        buf = C.create_string_buffer(n)
+        _check(self.lib.b2pt_shard_export(self._h, buf, n))
+        return buf.raw
+
+    def connect(self, blobs) -> None:
+        """``blobs``: the export blobs of all ranks in rank order (own entry included)."""
+        per = len(blobs[0])
+        if any(len(b) != per for b in blobs) or len(blobs) != self.world:
+            raise ValueError("one export blob per rank, all of the same size")
+        _check(self.lib.b2pt_shard_connect(self._h, b"".join(blobs), per))
+
+    def stream_ptr(self) -> int:
+        return int(self.lib.b2pt_shard_stream(self._h) or 0)
+
+    def frame_begin(self, first_iteration: int) -> None:
+        _check(self.lib.b2pt_shard_frame_begin(self._h, first_iteration))
+
+    def frame_reduce(self) -> None:
+        _check(self.lib.b2pt_shard_frame_reduce(self._h))
+
+    def frame_image_ptr(self) -> int:
+        return int(self.lib.b2pt_shard_frame_image(self._h) or 0)
+
+    def frame_merge(self) -> None:
+        _check(self.lib.b2pt_shard_frame_merge(self._h))
+
+    def frame_end(self, image: Optional[np.ndarray] = None, albedo: Optional[np.ndarray] = None) -> None:
+        _check(self.lib.b2pt_shard_frame_end(self._h, image.ctypes.data if image is not None else None,
+                                             albedo.ctypes.data if albedo is not None else None))
+
+    def reset(self, camera: Optional[np.ndarray] = None) -> None:
+        if camera is None:
+            _check(self.lib.b2pt_shard_reset(self._h, None))
+            return
+        cam = abi.Camera()
+        C.memmove(C.byref(cam), np.ascontiguousarray(camera).ctypes.data, C.sizeof(abi.Camera))
+        _check(self.lib.b2pt_shard_reset(self._h, C.byref(cam)))
+
+    def sync(self) -> None:
+        _check(self.lib.b2pt_shard_sync(self._h))
+
+    def device_image_ptr(self) -> int:
+        return int(self.lib.b2pt_shard_device_image(self._h) or 0)
+
+    def launch_count(self) -> int:
+        return int(self.lib.b2pt_shard_launch_count(self._h))
+
+    def misses(self) -> int:
+        return int(self.lib.b2pt_shard_misses(self._h))
+
+    def lane(self, k: int) -> "Renderer":
+        """Lane k's context as a non-owning :class:`Renderer` (statistics, profiling)."""
+        h = self.lib.b2pt_shard_lane(self._h, k)
+        if not h:
+            raise B2ptError(-6, "no such lane")
+        return Renderer.view(h, self.pod)
 
 
 # ---------------------------------------------------------------------------------------

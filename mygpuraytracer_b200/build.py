@@ -30,7 +30,7 @@ NVCC_FLAGS = [
 
 
 def sources():
-    return [os.path.join(CSRC, "b2pt.cu"), os.path.join(CSRC, "pipe.cu"), os.path.join(CSRC, "host", "scene_loader.cpp")]
+    return [os.path.join(CSRC, "b2pt.cu"), os.path.join(CSRC, "pipe.cu"), os.path.join(CSRC, "multi.cu"), os.path.join(CSRC, "host", "scene_loader.cpp")]
 
 
 def _deps():

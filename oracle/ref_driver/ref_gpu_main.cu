@@ -19,6 +19,7 @@
 #endif
 #include REF_PATHTRACE_CU
 
+#include <algorithm>
 #include <chrono>
 #include <string>
 #include <vector>
@@ -140,17 +141,27 @@ int main(int argc, char** argv) {
     pathtraceFree();
     pathtraceInit(scene);
     double loop_ms = 0.0;
+    std::vector<double> each;  // wall time of every call (pathtrace() ends with a device sync, pathtrace.cu:670)
     cudaDeviceSynchronize();
     auto t0 = std::chrono::steady_clock::now();
     for (int i = 0; i < iters; ++i) {
+      auto c0 = std::chrono::steady_clock::now();
       pathtrace(NULL, 0, iter_first + i);
+      cudaDeviceSynchronize();
+      each.push_back(1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - c0).count());
       loop_ms += timer().getGpuElapsedTimeForPreviousOperation();
     }
     cudaDeviceSynchronize();
     double call_ms = 1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    printf("REF_GPU_RESULT {\"iters\": %d, \"loop_ms_per_iter\": %.4f, \"call_ms_per_iter\": %.4f, "
+    std::vector<double> sorted = each;
+    std::sort(sorted.begin(), sorted.end());
+    const double med = sorted.empty() ? 0.0 : (sorted.size() & 1 ? sorted[sorted.size() / 2]
+                                                                : 0.5 * (sorted[sorted.size() / 2 - 1] + sorted[sorted.size() / 2]));
+    printf("REF_GPU_RESULT {\"iters\": %d, \"warmup\": %d, \"loop_ms_per_iter\": %.4f, \"call_ms_per_iter\": %.4f, "
+           "\"call_ms_min\": %.4f, \"call_ms_median\": %.4f, \"call_ms_max\": %.4f, "
            "\"mpaths_per_s_loop\": %.4f, \"mpaths_per_s_call\": %.4f, \"width\": %d, \"height\": %d, \"depth\": %d}\n",
-           iters, loop_ms / iters, call_ms / iters, (double)P * iters / (loop_ms * 1e-3) / 1e6,
+           iters, warmup, loop_ms / iters, call_ms / iters, sorted.empty() ? 0.0 : sorted.front(), med,
+           sorted.empty() ? 0.0 : sorted.back(), (double)P * iters / (loop_ms * 1e-3) / 1e6,
            (double)P * iters / (call_ms * 1e-3) / 1e6, scene->state.camera.resolution.x,
            scene->state.camera.resolution.y, D);
   } else {
