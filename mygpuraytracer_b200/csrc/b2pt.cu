@@ -101,6 +101,8 @@ extern "C" void b2pt_default_options(B2ptOptions* o) {
 struct MeshBuild {
   float4* nodes = nullptr;
   float4* tris = nullptr;
+  int root = 0;        // DevMesh::root
+  int wide_depth = 0;  // inner wide nodes on the longest root-to-leaf path
   float* face_pos = nullptr;
   float* face_uv = nullptr;
   size_t bvh_bytes = 0;
@@ -185,7 +187,7 @@ struct B2ptCtx {
   int long_cap = 0, long_carry = kLongCarry;
   int shade_stride_grid = 0, gen_trace_grid = 0;
   int isect_grid = 0, analytic_grid = 0, sort_grid = 0, shade_grid = 0, gen_grid = 0;
-  int* mesh_queue = nullptr;
+  float4* mesh_queue = nullptr;  // [3][P]: the rays that walk a mesh, see IsectParams::queue
   cudaEvent_t ev_loop_a = nullptr, ev_loop_b = nullptr;
   bool loop_timed = false;
   cudaGraph_t graph = nullptr;
@@ -370,14 +372,7 @@ static int build_mesh(B2ptCtx* c, const float* pos_host, const float* uv_host, i
   if ((rc = c->dalloc(&out->face_uv, (size_t)n * 6))) return rc;
   CK(cudaMemcpyAsync(out->face_pos, pos_host, (size_t)n * 36, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(out->face_uv, uv_host, (size_t)n * 24, cudaMemcpyHostToDevice, s));
-  // nodes and triangles share one allocation so that a single L2 access-policy
-  // window can keep the whole acceleration structure resident
-  const size_t node_f4 = (size_t)std::max(n - 1, 1) * 8, tri_f4 = (size_t)n * 3;
-  if ((rc = c->dalloc(&out->nodes, node_f4 + tri_f4))) return rc;
-  out->tris = out->nodes + node_f4;
-  out->bvh_bytes = (node_f4 + tri_f4) * sizeof(float4);
   out->info.n_faces = n;
-  out->info.n_nodes = std::max(n - 1, 0);
 
   // pad: a few 1e-6 of the mesh extent (host pass over the positions)
   float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
@@ -396,17 +391,28 @@ static int build_mesh(B2ptCtx* c, const float* pos_host, const float* uv_host, i
   Scratch tmp;
   TriBounds* bounds = nullptr;
   uint32_t *code = nullptr, *val = nullptr;
-  float4 *leaf_box = nullptr, *node_box = nullptr;
-  int2* children = nullptr;
-  int *parent = nullptr, *visit = nullptr;
+  float4 *leaf_box = nullptr, *node_box = nullptr, *tris_tmp = nullptr, *nodes_tmp = nullptr;
+  int2 *children = nullptr, *range = nullptr;
+  int *parent = nullptr, *wdepth = nullptr, *flag = nullptr, *slot = nullptr;
+  unsigned int* scan_ticket = nullptr;
+  unsigned long long* scan_status = nullptr;
+  const int inner = std::max(n - 1, 1);
+  const int scan_tiles = (inner + kScanTile - 1) / kScanTile;
   CK(tmp.get(&bounds, 1));
   CK(tmp.get(&code, (size_t)n));
   CK(tmp.get(&val, (size_t)n));
   CK(tmp.get(&leaf_box, (size_t)n * 2));
-  CK(tmp.get(&node_box, (size_t)std::max(n - 1, 1) * 2));
-  CK(tmp.get(&children, (size_t)std::max(n - 1, 1)));
+  CK(tmp.get(&node_box, (size_t)inner * 2));
+  CK(tmp.get(&tris_tmp, (size_t)n * 3));
+  CK(tmp.get(&nodes_tmp, (size_t)inner * 8));
+  CK(tmp.get(&children, (size_t)inner));
+  CK(tmp.get(&range, (size_t)inner));
   CK(tmp.get(&parent, (size_t)(2 * n)));
-  CK(tmp.get(&visit, (size_t)std::max(n - 1, 1)));
+  CK(tmp.get(&wdepth, (size_t)inner));
+  CK(tmp.get(&flag, (size_t)inner));
+  CK(tmp.get(&slot, (size_t)inner));
+  CK(tmp.get(&scan_ticket, 1));
+  CK(tmp.get(&scan_status, (size_t)scan_tiles));
   RadixTempsGuard rguard;  // allocated up front: build_ms below is device time, not cudaMalloc latency
   RadixTemps& rtemps = rguard.t;
   if ((rc = radix_temps_alloc(&rtemps, n))) return rc;
@@ -421,43 +427,71 @@ static int build_mesh(B2ptCtx* c, const float* pos_host, const float* uv_host, i
   k_morton<<<blocks, 256, 0, s>>>(out->face_pos, n, bounds, code, val);
   c->launches += 3;
   if ((rc = radix_sort_pairs_dev(code, val, n, s, &c->launches, rtemps))) return rc;
-  k_leaves<<<blocks, 256, 0, s>>>(out->face_pos, val, n, pad, out->tris, leaf_box);
+  k_leaves<<<blocks, 256, 0, s>>>(out->face_pos, val, n, pad, tris_tmp, leaf_box);
   c->launches += 1;
   TriBounds hb;
   memset(&hb, 0, sizeof hb);
-  if (n >= 2) {
-    CK(cudaMemsetAsync(visit, 0, (size_t)(n - 1) * sizeof(int), s));
+  int n_nodes = 0;  // wide nodes reachable from the root
+  const bool tree = n > kLeafTris;  // a mesh of at most kLeafTris triangles is a single leaf
+  if (tree) {
+    CK(cudaMemsetAsync(wdepth, 0, (size_t)(n - 1) * sizeof(int), s));
     const int iblocks = (n - 1 + 255) / 256;
-    k_karras<<<iblocks, 256, 0, s>>>(code, n, children, parent);
-    k_refit<<<blocks, 256, 0, s>>>(n, children, parent, leaf_box, node_box, visit, bounds);
+    k_karras<<<iblocks, 256, 0, s>>>(code, n, children, parent, range);
+    k_refit<<<blocks, 256, 0, s>>>(n, children, parent, leaf_box, node_box, wdepth, bounds);
     k_tree_depth<<<blocks, 256, 0, s>>>(n, parent, bounds);
-    k_node_depth<<<iblocks, 256, 0, s>>>(n, parent, visit);  // visit[] is free again: reuse it for the depths
-    k_emit_wide4<<<iblocks, 256, 0, s>>>(n, children, visit, leaf_box, node_box, out->nodes);
-    c->launches += 5;
-    // depth of the wide tree (visit[] is free again): one level per launch until nothing is reached any more;
-    // a binary tree of depth D gives at most D wide levels, and D is known by now (one small read-back)
-    CK(cudaMemsetAsync(visit, 0, (size_t)(n - 1) * sizeof(int), s));
+    k_emit_wide4<<<iblocks, 256, 0, s>>>(n, children, range, leaf_box, node_box, nodes_tmp);
+    c->launches += 4;
+    // which wide nodes the root reaches, and how deep the wide tree is: one level per launch (wdepth[] served
+    // the refit as its visit counters and is free again); a binary tree of depth D gives at most D wide levels,
+    // and D is known by now (one small read-back)
+    CK(cudaMemsetAsync(wdepth, 0, (size_t)(n - 1) * sizeof(int), s));
     const int one = 1;
-    CK(cudaMemcpyAsync(visit, &one, sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(wdepth, &one, sizeof(int), cudaMemcpyHostToDevice, s));
     CK(cudaMemcpyAsync(&hb, bounds, sizeof hb, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     const int levels = std::max(1, std::min(hb.max_depth, 64));
-    for (int level = 1; level <= levels; ++level) k_wide_levels<<<iblocks, 256, 0, s>>>(n, out->nodes, visit, level, bounds);
+    for (int level = 1; level <= levels; ++level) k_wide_levels<<<iblocks, 256, 0, s>>>(n, nodes_tmp, wdepth, level, bounds);
     c->launches += levels;
+    // number the reachable nodes (exclusive scan of the flags) ...
+    k_reach_flags<<<iblocks, 256, 0, s>>>(n, wdepth, flag);
+    CK(cudaMemsetAsync(scan_ticket, 0, sizeof(unsigned int), s));
+    CK(cudaMemsetAsync(scan_status, 0, (size_t)scan_tiles * sizeof(unsigned long long), s));
+    k_scan_family<0><<<scan_tiles, kScanThreads, 0, s>>>(flag, nullptr, n - 1, slot, nullptr, scan_ticket, scan_status, 1u, nullptr);
+    c->launches += 2;
+    int last[2] = {0, 0};
+    CK(cudaMemcpyAsync(&last[0], slot + (n - 2), sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&last[1], flag + (n - 2), sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    n_nodes = last[0] + last[1];
   }
+  // ... and keep only those: nodes and triangles share one allocation so that a single L2 access-policy window
+  // can keep the whole acceleration structure resident
+  const size_t node_f4 = (size_t)std::max(n_nodes, 1) * 8, tri_f4 = (size_t)n * 3;
+  if ((rc = c->dalloc(&out->nodes, node_f4 + tri_f4))) return rc;
+  out->tris = out->nodes + node_f4;
+  out->bvh_bytes = (node_f4 + tri_f4) * sizeof(float4);
+  out->info.n_nodes = n_nodes;
+  if (tree) {
+    k_compact_nodes<<<(n - 1 + 255) / 256, 256, 0, s>>>(n, nodes_tmp, wdepth, slot, out->nodes);
+    c->launches += 1;
+  } else {
+    CK(cudaMemsetAsync(out->nodes, 0, node_f4 * sizeof(float4), s));
+  }
+  CK(cudaMemcpyAsync(out->tris, tris_tmp, tri_f4 * sizeof(float4), cudaMemcpyDeviceToDevice, s));
   CK(cudaEventRecord(ev.b, s));
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(s));
   CK(cudaEventElapsedTime(&out->info.build_ms, ev.a, ev.b));
   CK(cudaMemcpy(&hb, bounds, sizeof hb, cudaMemcpyDeviceToHost));
-  out->info.max_depth = n >= 2 ? hb.max_depth : 1;
-  const int wide_depth = n >= 2 ? hb.wide_depth : 0;
+  out->info.max_depth = tree ? hb.max_depth : 1;
+  out->wide_depth = tree ? hb.wide_depth : 0;
+  out->root = tree ? 0 : leaf_code(0, n);
   if (getenv("B2PT_TRAVERSAL_STATS"))
-    fprintf(stderr, "[b2pt bvh] %d triangles: binary depth %d, 4-wide depth %d (stack bound %d of %d entries)\n", n,
-            out->info.max_depth, wide_depth, 3 * wide_depth, kWalkShort + kWalkSpill);
+    fprintf(stderr, "[b2pt bvh] %d triangles: binary depth %d, %d wide nodes (%.1f MB), 4-wide depth %d, leaves of <= %d triangles\n", n,
+            out->info.max_depth, n_nodes, n_nodes * 128.0 / 1e6, out->wide_depth, kLeafTris);
   // a walk's stack holds at most three entries per inner wide node on its path (nearest child first, the other
   // hits pushed); k_mesh_walk_long's depth-first fallback relies on the same bound
-  if (out->info.max_depth > 64 || 3 * wide_depth > kWalkShort + kWalkSpill)
+  if (out->info.max_depth > 64 || 3 * out->wide_depth > kWalkShort + kWalkSpill)
     return fail(B2PT_ERR_RANGE, "LBVH deeper than the traversal stack");
   return 0;
 }
@@ -617,7 +651,8 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
       M.face_pos = mb.face_pos;
       M.face_uv = mb.face_uv;
       M.n_faces = G.face_count;
-      M.root = G.face_count >= 2 ? 0 : ~0;
+      M.root = mb.root;
+      M.geom = g;
       if ((rc = upload_texture(c, sc, G.tex_kd, &M.kd))) return rc;
       if ((rc = upload_texture(c, sc, G.tex_ks, &M.ks))) return rc;
       if ((rc = upload_texture(c, sc, G.tex_bump, &M.bump))) return rc;
@@ -678,7 +713,7 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
   }
   if ((rc = c->dalloc(&c->perm, P))) return rc;
   if ((rc = c->dalloc(&c->apos, P))) return rc;
-  if ((rc = c->dalloc(&c->mesh_queue, P))) return rc;
+  if ((rc = c->dalloc(&c->mesh_queue, 3 * P))) return rc;
   c->long_cap = (int)std::max<size_t>(P / 4, 4096);
   if ((rc = c->dalloc(&c->long_queue, (size_t)c->long_cap))) return rc;
   if ((rc = c->dalloc(&c->long_best, (size_t)c->long_cap))) return rc;
@@ -782,18 +817,10 @@ extern "C" void b2pt_destroy(B2ptCtx* c) {
     for (int d = 0; d < c->loop_depth; ++d) {
       const unsigned long long* s = &h[(size_t)32 * d];
       if (!s[0]) continue;
-      fprintf(stderr, "[b2pt traversal] depth %d: %llu walks, nodes/walk %.1f (max %llu), tris/walk %.1f (max %llu), log2 hist:",
-              d, s[0], (double)s[1] / s[0], s[3], (double)s[2] / s[0], s[4]);
-      for (int k = 0; k < 13; ++k) fprintf(stderr, " %llu", s[5 + k]);
-      fprintf(stderr, "\n");
-      if (s[21])
-        fprintf(stderr, "[b2pt traversal]   per warp: %llu warps, loop iterations avg %.1f max %llu, cycles avg %.0f max %llu, "
-                        "refills avg %.1f (%.0f cycles each), prologue %.0f cycles, lanes per node step %.1f\n",
-                s[21], (double)s[22] / s[21], s[23], (double)s[24] / s[21], s[25], (double)s[26] / s[21],
-                s[26] ? (double)s[27] / s[26] : 0.0, (double)s[28] / s[21], s[30] ? (double)s[29] / s[30] : 0.0);
-      if (s[21])
-        fprintf(stderr, "[b2pt traversal]   cycles per node step %.0f (%llu steps), per leaf step %.0f (%llu steps), hand-off check %.0f per iteration\n",
-                s[30] ? (double)s[31] / s[30] : 0.0, s[30], s[19] ? (double)s[20] / s[19] : 0.0, s[19], s[22] ? (double)s[18] / s[22] : 0.0);
+      fprintf(stderr, "[b2pt traversal] depth %d: %llu walks, node steps/walk %.2f, leaf steps/walk %.2f; per warp: %llu warps, "
+                      "loop iterations avg %.1f max %llu, refill passes avg %.1f, lanes per node step %.1f\n",
+              d, s[0], (double)s[1] / s[0], (double)s[2] / s[0], s[21], s[21] ? (double)s[22] / s[21] : 0.0, s[23],
+              s[21] ? (double)s[26] / s[21] : 0.0, s[30] ? (double)s[29] / s[30] : 0.0);
     }
   }
   if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
@@ -912,6 +939,7 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
     np.ctr = c->ctr;
     np.depth = depth;
     np.queue = c->mesh_queue;
+    np.queue_cap = c->P;
     return np;
   };
   const bool fused_gen = fused && !c->fb_enabled;
@@ -952,10 +980,10 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
     ip.stats = c->trav_stats ? c->trav_stats + 32 * d : nullptr;
     if (kt) kt->mark(1);
     ip.queue = c->mesh_queue;
+    ip.queue_cap = c->P;
     ip.long_queue = c->long_queue;
-    // With several meshes a ray can have more than one long walk, and k_mesh_walk_long folds them concurrently
-    // from the closest hit it read when it started: keep every walk in its lane then.
-    ip.long_walk = c->dscene.n_meshes > 1 ? 0x3fffffff : c->long_walk;
+    // (several meshes are safe: a ray that is handed off is finished by k_mesh_walk_long, remaining meshes included)
+    ip.long_walk = c->long_walk;
     ip.long_cap = c->long_cap;
     ip.long_carry = c->long_carry;
     ip.long_best = c->long_best;

@@ -43,15 +43,15 @@ __global__ void __launch_bounds__(256) k_generate_trace(GenParams gp, const int*
     AnalyticHit r;
     r.mat = 0;
     r.survives = r.want_mesh = false;
+    V3 o = mk(0, 0, 0), d = mk(0, 0, 1);
     if (valid) {
-      V3 o, d;
       camera_ray<TRIG>(gp, iter, index, &o, &d);
       out.s0[index] = make_float4(o.x, o.y, o.z, __int_as_float(index));
       out.s1[index] = make_float4(d.x, d.y, d.z, __int_as_float(gp.trace_depth));
       out.s2[index] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
       analytic_trace(sgeom, next.scene.n_geoms, next.scene.materials, o, d, gp.trace_depth, &r);
     }
-    analytic_commit(next, shist, slive, index, valid, r);
+    analytic_commit(next, shist, slive, index, valid, r, o, d);
   }
   __syncthreads();
   analytic_flush(next, shist, slive);
@@ -105,15 +105,17 @@ __global__ void __launch_bounds__(kFusedThreads) k_shade_trace(ShadeParams p, Is
     r.mat = 0;
     r.survives = r.want_mesh = false;
     const int slot = (int)pos0 + tid;
+    V3 no = mk(0, 0, 0), nd = mk(0, 0, 1);
     if (have) {
       const float4 a = st0[tid], b = st1[tid], c = st2[tid];
       p.out.s0[slot] = a;
       p.out.s1[slot] = b;
       p.out.s2[slot] = c;
-      analytic_trace(sgeom, next.scene.n_geoms, next.scene.materials, mk(a.x, a.y, a.z), mk(b.x, b.y, b.z),
-                     __float_as_int(b.w), &r);
+      no = mk(a.x, a.y, a.z);
+      nd = mk(b.x, b.y, b.z);
+      analytic_trace(sgeom, next.scene.n_geoms, next.scene.materials, no, nd, __float_as_int(b.w), &r);
     }
-    analytic_commit(next, shist, slive, slot, have, r);
+    analytic_commit(next, shist, slive, slot, have, r, no, nd);
     __syncthreads();  // the staging arrays are reused by the next tile
   }
   __syncthreads();

@@ -36,7 +36,9 @@ struct IsectParams {
   uint8_t* live;  // 1 if the path will survive the coming shade (decided here, see will_survive)
   Counters* ctr;
   int depth;
-  int* queue;                 // rays that must walk a mesh (filled by k_intersect_analytic)
+  float4* queue;              // rays that must walk a mesh (filled by k_intersect_analytic), three planes of queue_cap
+                              // entries: (origin, path slot) (direction, closest analytic t) (geom|material<<16, survival flag)
+  int queue_cap;
   int2* long_queue;           // (ray, geom) walks that outgrew one lane (filled by k_mesh_walk)
   int long_walk;              // steps after which k_mesh_walk hands a walk to k_mesh_walk_long
   int long_cap;               // capacity of the hand-off queue
@@ -334,7 +336,7 @@ __device__ __forceinline__ void analytic_trace(const DevGeom* sgeom, int n_geoms
 // Store the record of slot i, count it in the CTA's histograms and queue it for the mesh walk.  Called by
 // WHOLE WARPS (lanes without a ray pass valid = false): the histogram and queue updates are warp-aggregated.
 __device__ __forceinline__ void analytic_commit(const IsectParams& p, int* shist, int* slive, int i, bool valid,
-                                                const AnalyticHit& r) {
+                                                const AnalyticHit& r, V3 o, V3 d) {
   const int lane = threadIdx.x & 31;
   if (valid) {
     p.out.h0[i] = r.h0;
@@ -355,7 +357,13 @@ __device__ __forceinline__ void analytic_commit(const IsectParams& p, int* shist
     unsigned int qbase = 0;
     if (lane == 0) qbase = atomicAdd(&p.ctr->mesh_count[p.depth], (unsigned int)__popc(mm));
     qbase = __shfl_sync(0xffffffffu, qbase, 0);
-    if (want) p.queue[qbase + __popc(mm & ((1u << lane) - 1u))] = i;
+    if (want) {
+      // the queue entry carries the ray: the walk's refill is then one coalesced round trip instead of a chain of gathers
+      const unsigned int q = qbase + __popc(mm & ((1u << lane) - 1u));
+      p.queue[q] = make_float4(o.x, o.y, o.z, __int_as_float(i));
+      p.queue[(size_t)p.queue_cap + q] = make_float4(d.x, d.y, d.z, r.h0.x);
+      p.queue[2 * (size_t)p.queue_cap + q] = make_float4(r.h1.z, __int_as_float(r.survives ? 1 : 0), 0.0f, 0.0f);
+    }
   }
 }
 
@@ -394,12 +402,15 @@ __global__ void __launch_bounds__(256) k_intersect_analytic(IsectParams p) {
     AnalyticHit r;
     r.mat = 0;
     r.survives = r.want_mesh = false;
+    V3 o = mk(0, 0, 0), d = mk(0, 0, 1);
     if (valid) {
       const float4 a = p.in.s0[i];
       const float4 b = p.in.s1[i];
-      analytic_trace(sgeom, p.scene.n_geoms, p.scene.materials, mk(a.x, a.y, a.z), mk(b.x, b.y, b.z), __float_as_int(b.w), &r);
+      o = mk(a.x, a.y, a.z);
+      d = mk(b.x, b.y, b.z);
+      analytic_trace(sgeom, p.scene.n_geoms, p.scene.materials, o, d, __float_as_int(b.w), &r);
     }
-    analytic_commit(p, shist, slive, i, valid, r);
+    analytic_commit(p, shist, slive, i, valid, r, o, d);
   }
   __syncthreads();
   analytic_flush(p, shist, slive);
@@ -436,7 +447,7 @@ __global__ void __launch_bounds__(kIsectThreads, 3) k_intersect_mesh_brute(Isect
     qb = __shfl_sync(0xffffffffu, qb, 0);
     if (qb >= total) break;
     if (qb + lane < total) {
-      const int i = p.queue[qb + lane];
+      const int i = __float_as_int(p.queue[qb + lane].w);
       const float4 a = p.in.s0[i];
       const float4 b = p.in.s1[i];
       const float4 h0 = p.out.h0[i];

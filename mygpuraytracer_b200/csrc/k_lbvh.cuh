@@ -10,10 +10,16 @@
 //   4. the Karras 2012 hierarchy (one thread per internal node, duplicates
 //      broken by index)
 //   5. bottom-up refit with one atomic counter per internal node
-//   6. 4-wide traversal nodes (k_emit_wide4): a binary node's two children, the larger inner
-//      one opened twice (surface-area greedy), their boxes in one 128-byte line; triangles in
-//      leaf order as 3 x float4 (v0|face id, v1, v2); the depth of the wide tree (k_wide_levels)
-//      bounds the traversal stacks.
+//   6. 4-wide traversal nodes with fat leaves (k_emit_wide4): every maximal subtree of at most
+//      kLeafTris triangles becomes ONE leaf (a contiguous range of the Morton order: Karras'
+//      nodes cover index ranges); a wide node takes a binary node's two children and opens the
+//      inner one with the largest surface area twice (surface-area greedy).  One node is one
+//      128-byte line with the boxes stored per axis.  Only the nodes reachable from the root are
+//      kept (k_wide_levels marks them level by level, a scan numbers them, k_compact_nodes moves
+//      them), so the tree the walk touches is contiguous: 250 500 triangles -> 71 k nodes = 9 MB
+//      with kLeafTris = 2, instead of one node per binary node = 32 MB.  Triangles stay in leaf
+//      order as 3 x float4 (v0|face id, v1, v2); the depth of the wide tree bounds the traversal
+//      stacks.
 // Boxes are inflated by `pad` (a few 1e-6 of the mesh extent) so that the
 // conservative slab test can never cull a triangle the reference's exact test
 // would accept: the BVH prunes, it never decides.
@@ -150,7 +156,8 @@ __device__ __forceinline__ int lbvh_delta(const uint32_t* __restrict__ code, int
 // One thread per internal node i in [0, n-2]: children and parent links.
 // child encoding: >= 0 internal node, < 0 ~leaf slot.  parent[] has n-1 internal
 // entries followed by n leaf entries.
-__global__ void __launch_bounds__(256) k_karras(const uint32_t* __restrict__ code, int n, int2* children, int* parent) {
+__global__ void __launch_bounds__(256) k_karras(const uint32_t* __restrict__ code, int n, int2* children, int* parent,
+                                                int2* range) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1) return;
   const int d = (lbvh_delta(code, n, i, i + 1) - lbvh_delta(code, n, i, i - 1)) >= 0 ? 1 : -1;
@@ -172,6 +179,7 @@ __global__ void __launch_bounds__(256) k_karras(const uint32_t* __restrict__ cod
   const int left = (lo == gamma) ? ~gamma : gamma;
   const int right = (hi == gamma + 1) ? ~(gamma + 1) : gamma + 1;
   children[i] = make_int2(left, right);
+  range[i] = make_int2(lo, hi);  // the leaves (Morton slots) under this node, inclusive
   if (left >= 0) parent[left] = i; else parent[(n - 1) + gamma] = i;
   if (right >= 0) parent[right] = i; else parent[(n - 1) + gamma + 1] = i;
   if (i == 0) parent[0] = -1;
@@ -215,45 +223,41 @@ __global__ void __launch_bounds__(256) k_tree_depth(int n, const int* __restrict
   atomicMax(&info->max_depth, depth);
 }
 
-// Depth of every internal node (number of ancestors).
-__global__ void __launch_bounds__(256) k_node_depth(int n, const int* __restrict__ parent, int* depth) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n - 1) return;
-  int d = 0;
-  for (int p = parent[i]; p >= 0; p = parent[p]) ++d;
-  depth[i] = d;
-}
-
-// 4-wide traversal nodes: a wide node's children are the binary node's two children with the
-// largest inner box opened twice (fixed two-level collapse = always the four grandchildren when
-// B2PT_WIDE_SAH is 0), so a walk makes about half as many dependent memory round trips.  One wide node is exactly
-// one 128-byte line, boxes stored per axis for the four slots:
+// ---- 4-wide traversal nodes with fat leaves -----------------------------------------------------------
+// child ids:  >= 0 (and < kEmptyChild)  inner node index
+//             kEmptyChild               unused slot
+//             < 0                       leaf: ~((first Morton slot << 3) | (triangles - 1))
+// node layout (8 x float4 = one 128-byte line), boxes per axis for the four slots:
 //   f0 = min.x[0..3]  f1 = max.x   f2 = min.y  f3 = max.y   f4 = min.z  f5 = max.z
-//   f6 = child ids as int bits (>= 0: wide node, < 0: ~leaf slot, kEmptyChild: unused)   f7 = pad
+//   f6 = child ids as int bits   f7 = pad
 // (both planes of an axis sit in one aligned 32-byte half-sector: the walk picks the plane a ray enters
-// through with a 16-byte address offset, or fetches the pair with one 256-bit load)
-// Wide nodes keep the index of the binary node they come from.
+// through with a 16-byte address offset).  An unused slot has min = +FLT_MAX, max = -FLT_MAX.
 constexpr int kEmptyChild = 0x40000000;
-
-#ifndef B2PT_WIDE_SAH
-#define B2PT_WIDE_SAH 1
+#ifndef B2PT_LEAF_TRIS
+#define B2PT_LEAF_TRIS 2
 #endif
+constexpr int kLeafTris = B2PT_LEAF_TRIS;  // triangles per leaf, at most
+static_assert(kLeafTris >= 1 && kLeafTris <= 8, "leaf codes keep the count in three bits");
+
+__host__ __device__ __forceinline__ int leaf_code(int first, int count) { return ~((first << 3) | (count - 1)); }
+__host__ __device__ __forceinline__ int leaf_first(int code) { return (~code) >> 3; }
+__host__ __device__ __forceinline__ int leaf_count(int code) { return ((~code) & 7) + 1; }
+
 __device__ __forceinline__ float box_area(const float4* b) {
   const float dx = b[1].x - b[0].x, dy = b[1].y - b[0].y, dz = b[1].z - b[0].z;
   return dx * dy + dy * dz + dz * dx;
 }
 
-__global__ void __launch_bounds__(256) k_emit_wide4(int n, const int2* __restrict__ children, const int* __restrict__ depth,
+// One thread per binary node: its wide node (only those reachable from the root survive the compaction).
+// Child ids are still BINARY node indices here; k_compact_nodes renumbers them.
+__global__ void __launch_bounds__(256) k_emit_wide4(int n, const int2* __restrict__ children, const int2* __restrict__ range,
                                                     const float4* __restrict__ leaf_box, const float4* __restrict__ node_box,
                                                     float4* nodes) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1) return;
+  // a child can be opened if it is an inner node with more triangles than a leaf may hold
+  auto openable = [&](int c) { return c >= 0 && range[c].y - range[c].x + 1 > kLeafTris; };
   int id[4] = {kEmptyChild, kEmptyChild, kEmptyChild, kEmptyChild};
-#if B2PT_WIDE_SAH
-  // Every binary node gets a wide node (only those reachable from the root are ever visited): start from its
-  // two children and twice replace the inner child with the LARGEST surface area by its own two children,
-  // instead of always taking the four grandchildren.  Big boxes are opened early, small ones stay closed.
-  (void)depth;
   int k = 2;
   {
     const int2 c = children[i];
@@ -264,7 +268,7 @@ __global__ void __launch_bounds__(256) k_emit_wide4(int n, const int2* __restric
     int pick = -1;
     float best_area = -1.0f;
     for (int q = 0; q < k; ++q) {
-      if (id[q] < 0) continue;  // a leaf cannot be opened
+      if (!openable(id[q])) continue;
       const float a = box_area(node_box + 2 * (size_t)id[q]);
       if (a > best_area) {
         best_area = a;
@@ -276,28 +280,18 @@ __global__ void __launch_bounds__(256) k_emit_wide4(int n, const int2* __restric
     id[pick] = g.x;
     id[k++] = g.y;
   }
-#else
-  if (depth[i] & 1) return;
-  int k = 0;
-  const int2 c = children[i];
-  const int side[2] = {c.x, c.y};
-  for (int s = 0; s < 2; ++s) {
-    if (side[s] < 0) {
-      id[k++] = side[s];
-    } else {
-      const int2 g = children[side[s]];
-      id[k++] = g.x;
-      id[k++] = g.y;
-    }
-  }
-#endif
   float lo[3][4], hi[3][4];
+  int code[4];
   for (int q = 0; q < 4; ++q) {
     float4 b0 = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, 0.0f), b1 = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, 0.0f);
+    code[q] = kEmptyChild;
     if (id[q] != kEmptyChild) {
       const float4* b = id[q] >= 0 ? node_box + 2 * (size_t)id[q] : leaf_box + 2 * (size_t)(~id[q]);
       b0 = b[0];
       b1 = b[1];
+      if (id[q] < 0) code[q] = leaf_code(~id[q], 1);
+      else if (!openable(id[q])) code[q] = leaf_code(range[id[q]].x, range[id[q]].y - range[id[q]].x + 1);
+      else code[q] = id[q];
     }
     lo[0][q] = b0.x; lo[1][q] = b0.y; lo[2][q] = b0.z;
     hi[0][q] = b1.x; hi[1][q] = b1.y; hi[2][q] = b1.z;
@@ -307,13 +301,14 @@ __global__ void __launch_bounds__(256) k_emit_wide4(int n, const int2* __restric
     o[2 * a] = make_float4(lo[a][0], lo[a][1], lo[a][2], lo[a][3]);
     o[2 * a + 1] = make_float4(hi[a][0], hi[a][1], hi[a][2], hi[a][3]);
   }
-  o[6] = make_float4(__int_as_float(id[0]), __int_as_float(id[1]), __int_as_float(id[2]), __int_as_float(id[3]));
+  o[6] = make_float4(__int_as_float(code[0]), __int_as_float(code[1]), __int_as_float(code[2]), __int_as_float(code[3]));
   o[7] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
-// Depth of the 4-wide tree, one level per launch: the nodes reached at `level` mark their inner children
-// with level + 1 (wdepth[0] = 1 for the root before the first launch).  A walk's stack holds at most three
-// entries per inner wide node on its path, which is what the traversal stacks are sized against.
+// Reachability and depth of the wide tree, one level per launch: the nodes reached at `level` mark their
+// inner children with level + 1 (wdepth[0] = 1 for the root before the first launch, 0 = not reachable).  A
+// walk's stack holds at most three entries per inner wide node on its path plus the four of the node being
+// opened, which is what the traversal stacks are sized against.
 __global__ void __launch_bounds__(256) k_wide_levels(int n, const float4* __restrict__ nodes, int* wdepth, int level,
                                                      TriBounds* info) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -323,6 +318,28 @@ __global__ void __launch_bounds__(256) k_wide_levels(int n, const float4* __rest
   for (int k = 0; k < 4; ++k)
     if (ch[k] >= 0 && ch[k] != kEmptyChild) wdepth[ch[k]] = level + 1;
   atomicMax(&info->wide_depth, level);
+}
+
+__global__ void __launch_bounds__(256) k_reach_flags(int n, const int* __restrict__ wdepth, int* flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n - 1) flag[i] = wdepth[i] != 0;
+}
+
+// Move the reachable nodes to their compact slots (slot[] = exclusive scan of the flags) and renumber the
+// inner child ids.  The root (binary node 0) stays node 0.
+__global__ void __launch_bounds__(256) k_compact_nodes(int n, const float4* __restrict__ src, const int* __restrict__ wdepth,
+                                                       const int* __restrict__ slot, float4* dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n - 1 || wdepth[i] == 0) return;
+  const float4* s = src + 8 * (size_t)i;
+  float4* d = dst + 8 * (size_t)slot[i];
+  for (int k = 0; k < 6; ++k) d[k] = s[k];
+  const float4 cf = s[6];
+  int ch[4] = {__float_as_int(cf.x), __float_as_int(cf.y), __float_as_int(cf.z), __float_as_int(cf.w)};
+  for (int k = 0; k < 4; ++k)
+    if (ch[k] >= 0 && ch[k] != kEmptyChild) ch[k] = slot[ch[k]];
+  d[6] = make_float4(__int_as_float(ch[0]), __int_as_float(ch[1]), __int_as_float(ch[2]), __int_as_float(ch[3]));
+  d[7] = s[7];
 }
 
 }  // namespace b2pt

@@ -58,12 +58,14 @@ struct DevGeom {
 };
 
 struct DevMesh {
-  const float4* nodes;    // 8 x float4 (one 128-byte line) per 4-wide BVH node (see k_lbvh.cuh)
-  const float4* tris;     // 3 x float4 per triangle in BVH leaf order: (v0,face) (v1,-) (v2,-)
+  const float4* nodes;    // 8 x float4 (one 128-byte line) per 4-wide BVH node, child-major (see k_lbvh.cuh)
+  const float4* tris;     // 3 x float4 per triangle in BVH leaf (Morton) order: (v0,face) (v1,-) (v2,-)
   const float* face_pos;  // 9 floats per face, original order
   const float* face_uv;   // 6 floats per face, original order
   int n_faces;
-  int root;  // >= 0: internal node index; < 0: ~leaf (single-triangle mesh)
+  int root;  // 0: the root node; < 0: a leaf code (a mesh of at most kLeafTris triangles has no nodes)
+  int geom;  // the geom this mesh belongs to (meshes are numbered in geom order)
+  int pad_;
   DevTexture kd, ks, bump, ke;
 };
 

@@ -384,6 +384,36 @@ def test_edge_cases(tmp_path):
     compare_iteration(pod, {}, iters=(1, 2), what="1x1")
 
 
+@pytest.mark.parametrize("n_tris", [1, 2, 3, 4, 5, 8, 9, 17])
+def test_tiny_meshes_bitexact(tmp_path, n_tris):
+    """Meshes of a handful of triangles: up to kLeafTris the whole mesh is ONE leaf (no BVH node at all, the root
+    is a leaf code), just above it the tree is a single wide node with leaves of uneven size."""
+    (tmp_path / "models" / "materials").mkdir(parents=True)
+    (tmp_path / "models" / "materials" / "tiny.mtl").write_text("newmtl plain\nKd 0.7 0.6 0.3\nKs 0.4 0.4 0.4\nKe 0 0 0\nNi 1.5\n")
+    rng = np.random.default_rng(100 + n_tris)
+    lines = ["mtllib tiny.mtl"]
+    faces = []
+    for k in range(n_tris):  # a fan of triangles facing the camera (+z seen from the ship's place in the box)
+        c = rng.uniform(-1.2, 1.2, 3) * (1.0, 0.8, 0.3)
+        a, b = rng.uniform(0.3, 0.9, 2)
+        ang = rng.uniform(0, 2 * np.pi)
+        p = [c + (a * np.cos(ang + t), b * np.sin(ang + t), 0.05 * k) for t in (0.0, 2.1, 4.2)]
+        for q in p:
+            lines.append("v %.6f %.6f %.6f" % tuple(q))
+        faces.append((3 * k + 1, 3 * k + 2, 3 * k + 3))
+    lines += ["vt 0.2 0.2", "vt 0.8 0.2", "vt 0.5 0.8", "vn 0 0 1", "usemtl plain"]
+    back = n_tris not in (1, 3)  # 1 and 3 stay single sided: meshes of exactly 1 and 3 triangles
+    for a, b, c in faces:
+        lines.append(f"f {a}/1/1 {b}/2/1 {c}/3/1")
+        if back:
+            lines.append(f"f {a}/1/1 {c}/3/1 {b}/2/1")  # the back side, so that every ray direction finds a front face
+    (tmp_path / "models" / "tiny.obj").write_text("\n".join(lines) + "\n")
+    path = scenes.write_scene("cornellObj", str(tmp_path / "scenes" / "s.txt"), width=48, height=40, obj_path="../models/tiny.obj")
+    pod = api.Scene(path).pod
+    assert len(pod.face_pos) == (2 if back else 1) * n_tris
+    compare_iteration(pod, {}, iters=(1, 2), what=f"{len(pod.face_pos)}-triangle mesh")
+
+
 def test_many_geoms_and_materials(tmp_path):
     """Capacity corners: 64 geoms (the shared-memory staging and the 64-bit
     candidate mask of k_intersect_analytic) and 200 materials of all four BSDF
