@@ -156,7 +156,6 @@ struct B2ptCtx {
   Counters* ctr = nullptr;
   int* iter_state = nullptr;
   unsigned long long* sort_status = nullptr;
-  unsigned long long* shade_status = nullptr;
   float* image = nullptr;
   float* albedo = nullptr;
   float* image_target = nullptr;  // where the gather accumulates (own image or caller's buffer)
@@ -709,10 +708,10 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
     if ((rc = c->dalloc(&c->hits[b].h0, P))) return rc;
     if ((rc = c->dalloc(&c->hits[b].h1, P))) return rc;
     if ((rc = c->dalloc(&c->key[b], P))) return rc;
-    if ((rc = c->dalloc(&c->live[b], P))) return rc;
+    if ((rc = c->dalloc(&c->live[b], P + kSortTile))) return rc;  // k_rank_live reads whole 16-byte groups
   }
   if ((rc = c->dalloc(&c->perm, P))) return rc;
-  if ((rc = c->dalloc(&c->apos, P))) return rc;
+  if ((rc = c->dalloc(&c->apos, P + kSortTile))) return rc;  // ... and writes whole int4s
   if ((rc = c->dalloc(&c->mesh_queue, 3 * P))) return rc;
   c->long_cap = (int)std::max<size_t>(P / 4, 4096);
   if ((rc = c->dalloc(&c->long_queue, (size_t)c->long_cap))) return rc;
@@ -726,7 +725,6 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
   c->gen_grid = (int)std::min<size_t>((P + 255) / 256, (size_t)c->sm_count * 8);
   if ((rc = c->dalloc(&c->sort_status, (size_t)c->sort_grid * 256))) return rc;
   if ((rc = c->dalloc(&c->sort_status_live, (size_t)c->sort_grid * 256))) return rc;
-  if ((rc = c->dalloc(&c->shade_status, (size_t)c->shade_grid))) return rc;
   if ((rc = c->dalloc(&c->image, P * 3))) return rc;
   if ((rc = c->dalloc(&c->albedo, P * 3))) return rc;
   c->image_target = c->image;
@@ -734,7 +732,6 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
   CK(cudaMemsetAsync(c->iter_state, 0, 4 * sizeof(int), c->stream));
   CK(cudaMemsetAsync(c->sort_status, 0, (size_t)c->sort_grid * 256 * 8, c->stream));
   CK(cudaMemsetAsync(c->sort_status_live, 0, (size_t)c->sort_grid * 256 * 8, c->stream));
-  CK(cudaMemsetAsync(c->shade_status, 0, (size_t)c->shade_grid * 8, c->stream));
   CK(cudaMemsetAsync(c->image, 0, P * 12, c->stream));
   CK(cudaMemsetAsync(c->albedo, 0, P * 12, c->stream));
   c->fb_enabled = opt.cache_first_bounce && !opt.antialiasing && !opt.depth_of_field;
@@ -742,7 +739,7 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
     if ((rc = c->dalloc(&c->fb_hits.h0, P))) return rc;
     if ((rc = c->dalloc(&c->fb_hits.h1, P))) return rc;
     if ((rc = c->dalloc(&c->fb_key, P))) return rc;
-    if ((rc = c->dalloc(&c->fb_live, P))) return rc;
+    if ((rc = c->dalloc(&c->fb_live, P + kSortTile))) return rc;
     if ((rc = c->dalloc(&c->fb_hist, (size_t)2 * kMaxMaterials))) return rc;
   }
   if (opt.record_stages) {
@@ -892,10 +889,7 @@ static void launch_generate(B2ptCtx* c, const IsectParams* next) {
 
 template <int TRIG, bool RECORD>
 static void launch_shade(B2ptCtx* c, const ShadeParams& sp) {
-  if (sp.apos)
-    k_shade_compact<TRIG, RECORD, true><<<std::min(c->shade_grid, c->shade_stride_grid), kShadeThreads, 0, c->stream>>>(sp);
-  else
-    k_shade_compact<TRIG, RECORD, false><<<c->shade_grid, kShadeThreads, 0, c->stream>>>(sp);
+  k_shade_compact<TRIG, RECORD><<<std::min(c->shade_grid, c->shade_stride_grid), kShadeThreads, 0, c->stream>>>(sp);
 }
 
 static void unpack3(const std::vector<float4>& v, int n, float* dst) {
@@ -928,7 +922,7 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
   // Fused form (k_fused.cuh): the kernel that produces the rays of depth d+1 also intersects them with the
   // analytic geoms.  Not when the records are read back between the stages, without the compaction ranks of
   // the material sort, or for the depth whose hits the first-bounce cache keeps.
-  const bool fused = c->fuse && !record && c->opt.sort_by_material;
+  const bool fused = c->fuse && !record;
   auto next_params = [&](int depth) {
     IsectParams np;
     memset(&np, 0, sizeof np);
@@ -1020,7 +1014,7 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
         c->launches += 1;
       }
     }
-    if (c->opt.sort_by_material) {
+    {
       MatSortParams mp;
       mp.key = key_d;
       mp.live = live_d;
@@ -1031,7 +1025,10 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
       mp.status_live = c->sort_status_live;
       mp.depth = d;
       if (kt) kt->mark(2);
-      k_sort_material<<<c->sort_grid, kSortThreads, 0, s>>>(mp);
+      if (c->opt.sort_by_material)
+        k_sort_material<<<c->sort_grid, kSortThreads, 0, s>>>(mp);
+      else  // SORT_BY_MATERIAL 0: slot order is kept, only the compaction ranks are needed
+        k_rank_live<<<c->sort_grid, kSortThreads, 0, s>>>(mp);
       c->launches += 1;
     }
     if (record) {
@@ -1050,11 +1047,10 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
     sp.in = in;
     sp.out = out;
     sp.hits = hits_d;
-    sp.perm = c->opt.sort_by_material ? c->perm : nullptr;
-    sp.apos = c->opt.sort_by_material ? c->apos : nullptr;
+    sp.perm = c->opt.sort_by_material ? c->perm : nullptr;  // NULL: identity
+    sp.apos = c->apos;
     sp.live = live_d;
     sp.ctr = c->ctr;
-    sp.status = c->shade_status;
     sp.image = c->image_target;
     sp.albedo = c->albedo;
     sp.iter_state = c->iter_state;

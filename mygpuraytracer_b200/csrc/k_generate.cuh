@@ -33,7 +33,6 @@ __global__ void k_iter_begin(Counters* c, int* iter_state, int n_paths, int dept
     c->long_count[i] = 0;
     c->long_ticket[i] = 0;
     c->sort_ticket[i] = 0;
-    c->shade_ticket[i] = 0;
   }
   if (tid == 0) c->n_live[depth_slots] = 0;
   unsigned int* h = &c->hist[0][0];

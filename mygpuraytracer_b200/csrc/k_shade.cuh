@@ -9,9 +9,9 @@
 // A thread shades sorted slot j: it gathers the hit record and the path state
 // through the sort permutation (the only pass that touches the payload of the
 // sort), seeds the reference's RNG with (iter, j, 0) and scatters.  Survivors
-// are written to the other path buffer at their rank among the survivors --
-// warp ballot + popc inside the warp, a shared-memory scan across warps, and a
-// decoupled look-back across tiles -- which is exactly the live prefix
+// are written to the other path buffer at their rank among the survivors
+// (computed by the kernel that ranked the survival flags: k_sort_material, or
+// k_rank_live when the material sort is off), which is exactly the live prefix
 // thrust::stable_partition produces.  A path that dies adds color*PI to its
 // pixel at once: every pixel owns exactly one path per iteration and dies
 // exactly once, so the accumulation needs no atomics and adds the same values
@@ -34,9 +34,8 @@ struct ShadeParams {
   PathBuf out;
   HitBuf hits;
   const int* perm;  // NULL: identity (SORT_BY_MATERIAL 0)
-  const int* apos;  // survivors in front of each sorted slot (k_sort_material); NULL: scan here
+  const int* apos;  // survivors in front of each sorted slot (k_sort_material / k_rank_live)
   Counters* ctr;
-  unsigned long long* status;  // [tiles] look-back words
   float* image;
   float* albedo;
   const int* iter_state;
@@ -238,81 +237,30 @@ __device__ __forceinline__ void shade_slot(const ShadeParams& p, int j, int iter
   }
 }
 
-// PRECOMP: the compaction ranks come from k_sort_material (apos); the kernel is
-// then embarrassingly parallel -- no shared memory, no barrier, no look-back.
-// Without the material sort (SORT_BY_MATERIAL 0) it scans the survivors itself.
-template <int TRIG, bool RECORD, bool PRECOMP>
+// The compaction ranks come from k_sort_material or k_rank_live (apos), so the kernel is embarrassingly parallel:
+// no shared memory, no barrier, no look-back; the CTAs stride over 256-slot tiles.
+template <int TRIG, bool RECORD>
 __global__ void __launch_bounds__(kShadeThreads) k_shade_compact(ShadeParams p) {
-  __shared__ unsigned int warp_cnt[kShadeWarps];
-  __shared__ unsigned int s_tile;
-  __shared__ unsigned int s_excl;
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   const int n = p.ctr->n_live[p.depth];
-  unsigned int tile = blockIdx.x;  // PRECOMP: no ordering between tiles is needed, the CTAs stride over them
-  if (!PRECOMP) {
-    if (tid == 0) s_tile = atomicAdd(&p.ctr->shade_ticket[p.depth], 1u);
-    __syncthreads();
-    tile = s_tile;
-  }
-  const unsigned int epoch = p.ctr->serial * (unsigned int)(kMaxDepth + 1) + (unsigned int)p.depth + 1u;
   const int iter = p.iter_state[0];
   const int ref_depth = p.depth + 1;
-  for (;; tile += gridDim.x) {
-  if ((long long)tile * kShadeThreads >= (long long)n) return;
-
-  const int j = (int)tile * kShadeThreads + tid;
-  const bool valid = j < n;
-  bool alive = false;
-  V3 o = mk(0, 0, 0), d = mk(0, 0, 0), col = mk(0, 0, 0);
-  int pixel = 0, bounces = 0;
-
-  if (valid) {
+  for (unsigned int tile = blockIdx.x; (long long)tile * kShadeThreads < (long long)n; tile += gridDim.x) {
+    const int j = (int)tile * kShadeThreads + tid;
+    if (j >= n) continue;
+    V3 o = mk(0, 0, 0), d = mk(0, 0, 0), col = mk(0, 0, 0);
+    int pixel = 0, bounces = 0;
     shade_slot<TRIG>(p, j, iter, ref_depth, o, d, col, pixel, bounces);
-    alive = bounces > 0;
+    const bool alive = bounces > 0;
     if (RECORD) {
       p.rec_s0[j] = make_float4(o.x, o.y, o.z, __int_as_float(pixel));
       p.rec_s1[j] = make_float4(d.x, d.y, d.z, __int_as_float(bounces));
       p.rec_s2[j] = make_float4(col.x, col.y, col.z, 0.0f);
     }
+    // stable compaction: the rank among the survivors was computed when the flags were
+    write_result<RECORD>(p, j, (unsigned int)p.apos[j], alive, o, d, col, pixel, bounces);
+    if (RECORD && alive != (p.live[p.perm ? p.perm[j] : j] != 0)) atomicAdd(&p.ctr->pred_mismatch, 1u);
   }
-
-  // ---- stable compaction: rank among the survivors --------------------------------
-  unsigned int ballot = 0;
-  if (PRECOMP) {
-    if (valid) {
-      const unsigned int pos = (unsigned int)p.apos[j];
-      write_result<RECORD>(p, j, pos, alive, o, d, col, pixel, bounces);
-      if (RECORD && alive != (p.live[p.perm ? p.perm[j] : j] != 0)) atomicAdd(&p.ctr->pred_mismatch, 1u);
-    }
-    continue;
-  }
-  ballot = __ballot_sync(0xffffffffu, alive);
-  if (lane == 0) warp_cnt[warp] = __popc(ballot);
-  __syncthreads();
-  if (warp == 0) {
-    unsigned int v = lane < kShadeWarps ? warp_cnt[lane] : 0u;
-    unsigned int incl = v;
-#pragma unroll
-    for (int off = 1; off < kShadeWarps; off <<= 1) {
-      const unsigned int t = __shfl_up_sync(0xffffffffu, incl, off);
-      if (lane >= off) incl += t;
-    }
-    if (lane < kShadeWarps) warp_cnt[lane] = incl - v;  // exclusive offsets of the warps
-    const unsigned int total = __shfl_sync(0xffffffffu, incl, kShadeWarps - 1);
-    const unsigned int excl = lookback_warp(p.status, 1, tile, epoch, total);
-    if (lane == 0) {
-      s_excl = excl;
-      // the last tile knows the live count of the next depth
-      if (((long long)tile + 1) * kShadeThreads >= (long long)n) p.ctr->n_live[p.depth + 1] = (int)(excl + total);
-    }
-  }
-  __syncthreads();
-  if (!valid) return;
-  const unsigned int pos = s_excl + warp_cnt[warp] + __popc(ballot & ((1u << lane) - 1u));
-  write_result<RECORD>(p, j, pos, alive, o, d, col, pixel, bounces);
-  return;
-  }  // tile loop (only PRECOMP comes back here)
 }
 
 }  // namespace b2pt

@@ -20,6 +20,7 @@
 // material sort, by k_radix_hist for the LSD sort).
 #pragma once
 
+#include "k_prims.cuh"
 #include "pt_device.cuh"
 
 namespace b2pt {
@@ -351,6 +352,58 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_material(MatSortParams p)
       const unsigned int j = bin_base[dig] + tile_excl[dig] + wcnt[warp][dig] + lrank[r];
       p.perm[j] = idx;
       p.apos[j] = (int)(live_base[dig] + tile_lexcl[dig] + wlive[warp][dig] + larank[r]);
+    }
+  }
+}
+
+// Compaction ranks WITHOUT a sort (SORT_BY_MATERIAL 0, apps/src/pathtrace.cu:38,611-613): paths are shaded in slot
+// order, so all the shade kernel needs is apos[j] = survivors in front of slot j (the live prefix of
+// thrust::stable_partition, :649) and the live count of the next depth.  One pass over the 1-byte survival flags:
+// 16 flags per thread, block scan, decoupled look-back across the 4096-slot tiles.  With the pixel-keyed RNG the
+// image does not depend on the order paths sit in the arrays, so this replaces the material sort altogether there.
+__global__ void __launch_bounds__(kSortThreads) k_rank_live(MatSortParams p) {
+  __shared__ unsigned int smem[kScanThreads / 32 + 1];
+  __shared__ unsigned int s_tile, s_excl;
+  static_assert(kScanThreads == kSortThreads && kSortTile == kSortThreads * 16, "16 flags per thread");
+  const int tid = threadIdx.x;
+  const int n = p.ctr->n_live[p.depth];
+  if (tid == 0) s_tile = atomicAdd(&p.ctr->sort_ticket[p.depth], 1u);
+  __syncthreads();
+  const unsigned int tile = s_tile;
+  if ((long long)tile * kSortTile >= (long long)n) return;
+  const unsigned int epoch = p.ctr->serial * (unsigned int)(kMaxDepth + 1) + (unsigned int)p.depth + 1u;
+  const int base = (int)tile * kSortTile + tid * 16;
+  unsigned int f[4] = {0u, 0u, 0u, 0u};  // 16 flags, one byte each (the arrays are allocated in whole tiles' worth of bytes)
+  if (base < n) {
+    const uint4 v = *reinterpret_cast<const uint4*>(p.live + base);
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  }
+  unsigned int alive = 0u;  // bit k: slot base + k survives
+#pragma unroll
+  for (int k = 0; k < 16; ++k)
+    if (base + k < n && ((f[k >> 2] >> (8 * (k & 3))) & 0xffu) != 0u) alive |= 1u << k;
+  unsigned int total;
+  const unsigned int excl = block_exclusive_scan((unsigned int)__popc(alive), &total, smem);
+  if (tid < 32) {
+    const unsigned int e = lookback_warp(p.status_live, 256, tile, epoch, total);
+    if (tid == 0) {
+      s_excl = e;
+      if (((long long)tile + 1) * kSortTile >= (long long)n) p.ctr->n_live[p.depth + 1] = (int)(e + total);
+    }
+  }
+  __syncthreads();
+  const unsigned int first = s_excl + excl;
+  if (base < n) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = base + 4 * q;
+      if (j >= n) break;
+      int4 o;
+      o.x = (int)(first + __popc(alive & ((1u << (4 * q)) - 1u)));
+      o.y = (int)(first + __popc(alive & ((1u << (4 * q + 1)) - 1u)));
+      o.z = (int)(first + __popc(alive & ((1u << (4 * q + 2)) - 1u)));
+      o.w = (int)(first + __popc(alive & ((1u << (4 * q + 3)) - 1u)));
+      *reinterpret_cast<int4*>(p.apos + j) = o;  // (apos holds whole tiles: the last int4 may pass n)
     }
   }
 }

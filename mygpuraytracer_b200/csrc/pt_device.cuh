@@ -103,7 +103,6 @@ struct Counters {
   unsigned int long_count[kMaxDepth + 1];    // tail of the long-walk queue (k_mesh_walk)
   unsigned int long_ticket[kMaxDepth + 1];   // head of the long-walk queue (k_mesh_walk_long)
   unsigned int sort_ticket[kMaxDepth + 1];   // tile order of the sort
-  unsigned int shade_ticket[kMaxDepth + 1];  // tile order of shade + compaction
   unsigned int hist[kMaxDepth + 1][kMaxMaterials];       // material histogram per depth
   unsigned int hist_live[kMaxDepth + 1][kMaxMaterials];  // ... of the paths that will survive the shade
   unsigned int pred_mismatch;                            // record mode: shade disagreed with the prediction

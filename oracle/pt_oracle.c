@@ -622,7 +622,10 @@ int oracle_shade(const B2ptScene* s, const B2ptOptions* opt, int32_t iter, int32
       }
     }
     if (t > 0.0f) {
-      uint32_t rng = oracle_seed(iter, idx, 0);
+      /* apps/src/pathtrace.cu:467 seeds with the array slot (after sort + compaction): B2PT_RNG_SLOT.
+       * B2PT_RNG_PIXEL is the second mode of north_star: a counter keyed on (pixel, iteration, depth), which no
+       * longer depends on where the path sits in the arrays (no reference behaviour; this restatement defines it). */
+      uint32_t rng = opt->rng_mode == B2PT_RNG_PIXEL ? oracle_seed(iter, pixel[idx], depth) : oracle_seed(iter, idx, 0);
       const B2ptMaterial* m = &s->materials[hit_material[idx]];
       if (m->emittance > 0.0f) {
         st3(color + i3, mulv(ld3(color + i3), muls(ld3(m->color), m->emittance)));

@@ -467,3 +467,62 @@ def test_invalid_scenes_are_rejected():
     bad.trace_depth = 1000
     with pytest.raises(api.B2ptError):
         api.Renderer(bad)
+
+
+# ---- the pixel-keyed RNG (north_star's second mode: a counter keyed on (pixel, iteration, depth)) ---------------
+@pytest.mark.parametrize("case,optkw", [("cornellGlass_32x32", {}), ("both_refl_refr_48x20", {}), ("texquad_32x32", {}),
+                                         ("cornell_32x32", {"sort_by_material": 0})])
+def test_pixel_rng_every_stage_bitexact(case, optkw):
+    """rng_mode = PIXEL against the oracle's restatement of it, every stage of two iterations."""
+    pod, *_ = load_golden(case)
+    compare_iteration(pod, dict(rng_mode=abi.RNG_PIXEL, **optkw), iters=(1, 2), what=f"{case} pixel rng")
+
+
+def test_pixel_rng_mesh_scene_and_order_independence(tmp_path):
+    """With pixel keys the radiance of a path no longer depends on its slot: the image is the same, bit for bit,
+    with and without the material sort, from one context or from members that share the iterations."""
+    pod = _mesh_scene(tmp_path, "cornellSpaceship", 160, 90, 5000)
+    compare_iteration(pod, dict(rng_mode=abi.RNG_PIXEL), iters=(1,), what="mesh scene, pixel rng")
+    imgs = []
+    for sort in (1, 0):
+        with api.Renderer(pod, abi.default_options(rng_mode=abi.RNG_PIXEL, sort_by_material=sort)) as r:
+            r.render(1, 6, 1)
+            imgs.append(r.read()[0])
+    assert_same_bits(imgs[0], imgs[1], "pixel rng: material sort on / off")
+    n = pod.n_pixels
+    host = np.zeros((n, 3), np.float32)
+    with api.MultiRenderer(pod, abi.default_options(rng_mode=abi.RNG_PIXEL, sort_by_material=0), devices=[0, 0, 0], lanes=2) as multi:
+        multi.pathtrace(1, host, None)
+        multi.pathtrace(4, host, None)
+    assert_same_bits(imgs[0], host, "pixel rng: three members, two frames")
+    # and it is a different random sequence from the reference's slot keys
+    with api.Renderer(pod, abi.default_options()) as r:
+        r.render(1, 6, 1)
+        slot = r.read()[0]
+    assert not np.array_equal(slot, imgs[0])
+
+
+def test_pixel_rng_converges_to_the_slot_keyed_image(tmp_path):
+    """north_star's gate for the second RNG mode: the converged image at equal spp reaches PSNR >= 50 dB against the
+    reference-mode (slot-keyed) image.  Two unbiased estimates with independent noise differ by MSE = 2 var / N, so the
+    PSNR must ALSO grow by ~3 dB per doubling of N -- a biased mode would level off instead.  The scene is the Cornell
+    box with the whole ceiling as a dim light (per-sample variance ~0.03, so that 50 dB is reached at ~10^4 spp; the
+    shipped scenes' small bright light needs ~10^6 spp for the same PSNR, with any RNG)."""
+    mats = [((1, 1, 1), 0, (0, 0, 0), 0, 0, 0, 0.25), scenes._WHITE, scenes._RED, scenes._GREEN, scenes._MIRROR, scenes._GLASS]
+    objs = [("cube", 0, (0, 10, 0), (0, 0, 0), (10, .3, 10))] + list(scenes._BOX[1:]) + [("sphere", 5, (-1, 4, -1), (0, 0, 0), (3, 3, 3))]
+    scenes.SCENES["_bright"] = dict(file="cornell", materials=mats, objects=objs)
+    try:
+        pod = api.Scene(scenes.write_scene("_bright", str(tmp_path / "s.txt"), width=40, height=40)).pod
+    finally:
+        del scenes.SCENES["_bright"]
+
+    def render(mode, sort, spp):
+        with api.Renderer(pod, abi.default_options(rng_mode=mode, sort_by_material=sort)) as r:
+            r.render(1, spp, 1)
+            return np.clip(r.read()[0] / np.float32(spp), 0.0, 1.0)
+
+    got = {}
+    for spp in (2048, 32768):
+        got[spp] = psnr(render(abi.RNG_SLOT, 1, spp), render(abi.RNG_PIXEL, 0, spp))
+    assert got[32768] >= 50.0, got
+    assert 9.0 <= got[32768] - got[2048] <= 15.0, got  # 16x the samples: +12 dB
