@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define B2PT_ABI_VERSION 1
+#define B2PT_ABI_VERSION 2 /* 2: B2ptScene::face_material / material_textures, B2ptLoadOverrides::per_face_materials */
 
 /* ---- error codes ------------------------------------------------------ */
 enum {
@@ -121,6 +121,18 @@ typedef struct B2ptScene {
   B2ptCamera camera;
   int32_t trace_depth; /* RenderState::traceDepth */
   int32_t iterations;  /* RenderState::iterations (informational) */
+  /* Per-face materials, optional (both NULL = the reference's behaviour).  The
+   * reference reads tinyobj's mesh.material_ids[f] and discards it
+   * (apps/src/scene.cpp:121-122): every face of an OBJ is shaded with the one
+   * material the loader appends per OBJ from MTL material 0 (:68,134,221-231).
+   *   face_material[f]         scene material of face f (n_faces entries, every
+   *                            entry in [0, n_materials))
+   *   material_textures[4*m+k] texture index (or -1) of scene material m for
+   *                            k = 0 kd, 1 ks, 2 bump, 3 ke (4*n_materials
+   *                            entries): with it an OBJ face takes its four maps
+   *                            from its material instead of from its geom */
+  const int32_t* face_material;
+  const int32_t* material_textures;
 } B2ptScene;
 
 /* ---- options ------------------------------------------------------------ */
@@ -534,6 +546,11 @@ typedef struct B2ptLoadOverrides {
   int32_t height;     /* >0 overrides RES y                                  */
   int32_t iterations; /* >0 overrides ITERATIONS                             */
   int32_t depth;      /* >0 overrides DEPTH                                  */
+  int32_t per_face_materials; /* 1: keep tinyobj's per-face material ids: every
+                         MTL material of an OBJ becomes a scene material with its
+                         own four maps (B2ptScene::face_material /
+                         material_textures); 0 (def): the reference's one material
+                         per OBJ                                               */
 } B2ptLoadOverrides;
 
 int b2pt_scene_load(const char* path, const B2ptLoadOverrides* ov, B2ptLoadedScene** out);

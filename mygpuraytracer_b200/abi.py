@@ -104,6 +104,8 @@ class Scene(C.Structure):
         ("camera", Camera),
         ("trace_depth", C.c_int32),
         ("iterations", C.c_int32),
+        ("face_material", C.POINTER(C.c_int32)),
+        ("material_textures", C.POINTER(C.c_int32)),
     ]
 
 
@@ -173,6 +175,7 @@ class LoadOverrides(C.Structure):
         ("height", C.c_int32),
         ("iterations", C.c_int32),
         ("depth", C.c_int32),
+        ("per_face_materials", C.c_int32),
     ]
 
 

@@ -95,16 +95,18 @@ class Scene:
 
     ``width``/``height``/``iterations``/``depth`` override the RES /
     ITERATIONS / DEPTH lines (every shipped scene says 800x800, 5000, 8).
+    ``per_face_materials`` keeps tinyobj's per-face material ids, which the
+    reference reads and discards (apps/src/scene.cpp:121-122).
     A :class:`Scene` can also wrap an existing :class:`PodScene`.
     """
 
     def __init__(self, filename: Optional[str] = None, *, width: int = 0, height: int = 0, iterations: int = 0,
-                 depth: int = 0, pod: Optional[PodScene] = None):
+                 depth: int = 0, per_face_materials: bool = False, pod: Optional[PodScene] = None):
         if pod is None:
             if filename is None:
                 raise ValueError("Scene needs a file name or a PodScene")
             lib = load_library()
-            ov = abi.LoadOverrides(width, height, iterations, depth)
+            ov = abi.LoadOverrides(width, height, iterations, depth, 1 if per_face_materials else 0)
             h = C.c_void_p()
             _check(lib.b2pt_scene_load(os.fsencode(filename), C.byref(ov), C.byref(h)))
             try:

@@ -498,11 +498,15 @@ static int build_mesh(B2ptCtx* c, const float* pos_host, const float* uv_host, i
 // ---------------------------------------------------------------------------------
 // create / destroy
 // ---------------------------------------------------------------------------------
-static int upload_texture(B2ptCtx* c, const B2ptScene* sc, int idx, DevTexture* out) {
+static int upload_texture(B2ptCtx* c, const B2ptScene* sc, int idx, DevTexture* out, std::vector<DevTexture>* cache) {
   out->texels = nullptr;
   out->w = out->h = out->channels = 0;
   if (idx < 0) return 0;
   if (idx >= sc->n_textures) return fail(B2PT_ERR_INVALID, "texture index out of range");
+  if (cache && (*cache)[(size_t)idx].texels) {  // several materials / geoms may name the same map
+    *out = (*cache)[(size_t)idx];
+    return 0;
+  }
   const B2ptTexture& t = sc->textures[idx];
   if (t.channels == 0 || t.texels == nullptr) return 0;
   if (t.channels < 3 || t.width <= 0 || t.height <= 0)
@@ -516,6 +520,7 @@ static int upload_texture(B2ptCtx* c, const B2ptScene* sc, int idx, DevTexture* 
   out->w = t.width;
   out->h = t.height;
   out->channels = t.channels;
+  if (cache) (*cache)[(size_t)idx] = *out;
   return 0;
 }
 
@@ -602,6 +607,17 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
   // ---- geoms, meshes, textures -----------------------------------------------------
   std::vector<DevGeom> hg(sc->n_geoms);
   std::vector<DevMesh> hm;
+  std::vector<DevTexture> tex_cache((size_t)std::max(sc->n_textures, 0));
+  for (DevTexture& t : tex_cache) t.texels = nullptr;
+  // per-face materials (B2ptScene::face_material): one device copy of the ids, every mesh points at its faces
+  int* face_mat_dev = nullptr;
+  if (sc->face_material && sc->n_faces > 0) {
+    for (int f = 0; f < sc->n_faces; ++f)
+      if (sc->face_material[f] < 0 || sc->face_material[f] >= sc->n_materials)
+        return fail(B2PT_ERR_INVALID, "face_material entry out of range");
+    if ((rc = c->dalloc(&face_mat_dev, (size_t)sc->n_faces))) return rc;
+    CK(cudaMemcpyAsync(face_mat_dev, sc->face_material, (size_t)sc->n_faces * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  }
   c->geom_mesh.assign(sc->n_geoms, -1);
   for (int g = 0; g < sc->n_geoms; ++g) {
     const B2ptGeom& G = sc->geoms[g];
@@ -652,10 +668,11 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
       M.n_faces = G.face_count;
       M.root = mb.root;
       M.geom = g;
-      if ((rc = upload_texture(c, sc, G.tex_kd, &M.kd))) return rc;
-      if ((rc = upload_texture(c, sc, G.tex_ks, &M.ks))) return rc;
-      if ((rc = upload_texture(c, sc, G.tex_bump, &M.bump))) return rc;
-      if ((rc = upload_texture(c, sc, G.tex_ke, &M.ke))) return rc;
+      M.face_mat = face_mat_dev ? face_mat_dev + G.face_begin : nullptr;
+      if ((rc = upload_texture(c, sc, G.tex_kd, &M.kd, &tex_cache))) return rc;
+      if ((rc = upload_texture(c, sc, G.tex_ks, &M.ks, &tex_cache))) return rc;
+      if ((rc = upload_texture(c, sc, G.tex_bump, &M.bump, &tex_cache))) return rc;
+      if ((rc = upload_texture(c, sc, G.tex_ke, &M.ke, &tex_cache))) return rc;
       D.mesh = (int)hm.size();
       c->geom_mesh[g] = D.mesh;
       hm.push_back(M);
@@ -688,9 +705,19 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
   if (!hm.empty()) CK(cudaMemcpyAsync(dm, hm.data(), hm.size() * sizeof(DevMesh), cudaMemcpyHostToDevice, c->stream));
   static_assert(sizeof(DevMaterial) == sizeof(B2ptMaterial), "material layout");
   CK(cudaMemcpyAsync(dmat, sc->materials, (size_t)sc->n_materials * sizeof(DevMaterial), cudaMemcpyHostToDevice, c->stream));
+  DevTexture* dmt = nullptr;
+  if (sc->material_textures) {  // the four maps of every material (kd, ks, bump, ke)
+    std::vector<DevTexture> hmt(4 * (size_t)sc->n_materials);
+    for (size_t k = 0; k < hmt.size(); ++k)
+      if ((rc = upload_texture(c, sc, sc->material_textures[k], &hmt[k], &tex_cache))) return rc;
+    if ((rc = c->dalloc(&dmt, hmt.size()))) return rc;
+    CK(cudaMemcpyAsync(dmt, hmt.data(), hmt.size() * sizeof(DevTexture), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));  // hmt is a local
+  }
   c->dscene.geoms = dg;
   c->dscene.meshes = dm;
   c->dscene.materials = dmat;
+  c->dscene.mat_tex = dmt;
   c->dscene.n_geoms = sc->n_geoms;
   c->dscene.n_meshes = (int)hm.size();
   c->dscene.n_materials = sc->n_materials;

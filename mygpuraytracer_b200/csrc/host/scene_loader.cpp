@@ -21,6 +21,7 @@
 #include <fstream>
 #include <sstream>
 #include <limits>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -47,6 +48,9 @@ struct B2ptLoadedScene {
   std::vector<LoadedTexture> tex_store;
   std::vector<B2ptTexture> textures;
   std::vector<float> face_pos, face_uv;
+  bool per_face_materials = false;           // B2ptLoadOverrides::per_face_materials
+  std::vector<int32_t> face_material;        // [n_faces] when per_face_materials
+  std::vector<int32_t> material_textures;    // [4 * n_materials] (kd, ks, bump, ke) when per_face_materials
   B2ptScene view{};
   std::string image_name;
   std::string scene_dir;
@@ -128,6 +132,7 @@ struct MtlInfo {
   float kd[3] = {0, 0, 0}, ks[3] = {0, 0, 0}, ke[3] = {0, 0, 0};  // tinyobjloader 2.0.0 starts every material at zero
   float ior = 1.0f;
   std::string map_kd, map_ks, map_ke, map_bump;
+  std::string name;
   bool found = false;
 };
 
@@ -162,9 +167,10 @@ static std::string texture_name_of(const std::string& args) {
   }
 }
 
-// First material of an MTL file (the reference uses objMaterials[0] only, scene.cpp:68,134).
-MtlInfo parse_first_mtl(const std::string& path) {
-  MtlInfo m;
+// The materials of an MTL file in file order (the reference uses objMaterials[0] only, scene.cpp:68,134; the others
+// matter with B2ptLoadOverrides::per_face_materials).
+std::vector<MtlInfo> parse_mtl(const std::string& path) {
+  std::vector<MtlInfo> all;
   std::ifstream f(path.c_str());
   std::string line;
   int count = 0;
@@ -174,11 +180,14 @@ MtlInfo parse_first_mtl(const std::string& path) {
     std::vector<std::string> tk = tokens_of(t);
     const std::string& k = tk[0];
     if (k == "newmtl") {
-      if (++count > 1) break;
-      m.found = true;
+      ++count;
+      all.emplace_back();
+      all.back().found = true;
+      all.back().name = trim(t.substr(k.size()));
       continue;
     }
-    if (count != 1) continue;
+    if (count < 1) continue;
+    MtlInfo& m = all.back();
     auto rest = [&]() { return slashes(trim(texture_name_of(t.substr(k.size())))); };
     auto f3 = [&](float* o) {
       for (int i = 0; i < 3 && i + 1 < (int)tk.size(); ++i) o[i] = (float)atof(tk[i + 1].c_str());
@@ -192,7 +201,7 @@ MtlInfo parse_first_mtl(const std::string& path) {
     else if (k == "map_Ke") m.map_ke = rest();
     else if (k == "map_Bump" || k == "map_bump" || k == "bump") m.map_bump = rest();
   }
-  return m;
+  return all;
 }
 
 struct ObjIndex {
@@ -243,10 +252,17 @@ int load_obj(B2ptLoadedScene* S, const std::string& obj_path, const std::vector<
   std::ifstream f(path.c_str());
   std::vector<float> v, vt;
   int nvn = 0;
-  std::string mtllib;
   std::string line;
+  // materials accumulate over the mtllib statements, a usemtl is resolved against what has been loaded when it is
+  // read, an unknown name means "no material" (-1): tinyobjloader 2.0.0, apps/src/tiny_obj_loader.h:2729-2810
+  std::vector<MtlInfo> mtls;
+  std::map<std::string, int> mtl_index;
+  std::vector<std::string> tex_dirs = search;
+  int cur_mat = -1;
+  std::vector<int> face_mids;  // tinyobj's mesh.material_ids, one per emitted triangle
   g->face_begin = (int)(S->face_pos.size() / 9);
   auto emit = [&](const ObjIndex& a, const ObjIndex& b, const ObjIndex& c) {
+    face_mids.push_back(cur_mat);
     const ObjIndex* t[3] = {&a, &b, &c};
     for (int k = 0; k < 3; ++k) {
       for (int j = 0; j < 3; ++j) S->face_pos.push_back(v[3 * (size_t)t[k]->v + j]);
@@ -374,33 +390,41 @@ int load_obj(B2ptLoadedScene* S, const std::string& obj_path, const std::vector<
         }
         if (rest.size() == 3) emit(rest[0], rest[1], rest[2]);
       }
-    } else if (strncmp(p, "mtllib", 6) == 0) {
-      mtllib = trim(std::string(p + 6));
+    } else if (strncmp(p, "usemtl", 6) == 0) {
+      const std::vector<std::string> tk = tokens_of(p + 6);
+      const auto it = tk.empty() ? mtl_index.end() : mtl_index.find(tk[0]);
+      cur_mat = it == mtl_index.end() ? -1 : it->second;
+    } else if (strncmp(p, "mtllib", 6) == 0 && (p[6] == ' ' || p[6] == '\t')) {
+      const std::string mtllib = trim(std::string(p + 6));
+      if (mtllib.empty()) continue;
+      std::vector<std::string> mdirs = {dir_of(path) + "/materials", dir_of(path), "../models/materials"};
+      for (const std::string& d : search) mdirs.push_back(d);
+      // `mtllib a.mtl b.mtl`: tinyobjloader splits the statement at blanks and takes the first file that loads
+      // (apps/src/tiny_obj_loader.h:2761-2806); a name that exists as written (blanks and all) is tried first
+      std::vector<std::string> names = {mtllib};
+      for (const std::string& n : tokens_of(mtllib)) names.push_back(n);
+      for (const std::string& n : names) {
+        const std::string mp = find_file(slashes(n), mdirs);
+        if (mp.empty()) continue;
+        for (MtlInfo& mi : parse_mtl(mp)) {
+          mtl_index.insert(std::make_pair(mi.name, (int)mtls.size()));  // the first definition of a name wins
+          mtls.push_back(std::move(mi));
+        }
+        tex_dirs.push_back(dir_of(mp));
+        break;
+      }
     }
   }
   g->face_count = (int)(S->face_pos.size() / 9) - g->face_begin;
 
-  // material + textures of the first MTL material
-  MtlInfo mtl;
-  std::vector<std::string> tex_dirs = search;
-  if (!mtllib.empty()) {
-    std::vector<std::string> mdirs = {dir_of(path) + "/materials", dir_of(path), "../models/materials"};
-    for (const std::string& d : search) mdirs.push_back(d);
-    // `mtllib a.mtl b.mtl`: tinyobjloader splits the statement at blanks and takes the first file that loads
-    // (apps/src/tiny_obj_loader.h, "mtllib"); a name that exists as written (blanks and all) is tried first
-    std::vector<std::string> names = {mtllib};
-    for (const std::string& n : tokens_of(mtllib)) names.push_back(n);
-    for (const std::string& n : names) {
-      const std::string mp = find_file(slashes(n), mdirs);
-      if (mp.empty()) continue;
-      mtl = parse_first_mtl(mp);
-      tex_dirs.push_back(dir_of(mp));
-      break;
-    }
-  }
+  // material + textures of the first MTL material (objMaterials[0], scene.cpp:68,134)
+  const MtlInfo mtl = mtls.empty() ? MtlInfo() : mtls[0];
   tex_dirs.push_back(dir_of(path));
+  std::map<std::string, int> tex_cache;  // several materials may name the same file
   auto load_tex = [&](const std::string& name) -> int {
     if (name.empty()) return -1;
+    const auto hit = tex_cache.find(name);
+    if (hit != tex_cache.end()) return hit->second;
     std::string tp = find_file(name, tex_dirs);
     LoadedTexture t;
     if (tp.empty() || !decode_image_file(tp, /*flip_vertically=*/true, &t.w, &t.h, &t.c, &t.texels)) {
@@ -408,6 +432,7 @@ int load_obj(B2ptLoadedScene* S, const std::string& obj_path, const std::vector<
       return -1;
     }
     S->tex_store.push_back(std::move(t));
+    tex_cache[name] = (int)S->tex_store.size() - 1;
     return (int)S->tex_store.size() - 1;
   };
   g->tex_kd = load_tex(mtl.map_kd);
@@ -416,19 +441,37 @@ int load_obj(B2ptLoadedScene* S, const std::string& obj_path, const std::vector<
   g->tex_ke = load_tex(mtl.map_ke);
 
   // "New material for this object", scene.cpp:220-231
-  B2ptMaterial m;
-  memset(&m, 0, sizeof m);
-  for (int k = 0; k < 3; ++k) {
-    m.specular_color[k] = mtl.ks[k];
-    m.color[k] = mtl.kd[k];
+  auto scene_material = [](const MtlInfo& mi) {
+    B2ptMaterial m;
+    memset(&m, 0, sizeof m);
+    for (int k = 0; k < 3; ++k) {
+      m.specular_color[k] = mi.ks[k];
+      m.color[k] = mi.kd[k];
+    }
+    m.specular_exponent = 0.0f;
+    m.index_of_refraction = mi.ior;
+    m.emittance = mi.ke[0];
+    m.has_reflective = 0.0f;
+    m.has_refractive = 0.0f;
+    return m;
+  };
+  const int base = (int)S->materials.size();
+  S->materials.push_back(scene_material(mtl));
+  g->material_id = base;
+  if (S->per_face_materials) {
+    // Every MTL material becomes a scene material with its own four maps, converted the way the reference converts
+    // material 0; a face without a (known) usemtl takes material 0, the one the reference shades everything with.
+    S->material_textures.resize(4 * (size_t)base, -1);
+    const int tex0[4] = {g->tex_kd, g->tex_ks, g->tex_bump, g->tex_ke};
+    S->material_textures.insert(S->material_textures.end(), tex0, tex0 + 4);
+    for (size_t k = 1; k < mtls.size(); ++k) {
+      S->materials.push_back(scene_material(mtls[k]));
+      const int tx[4] = {load_tex(mtls[k].map_kd), load_tex(mtls[k].map_ks), load_tex(mtls[k].map_bump), load_tex(mtls[k].map_ke)};
+      S->material_textures.insert(S->material_textures.end(), tx, tx + 4);
+    }
+    S->face_material.resize((size_t)g->face_begin, 0);
+    for (int mid : face_mids) S->face_material.push_back(base + ((mid > 0 && mid < (int)mtls.size()) ? mid : 0));
   }
-  m.specular_exponent = 0.0f;
-  m.index_of_refraction = mtl.ior;
-  m.emittance = mtl.ke[0];
-  m.has_reflective = 0.0f;
-  m.has_refractive = 0.0f;
-  S->materials.push_back(m);
-  g->material_id = (int)S->materials.size() - 1;
   return 0;
 }
 
@@ -440,6 +483,7 @@ extern "C" int b2pt_scene_load(const char* path, const B2ptLoadOverrides* ov, B2
   std::ifstream in(path);
   if (!in.is_open()) return fail(B2PT_ERR_IO, std::string("cannot open scene file ") + path);
   B2ptLoadedScene* S = new B2ptLoadedScene();
+  S->per_face_materials = ov && ov->per_face_materials != 0;
   S->scene_dir = dir_of(path);
   const std::vector<std::string> search = {S->scene_dir, S->scene_dir + "/../bin", "."};
   B2ptCamera cam;
@@ -624,6 +668,14 @@ extern "C" int b2pt_scene_load(const char* path, const B2ptLoadOverrides* ov, B2
   V.camera = cam;
   V.trace_depth = trace_depth;
   V.iterations = iterations;
+  V.face_material = nullptr;
+  V.material_textures = nullptr;
+  if (S->per_face_materials) {
+    S->face_material.resize((size_t)V.n_faces, 0);
+    S->material_textures.resize(4 * (size_t)V.n_materials, -1);
+    V.face_material = S->face_material.data();
+    V.material_textures = S->material_textures.data();
+  }
   *out = S;
   return 0;
 }

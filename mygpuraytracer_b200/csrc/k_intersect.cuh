@@ -120,6 +120,17 @@ __device__ __forceinline__ V3 fetch_texel(const DevTexture& tx, float u, float v
   return mk((float)r / 255.f, (float)g / 255.f, (float)b / 255.f);
 }
 
+// The material of a mesh face and the four maps of an OBJ hit.  The reference has one material per OBJ and
+// keeps the maps in the geom (apps/src/scene.cpp:134-231); with per-face materials (B2ptScene::face_material /
+// material_textures, an extension: the reference discards tinyobj's ids, scene.cpp:121-122) both come from the
+// face that was hit.  which: 0 kd, 1 ks, 2 bump, 3 ke.
+__device__ __forceinline__ int mesh_face_material(const int* __restrict__ face_mat, int face, int geom_material) {
+  return face_mat ? __ldg(face_mat + face) : geom_material;
+}
+__device__ __forceinline__ const DevTexture& obj_tex(const DevScene& sc, const DevMesh& M, int material, int which) {
+  return sc.mat_tex ? sc.mat_tex[4 * material + which] : (&M.kd)[which];
+}
+
 // boxIntersectionTest, apps/src/intersections.h:48-90.  Returns the world-space
 // distance (or -1) and the object-space axis normal of the face that was hit.
 __device__ __forceinline__ float box_exact(const DevGeom& G, V3 o, V3 d, V3* axis_normal) {
@@ -211,8 +222,8 @@ __device__ __forceinline__ bool may_beat(const DevGeom& G, V3 id, V3 noid, float
 
 // The mesh part of the winner's record: uv, geometric normal, bump map
 // (apps/src/intersections.h:226,235-279).
-__device__ __forceinline__ void mesh_record(const DevGeom& G, const DevMesh& M, int face, float bu, float bv, V3* nrm_out,
-                                            float* tu_out, float* tv_out) {
+__device__ __forceinline__ void mesh_record(const DevGeom& G, const DevMesh& M, const DevTexture& bump, int face, float bu,
+                                            float bv, V3* nrm_out, float* tu_out, float* tv_out) {
   const float* fp = M.face_pos + 9 * (size_t)face;
   const float* fu = M.face_uv + 6 * (size_t)face;
   const V3 v0 = mk(__ldg(fp), __ldg(fp + 1), __ldg(fp + 2));
@@ -225,7 +236,7 @@ __device__ __forceinline__ void mesh_record(const DevGeom& G, const DevMesh& M, 
   const float tv = (w * u0y + bu * u1y) + bv * u2y;
   const V3 e1 = v1 - v0, e2 = v2 - v0;
   V3 nrm = normalize(xform(G.invT, normalize(cross(e1, e2)), 0.0f));
-  if (M.bump.channels) {
+  if (bump.channels) {
     const float d1x = u1x - u0x, d1y = u1y - u0y, d2x = u2x - u0x, d2y = u2y - u0y;
     const float f = 1.0f / (d1x * d2y - d2x * d1y);
     V3 tang = mk(f * (d2y * e1.x - d1y * e2.x), f * (d2y * e1.y - d1y * e2.y), f * (d2y * e1.z - d1y * e2.z));
@@ -234,7 +245,7 @@ __device__ __forceinline__ void mesh_record(const DevGeom& G, const DevMesh& M, 
     bit = normalize(bit);
     const V3 T = normalize(xform(G.fwd, tang, 0.0f));
     const V3 B = normalize(xform(G.fwd, bit, 0.0f));
-    V3 tsn = normalize(fetch_texel(M.bump, tu, tv));
+    V3 tsn = normalize(fetch_texel(bump, tu, tv));
     tsn = normalize(mk(tsn.x * 2.0f - 1.0f, tsn.y * 2.0f - 1.0f, tsn.z * 2.0f - 1.0f));
     nrm = normalize(mk((T.x * tsn.x + B.x * tsn.y) + nrm.x * tsn.z, (T.y * tsn.x + B.y * tsn.y) + nrm.y * tsn.z,
                        (T.z * tsn.x + B.z * tsn.y) + nrm.z * tsn.z));
@@ -478,8 +489,8 @@ __global__ void __launch_bounds__(kIsectThreads, 3) k_intersect_mesh_brute(Isect
         const DevGeom& G = sgeom[mhit];
         V3 nrm;
         float tu, tv;
-        mesh_record(G, p.scene.meshes[G.mesh], mface, mbu, mbv, &nrm, &tu, &tv);
-        const int mat = G.material;
+        const int mat = mesh_face_material(p.scene.meshes[G.mesh].face_mat, mface, G.material);
+        mesh_record(G, p.scene.meshes[G.mesh], obj_tex(p.scene, p.scene.meshes[G.mesh], mat, 2), mface, mbu, mbv, &nrm, &tu, &tv);
         p.out.h0[i] = make_float4(t_min, nrm.x, nrm.y, nrm.z);
         p.out.h1[i] = make_float4(tu, tv, __int_as_float((mhit & 0xffff) | (mat << 16)), __int_as_float(mface));
         p.key[i] = (uint8_t)mat;
@@ -488,8 +499,9 @@ __global__ void __launch_bounds__(kIsectThreads, 3) k_intersect_mesh_brute(Isect
         bool emissive = false;
         const DevMaterial& mm = p.scene.materials[mat];
         // scatterRay only looks at the emission map in its OBJ branch (not reflective, not refractive)
-        if (MM.ke.channels && !(__ldg(&mm.has_reflective) > 0) && !(__ldg(&mm.has_refractive) > 0)) {
-          const V3 e = fetch_texel(MM.ke, tu, tv);
+        const DevTexture& ke = obj_tex(p.scene, MM, mat, 3);
+        if (ke.channels && !(__ldg(&mm.has_reflective) > 0) && !(__ldg(&mm.has_refractive) > 0)) {
+          const V3 e = fetch_texel(ke, tu, tv);
           emissive = e.x > FLT_EPSILON || e.y > FLT_EPSILON || e.z > FLT_EPSILON;
         }
         const bool survives = will_survive(p.scene.materials, mat, __float_as_int(b.w), emissive);

@@ -123,12 +123,14 @@ __device__ __forceinline__ void shade_slot(const ShadeParams& p, int j, int iter
       const DevGeom& G = p.scene.geoms[geom_id];
       if (G.type == 3) {
         const DevMesh& M = p.scene.meshes[G.mesh];
+        const DevTexture& ke = obj_tex(p.scene, M, mat_id, 3);
+        const DevTexture& kd = obj_tex(p.scene, M, mat_id, 0);
         V3 emission = mk(0, 0, 0);
-        if (M.ke.channels) emission = fetch_texel(M.ke, tu, tv);
+        if (ke.channels) emission = fetch_texel(ke, tu, tv);
         if (emission.x > FLT_EPSILON || emission.y > FLT_EPSILON || emission.z > FLT_EPSILON) {
           a = emission * 5.0f;
-        } else if (M.kd.channels) {
-          a = fetch_texel(M.kd, tu, tv);
+        } else if (kd.channels) {
+          a = fetch_texel(kd, tu, tv);
         }
       } else if (m.emittance > 0.0f) {
         a = a * m.emittance;
@@ -196,8 +198,9 @@ __device__ __forceinline__ void shade_slot(const ShadeParams& p, int j, int iter
         const DevGeom& G = p.scene.geoms[geom_id];
         if (G.type == 3) {
           const DevMesh& M = p.scene.meshes[G.mesh];
+          const DevTexture& ke = obj_tex(p.scene, M, mat_id, 3);
           V3 emission = mk(0, 0, 0);
-          if (M.ke.channels) emission = fetch_texel(M.ke, tu, tv);
+          if (ke.channels) emission = fetch_texel(ke, tu, tv);
           if (emission.x > FLT_EPSILON || emission.y > FLT_EPSILON || emission.z > FLT_EPSILON) {
             col = mulv(col, emission * 5.0f);
             bounces = 1;  // interactions.h:184; decremented to 0 below
@@ -211,13 +214,15 @@ __device__ __forceinline__ void shade_slot(const ShadeParams& p, int j, int iter
             const float rnd = rng_uniform(rng, 0.0f, 1.0f);
             if (rnd < coeff) {
               const V3 rdir = reflect(d, nrm);
-              V3 sc = M.ks.channels ? fetch_texel(M.ks, tu, tv) : scol;
+              const DevTexture& ks = obj_tex(p.scene, M, mat_id, 1);
+              V3 sc = ks.channels ? fetch_texel(ks, tu, tv) : scol;
               sc = sc * 1.0f;  // spec = pow(x, 0.0f) == 1, interactions.h:204,214
               col = mulv(col, sc);
               o = x + nrm * 0.01f;
               d = rdir;
             } else {
-              const V3 dc = M.kd.channels ? fetch_texel(M.kd, tu, tv) : mcol;
+              const DevTexture& kd = obj_tex(p.scene, M, mat_id, 0);
+              const V3 dc = kd.channels ? fetch_texel(kd, tu, tv) : mcol;
               col = mulv(col, dc);
               d = hemisphere<TRIG>(nrm, rng);
               o = x + d * 0.01f;

@@ -150,6 +150,7 @@ __device__ __forceinline__ float leaf_exact(const float4* __restrict__ tris, int
 struct WalkMesh {  // what the walk keeps of a mesh in shared memory
   const float4* nodes;
   const float4* tris;
+  const int* face_mat;
   int root, geom;
 };
 
@@ -183,6 +184,7 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkMinBlocks) k_mesh_walk(Isec
       const DevMesh& M = p.scene.meshes[tid];
       smesh[tid].nodes = M.nodes;
       smesh[tid].tris = M.tris;
+      smesh[tid].face_mat = M.face_mat;
       smesh[tid].root = M.root;
       smesh[tid].geom = M.geom;
     }
@@ -208,6 +210,7 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkMinBlocks) k_mesh_walk(Isec
   int best = -1;
   float t_min = FLT_MAX;  // closest hit so far over all geoms (analytic + meshes already walked)
   int hit = kNoGeom;
+  int old_material = 0;   // ... and its material (the one the histograms counted this ray under)
   int steps = 0;
   bool handed = false, was_live = false;
   V3 wo = mk(0, 0, 0), wd = mk(0, 0, 1);  // the ray in world space (read again only when there are several meshes)
@@ -287,8 +290,9 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkMinBlocks) k_mesh_walk(Isec
         if (STATS) ++s_walks;
         if (!handed && mesh_wins(R.tbest, best, g, t_min, hit)) {
           // the mesh is the closest geom so far: (t, barycentrics, face) into the record, k_mesh_finish does the rest
-          const int old_mat = hit == kNoGeom ? 0 : smat[hit];
-          const int mat = smat[g];
+          // (the record this fold replaces is an analytic geom's or an earlier mesh's: its material is in the record)
+          const int old_mat = hit == kNoGeom ? 0 : old_material;
+          const int mat = mesh_face_material(m < kWalkMeshes ? smesh[m].face_mat : p.scene.meshes[m].face_mat, best, smat[g]);
           if (mat != old_mat) {
             atomicAdd(&shist[mat], 1);
             atomicSub(&shist[old_mat], 1);
@@ -303,6 +307,7 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkMinBlocks) k_mesh_walk(Isec
           p.out.h1[ray] = make_float4(bu, bv, __int_as_float((g & 0xffff) | (mat << 16)), __int_as_float(best));
           t_min = R.tbest;
           hit = g;
+          old_material = mat;
         }
         // a handed-off ray is finished by k_mesh_walk_long, meshes included
         if (handed || m + 1 >= n_meshes || !setup(m + 1)) ray = -1;
@@ -331,6 +336,7 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkMinBlocks) k_mesh_walk(Isec
             wd = mk(b.x, b.y, b.z);
             t_min = b.w > 0.0f ? b.w : FLT_MAX;
             hit = b.w > 0.0f ? (__float_as_int(c.x) & 0xffff) : kNoGeom;
+            old_material = b.w > 0.0f ? ((__float_as_int(c.x) >> 16) & 0xffff) : 0;
             was_live = __float_as_int(c.y) != 0;
             handed = false;
             if (!setup(0)) ray = -1;
@@ -475,7 +481,7 @@ __global__ void __launch_bounds__(kCoopThreads) k_mesh_walk_long(IsectParams p) 
   const int n_meshes = p.scene.n_meshes;
 
   // ---- group state (replicated in the lanes of the group) ----
-  int ray = -1, m = 0, g = 0, hit = kNoGeom, sp = 0, best = -1;
+  int ray = -1, m = 0, g = 0, hit = kNoGeom, old_material = 0, sp = 0, best = -1;
   float t_min = FLT_MAX, bu = 0.0f, bv = 0.0f;
   WalkRay R;
   R.qo = R.qd = R.id = R.noid = mk(0, 0, 1);
@@ -490,9 +496,9 @@ __global__ void __launch_bounds__(kCoopThreads) k_mesh_walk_long(IsectParams p) 
     if (sp == 0) {  // group-uniform: fold the finished walk, go on with the ray's next mesh or fetch the next job
       if (ray >= 0) {
         if (mesh_wins(R.tbest, best, g, t_min, hit)) {
+          const int old_mat = hit == kNoGeom ? 0 : old_material;
+          const int mat = mesh_face_material(p.scene.meshes[m].face_mat, best, p.scene.geoms[g].material);
           if (gl == 0) {
-            const int old_mat = hit == kNoGeom ? 0 : p.scene.geoms[hit].material;
-            const int mat = p.scene.geoms[g].material;
             if (mat != old_mat) {
               atomicAdd(&p.ctr->hist[p.depth][mat], 1u);
               atomicSub(&p.ctr->hist[p.depth][old_mat], 1u);
@@ -507,6 +513,7 @@ __global__ void __launch_bounds__(kCoopThreads) k_mesh_walk_long(IsectParams p) 
           }
           t_min = R.tbest;
           hit = g;
+          old_material = mat;
         }
         // the ray's remaining meshes (k_mesh_walk dropped the ray when it handed the walk off)
         bool more = false;
@@ -548,6 +555,7 @@ __global__ void __launch_bounds__(kCoopThreads) k_mesh_walk_long(IsectParams p) 
           const int gm0 = __float_as_int(p.out.h1[ray].z);
           t_min = t0 > 0.0f ? t0 : FLT_MAX;
           hit = t0 > 0.0f ? (gm0 & 0xffff) : kNoGeom;
+          old_material = t0 > 0.0f ? ((gm0 >> 16) & 0xffff) : 0;
           wo = mk(a.x, a.y, a.z);
           wd = mk(b.x, b.y, b.z);
           walk_ray_setup(G, wo, wd, t_min, &R);
@@ -670,15 +678,16 @@ __global__ void __launch_bounds__(256) k_mesh_finish(IsectParams p) {
     const float t = reinterpret_cast<const float*>(p.out.h0 + i)[0];
     V3 nrm;
     float tu, tv;
-    mesh_record(G, M, face, h1.x, h1.y, &nrm, &tu, &tv);
+    mesh_record(G, M, obj_tex(p.scene, M, mat, 2), face, h1.x, h1.y, &nrm, &tu, &tv);
     p.out.h0[i] = make_float4(t, nrm.x, nrm.y, nrm.z);
     p.out.h1[i] = make_float4(tu, tv, h1.z, h1.w);
     // survival: an emissive texel turns the hit into a light (interactions.h:171-186);
     // scatterRay only looks at the emission map in its OBJ branch (not reflective, not refractive)
     bool emissive = false;
     const DevMaterial& mm = p.scene.materials[mat];
-    if (M.ke.channels && !(__ldg(&mm.has_reflective) > 0) && !(__ldg(&mm.has_refractive) > 0)) {
-      const V3 e = fetch_texel(M.ke, tu, tv);
+    const DevTexture& ke = obj_tex(p.scene, M, mat, 3);
+    if (ke.channels && !(__ldg(&mm.has_reflective) > 0) && !(__ldg(&mm.has_refractive) > 0)) {
+      const V3 e = fetch_texel(ke, tu, tv);
       emissive = e.x > FLT_EPSILON || e.y > FLT_EPSILON || e.z > FLT_EPSILON;
     }
     const int bounces = __float_as_int(p.in.s1[i].w);

@@ -66,7 +66,8 @@ struct DevMesh {
   int root;  // 0: the root node; < 0: a leaf code (a mesh of at most kLeafTris triangles has no nodes)
   int geom;  // the geom this mesh belongs to (meshes are numbered in geom order)
   int pad_;
-  DevTexture kd, ks, bump, ke;
+  const int* face_mat;  // scene material of every face (B2ptScene::face_material), or NULL: the geom's material
+  DevTexture kd, ks, bump, ke;  // the geom's four maps, in this order (obj_tex indexes them)
 };
 
 struct DevMaterial {  // Material, apps/src/sceneStructs.h:72-82
@@ -89,6 +90,7 @@ struct DevScene {
   const DevGeom* geoms;
   const DevMesh* meshes;
   const DevMaterial* materials;
+  const DevTexture* mat_tex;  // [4 * n_materials] (kd, ks, bump, ke) per material (B2ptScene::material_textures), or NULL
   int n_geoms, n_meshes, n_materials;
 };
 

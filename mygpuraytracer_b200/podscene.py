@@ -16,13 +16,14 @@ Layout of ``.b2s`` (little endian)::
     B2ptMaterial materials[n_materials]
     per texture: int32 w, h, channels, reserved; uint8 texels[w*h*channels]
     float face_pos[n_faces*9]; float face_uv[n_faces*6]
+    optional: char tag[4] = "PFM1"; int32 face_material[n_faces]; int32 material_textures[4*n_materials]
 """
 from __future__ import annotations
 
 import ctypes as C
 import struct
 from dataclasses import dataclass, field
-from typing import List
+from typing import List, Optional
 
 import numpy as np
 
@@ -81,6 +82,8 @@ class PodScene:
     face_uv: np.ndarray = field(default_factory=lambda: np.zeros((0, 6), np.float32))
     trace_depth: int = 8
     iterations: int = 1
+    face_material: Optional[np.ndarray] = None      # int32[n_faces] or None (the reference: one material per OBJ)
+    material_textures: Optional[np.ndarray] = None  # int32[n_materials, 4] (kd, ks, bump, ke) or None
 
     # -- convenience -----------------------------------------------------------
     @property
@@ -99,6 +102,8 @@ class PodScene:
         return PodScene(
             self.geoms.copy(), self.materials.copy(), self.camera.copy(), [t.copy() for t in self.textures],
             self.face_pos.copy(), self.face_uv.copy(), self.trace_depth, self.iterations,
+            None if self.face_material is None else self.face_material.copy(),
+            None if self.material_textures is None else self.material_textures.copy(),
         )
 
     # -- ctypes view -------------------------------------------------------------
@@ -128,6 +133,12 @@ class PodScene:
         C.memmove(C.byref(s.camera), self.camera.ctypes.data, C.sizeof(abi.Camera))
         s.trace_depth = int(self.trace_depth)
         s.iterations = int(self.iterations)
+        if self.face_material is not None:
+            self.face_material = np.ascontiguousarray(self.face_material, np.int32).reshape(-1)
+            s.face_material = C.cast(self.face_material.ctypes.data, C.POINTER(C.c_int32))
+        if self.material_textures is not None:
+            self.material_textures = np.ascontiguousarray(self.material_textures, np.int32).reshape(-1, 4)
+            s.material_textures = C.cast(self.material_textures.ctypes.data, C.POINTER(C.c_int32))
         s._keepalive = (self, tex)  # noqa: SLF001 - pin the backing storage
         return s
 
@@ -156,9 +167,16 @@ class PodScene:
         off += nf * 36
         uv = np.frombuffer(buf, "<f4", nf * 6, off).reshape(nf, 6).copy()
         off += nf * 24
+        fm = mt = None
+        if buf[off:off + 4] == b"PFM1":
+            off += 4
+            fm = np.frombuffer(buf, "<i4", nf, off).copy()
+            off += 4 * nf
+            mt = np.frombuffer(buf, "<i4", 4 * nm, off).reshape(nm, 4).copy()
+            off += 16 * nm
         if off != len(buf):
             raise ValueError(f"{path}: trailing bytes ({len(buf) - off})")
-        return PodScene(geoms, mats, cam, texs, pos, uv, depth, iters)
+        return PodScene(geoms, mats, cam, texs, pos, uv, depth, iters, fm, mt)
 
     def save(self, path: str) -> None:
         with open(path, "wb") as f:
@@ -174,6 +192,10 @@ class PodScene:
                 f.write(np.ascontiguousarray(t, np.uint8).tobytes())
             f.write(np.ascontiguousarray(self.face_pos, "<f4").tobytes())
             f.write(np.ascontiguousarray(self.face_uv, "<f4").tobytes())
+            if self.face_material is not None and self.material_textures is not None:
+                f.write(b"PFM1")
+                f.write(np.ascontiguousarray(self.face_material, "<i4").tobytes())
+                f.write(np.ascontiguousarray(self.material_textures, "<i4").tobytes())
 
     @staticmethod
     def from_ctypes(s: abi.Scene) -> "PodScene":
@@ -192,4 +214,7 @@ class PodScene:
         nf = s.n_faces
         pos = np.ctypeslib.as_array(s.face_pos, (nf * 9,)).reshape(nf, 9).copy() if nf else np.zeros((0, 9), np.float32)
         uv = np.ctypeslib.as_array(s.face_uv, (nf * 6,)).reshape(nf, 6).copy() if nf else np.zeros((0, 6), np.float32)
-        return PodScene(geoms, mats, cam, texs, pos, uv, s.trace_depth, s.iterations)
+        fm = np.ctypeslib.as_array(s.face_material, (nf,)).copy() if (s.face_material and nf) else None
+        mt = (np.ctypeslib.as_array(s.material_textures, (s.n_materials * 4,)).reshape(-1, 4).copy()
+              if s.material_textures else None)
+        return PodScene(geoms, mats, cam, texs, pos, uv, s.trace_depth, s.iterations, fm, mt)

@@ -270,6 +270,20 @@ static inline const B2ptTexture* geom_tex(const B2ptScene* s, int32_t idx) {
   return t->channels ? t : NULL;
 }
 
+/* The four maps of an OBJ hit: the reference takes them from the geom (one material per OBJ,
+ * apps/src/scene.cpp:134-231).  With B2ptScene::material_textures (per-face materials, an extension the
+ * reference does not have: it discards tinyobj's material_ids, scene.cpp:121-122) they come from the
+ * material of the face that was hit.  which: 0 kd, 1 ks, 2 bump, 3 ke. */
+static inline const B2ptTexture* obj_tex(const B2ptScene* s, const B2ptGeom* g, int32_t material, int which) {
+  if (s->material_textures && material >= 0 && material < s->n_materials)
+    return geom_tex(s, s->material_textures[4 * (size_t)material + which]);
+  const int32_t idx = which == 0 ? g->tex_kd : which == 1 ? g->tex_ks : which == 2 ? g->tex_bump : g->tex_ke;
+  return geom_tex(s, idx);
+}
+static inline int32_t face_material_of(const B2ptScene* s, const B2ptGeom* g, int32_t face) {
+  return (s->face_material && face >= 0) ? s->face_material[(size_t)g->face_begin + face] : g->material_id;
+}
+
 /* meshIntersectionTest, apps/src/intersections.h:207-282. */
 float oracle_mesh_test(const B2ptScene* s, const B2ptGeom* g, const float o[3], const float d[3],
                        float normal[3], float uv[2], int32_t* face) {
@@ -305,7 +319,7 @@ float oracle_mesh_test(const B2ptScene* s, const B2ptGeom* g, const float o[3], 
   v3 e2 = sub(ld3(tri + 6), ld3(tri));
   v3 objn = normalize3(cross3(e1, e2));
   v3 nn = normalize3(mat4_mul(g->inv_transpose, objn, 0.0f));
-  const B2ptTexture* bump = geom_tex(s, g->tex_bump);
+  const B2ptTexture* bump = obj_tex(s, g, face_material_of(s, g, nearest), 2);
   if (g->type == B2PT_OBJ && bump) {
     float d1x = tuv[2] - tuv[0], d1y = tuv[3] - tuv[1];
     float d2x = tuv[4] - tuv[0], d2y = tuv[5] - tuv[1];
@@ -484,7 +498,7 @@ int oracle_intersect(const B2ptScene* s, int32_t n, const float* origin, const f
       memcpy(uv + 2 * (size_t)i, huv, sizeof huv);
       geom[i] = hit;
       face[i] = hit_face;
-      material[i] = s->geoms[hit].material_id;
+      material[i] = face_material_of(s, &s->geoms[hit], hit_face);
     }
   }
   return 0;
@@ -550,9 +564,10 @@ static void scatter(const B2ptScene* s, const B2ptOptions* opt, v3* o, v3* d, v3
     *o = add(intersect, muls(*d, 0.01f));
   } else if (s->geoms[geom_id].type == B2PT_OBJ) {
     const B2ptGeom* g = &s->geoms[geom_id];
-    const B2ptTexture* ke = geom_tex(s, g->tex_ke);
-    const B2ptTexture* ks = geom_tex(s, g->tex_ks);
-    const B2ptTexture* kd = geom_tex(s, g->tex_kd);
+    const int32_t mat_id = (int32_t)(m - s->materials);
+    const B2ptTexture* ke = obj_tex(s, g, mat_id, 3);
+    const B2ptTexture* ks = obj_tex(s, g, mat_id, 1);
+    const B2ptTexture* kd = obj_tex(s, g, mat_id, 0);
     v3 emission = V(0, 0, 0);
     if (ke) emission = fetch_texel(ke, u, v);
     if (emission.x > FLT_EPSILON || emission.y > FLT_EPSILON || emission.z > FLT_EPSILON) {
@@ -603,8 +618,8 @@ int oracle_shade(const B2ptScene* s, const B2ptOptions* opt, int32_t iter, int32
         st3(a, ld3(m->color));
         const B2ptGeom* g = &s->geoms[hit_geom[idx]];
         if (g->type == B2PT_OBJ) {
-          const B2ptTexture* ke = geom_tex(s, g->tex_ke);
-          const B2ptTexture* kd = geom_tex(s, g->tex_kd);
+          const B2ptTexture* ke = obj_tex(s, g, hit_material[idx], 3);
+          const B2ptTexture* kd = obj_tex(s, g, hit_material[idx], 0);
           v3 emission = V(0, 0, 0);
           if (ke) emission = fetch_texel(ke, hit_uv[2 * (size_t)idx], hit_uv[2 * (size_t)idx + 1]);
           if (emission.x > FLT_EPSILON || emission.y > FLT_EPSILON || emission.z > FLT_EPSILON) {

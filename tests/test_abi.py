@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version_and_defaults():
     lib = api.load_library()
-    assert lib.b2pt_abi_version() == 1
+    assert lib.b2pt_abi_version() == 2
     o = abi.Options()
     lib.b2pt_default_options(C.byref(o))
     d = abi.default_options()

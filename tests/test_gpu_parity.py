@@ -526,3 +526,50 @@ def test_pixel_rng_converges_to_the_slot_keyed_image(tmp_path):
         got[spp] = psnr(render(abi.RNG_SLOT, 1, spp), render(abi.RNG_PIXEL, 0, spp))
     assert got[32768] >= 50.0, got
     assert 9.0 <= got[32768] - got[2048] <= 15.0, got  # 16x the samples: +12 dB
+
+
+# ---- per-face materials (B2ptScene::face_material / material_textures; the reference discards the ids) -----------
+def test_per_face_materials_small_obj_bitexact(tmp_path):
+    """tests/golden/multimat.obj through the loader with per_face_materials: faces of one OBJ shaded with different
+    materials, one of them with all four maps; every stage against the oracle, BVH walk and brute force."""
+    import shutil
+
+    (tmp_path / "models" / "materials").mkdir(parents=True)
+    (tmp_path / "textures").mkdir()
+    shutil.copy(os.path.join(GOLDEN, "multimat.obj"), tmp_path / "models")
+    shutil.copy(os.path.join(GOLDEN, "multimat.mtl"), tmp_path / "models" / "materials")
+    for f in os.listdir(os.path.join(GOLDEN, "texquad")):
+        shutil.copy(os.path.join(GOLDEN, "texquad", f), tmp_path / "textures")
+    path = scenes.write_scene("cornellObj", str(tmp_path / "scenes" / "s.txt"), width=64, height=48, obj_path="../models/multimat.obj")
+    pod = api.Scene(path, per_face_materials=True).pod
+    assert pod.face_material is not None and len(set(pod.face_material.tolist())) >= 3
+    compare_iteration(pod, {}, iters=(1, 2), what="multimat")
+    compare_iteration(pod, {"use_bvh": 0}, iters=(1,), what="multimat, brute force")
+    compare_iteration(pod, {"sort_by_material": 0}, iters=(1,), what="multimat, no sort")
+
+
+@pytest.mark.parametrize("env", [{}, {"B2PT_LONG_WALK": "2"}])
+def test_per_face_materials_large_mesh_bitexact(tmp_path, monkeypatch, env):
+    """The stand-in hull with its faces spread over four materials (one keeps the maps, one is emissive) in two OBJ
+    geoms: the fold of the walk, the long-walk kernel and the material histograms all work per face."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    pod = _mesh_scene(tmp_path, "twoShips", 112, 63, 5000).copy()
+    base = len(pod.materials)
+    extra = np.zeros(3, pod.materials.dtype)
+    extra["color"] = [(0.2, 0.7, 0.9), (0.9, 0.9, 0.2), (1.0, 0.8, 0.6)]
+    extra["specular_color"] = [(0.5, 0.5, 0.5), (0.9, 0.2, 0.2), (0, 0, 0)]
+    extra["index_of_refraction"] = [1.3, 2.2, 1.0]
+    extra["emittance"] = [0.0, 0.0, 2.0]
+    pod.materials = np.concatenate([pod.materials, extra])
+    rng = np.random.default_rng(5)
+    fm = np.zeros(len(pod.face_pos), np.int32)
+    mt = np.full((len(pod.materials), 4), -1, np.int32)
+    for g in np.nonzero(pod.geoms["type"] == abi.OBJ)[0]:
+        fb, fc, gm = int(pod.geoms["face_begin"][g]), int(pod.geoms["face_count"][g]), int(pod.geoms["material_id"][g])
+        choice = rng.integers(0, 4, fc)
+        fm[fb: fb + fc] = np.where(choice == 0, gm, base + choice - 1)
+        mt[gm] = [pod.geoms[k][g] for k in ("tex_kd", "tex_ks", "tex_bump", "tex_ke")]
+    mt[base] = mt[int(pod.geoms["material_id"][np.nonzero(pod.geoms["type"] == abi.OBJ)[0][0]])]  # a second material with the maps
+    pod.face_material, pod.material_textures = fm, mt
+    compare_iteration(pod, {}, iters=(1, 2), what=f"per-face materials {env}")

@@ -6,7 +6,7 @@ import shutil
 import numpy as np
 import pytest
 
-from mygpuraytracer_b200 import api, assets, scenes, standin_mesh
+from mygpuraytracer_b200 import abi, api, assets, scenes, standin_mesh
 from mygpuraytracer_b200.podscene import PodScene
 from util import GOLDEN, assert_same_bits
 
@@ -388,3 +388,74 @@ def test_text_parsers_survive_mutations(tmp_path, what):
         except api.B2ptError as e:
             assert e.code < 0
     assert loaded > 0
+
+
+def _multimat_tree(tmp_path):
+    (tmp_path / "models" / "materials").mkdir(parents=True)
+    (tmp_path / "textures").mkdir()
+    shutil.copy(os.path.join(GOLDEN, "multimat.obj"), tmp_path / "models")
+    shutil.copy(os.path.join(GOLDEN, "multimat.mtl"), tmp_path / "models" / "materials")
+    for f in os.listdir(os.path.join(GOLDEN, "texquad")):
+        shutil.copy(os.path.join(GOLDEN, "texquad", f), tmp_path / "textures")
+    return scenes.write_scene("cornellObj", str(tmp_path / "scenes" / "s.txt"), width=32, height=32, obj_path="../models/multimat.obj")
+
+
+def test_per_face_materials_match_tinyobj(tmp_path):
+    """per_face_materials=1 keeps what the reference reads and discards (apps/src/scene.cpp:121-122): the ids are
+    tinyobjloader's own (tests/golden/multimat_tinyobj.json, from the reference's vendored copy), every MTL material
+    becomes a scene material converted like material 0 (scene.cpp:221-231) with its own four maps."""
+    import json
+
+    gold = json.load(open(os.path.join(GOLDEN, "multimat_tinyobj.json")))
+    path = _multimat_tree(tmp_path)
+    plain = api.Scene(path).pod
+    pod = api.Scene(path, per_face_materials=True).pod
+    assert plain.face_material is None and plain.material_textures is None
+    n_mtl = len(gold["materials"])
+    base = len(plain.materials) - 1                      # the reference appends ONE material per OBJ
+    assert len(pod.materials) == base + n_mtl
+    assert np.array_equal(pod.materials[: base + 1], plain.materials)   # material 0 is the reference's
+    g = int(np.nonzero(pod.geoms["type"] == abi.OBJ)[0][0])
+    assert pod.geoms["material_id"][g] == base
+    fb, fc = int(pod.geoms["face_begin"][g]), int(pod.geoms["face_count"][g])
+    assert fc == len(gold["material_ids"])
+    want = np.array([base + max(i, 0) for i in gold["material_ids"]], np.int32)   # no / unknown usemtl -> material 0
+    assert np.array_equal(pod.face_material[fb: fb + fc], want)
+    for k, m in enumerate(gold["materials"]):
+        sm = pod.materials[base + k]
+        assert np.array_equal(sm["color"], np.array(m["kd"], np.float32))
+        assert np.array_equal(sm["specular_color"], np.array(m["ks"], np.float32))
+        assert sm["index_of_refraction"] == np.float32(m["ior"]) and sm["emittance"] == np.float32(m["ke"][0])
+        assert sm["has_reflective"] == 0 and sm["has_refractive"] == 0 and sm["specular_exponent"] == 0
+        has_maps = bool(m["map_kd"])
+        assert all((t >= 0) == has_maps for t in pod.material_textures[base + k])
+    assert (pod.material_textures[:base] == -1).all()
+    # the geom keeps material 0's maps (none here), as in reference mode
+    assert pod.geoms["tex_kd"][g] == plain.geoms["tex_kd"][g] == -1
+    # one decoded image per file, however many materials name it
+    assert len(pod.textures) == 4
+
+
+def test_per_face_materials_change_the_render_and_roundtrip_b2s(tmp_path):
+    """The oracle defines the behaviour: a face is shaded with ITS material and maps; with the ids dropped the same
+    scene renders as the reference does.  The .b2s container keeps the two arrays."""
+    from mygpuraytracer_b200.podscene import PodScene
+    from oracle import oracle
+
+    path = _multimat_tree(tmp_path)
+    pod = api.Scene(path, per_face_materials=True, width=24, height=24).pod
+    plain = api.Scene(path, width=24, height=24).pod
+    a = oracle.render(pod, abi.default_options(trig_mode=abi.TRIG_PORTABLE), 1, 2, 1)
+    b = oracle.render(plain, abi.default_options(trig_mode=abi.TRIG_PORTABLE), 1, 2, 1)
+    assert not np.array_equal(a[0], b[0]) and not np.array_equal(a[1], b[1])
+    # dropping the ids (every face -> material 0, no per-material maps) is the reference's scene
+    same = pod.copy()
+    same.face_material = None
+    same.material_textures = None
+    c = oracle.render(same, abi.default_options(trig_mode=abi.TRIG_PORTABLE), 1, 2, 1)
+    assert np.array_equal(c[0], b[0]) and np.array_equal(c[1], b[1])
+    f = str(tmp_path / "mm.b2s")
+    pod.save(f)
+    back = PodScene.load(f)
+    assert np.array_equal(back.face_material, pod.face_material) and np.array_equal(back.material_textures, pod.material_textures)
+    assert_same_scene(pod, back)
