@@ -509,13 +509,18 @@ static int upload_texture(B2ptCtx* c, const B2ptScene* sc, int idx, DevTexture* 
   }
   const B2ptTexture& t = sc->textures[idx];
   if (t.channels == 0 || t.texels == nullptr) return 0;
-  if (t.channels < 3 || t.width <= 0 || t.height <= 0)
-    return fail(B2PT_ERR_INVALID, "textures need >= 3 channels and positive dimensions");
+  if (t.channels < 1 || t.width <= 0 || t.height <= 0)
+    return fail(B2PT_ERR_INVALID, "textures need >= 1 channel and positive dimensions");
+  // The fetch reads three consecutive bytes per texel whatever the channel count, like the reference
+  // (apps/src/interactions.h:199-212): with 1 or 2 channels that runs into the next texels and, for the last ones,
+  // past the end of the image (undefined in the reference).  Two padding bytes that repeat the last byte make that
+  // read defined (the oracle reads the same) without a bounds check per texel.
   uint8_t* d = nullptr;
   const size_t bytes = (size_t)t.width * t.height * t.channels;
-  int rc = c->dalloc(&d, bytes);
+  int rc = c->dalloc(&d, bytes + 2);
   if (rc) return rc;
   CK(cudaMemcpyAsync(d, t.texels, bytes, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemsetAsync(d + bytes, t.texels[bytes - 1], 2, c->stream));
   out->texels = d;
   out->w = t.width;
   out->h = t.height;

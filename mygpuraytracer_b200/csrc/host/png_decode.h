@@ -10,6 +10,7 @@
 #pragma once
 
 #include <cstdint>
+#include <algorithm>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -121,7 +122,9 @@ struct Huffman {  // canonical code: how many codes of each length, symbols orde
   }
 };
 
-inline bool inflate(const uint8_t* src, size_t n, std::vector<uint8_t>* out, std::string* err) {
+// `cap`: the number of bytes the caller can use (the scanlines of the image); the stream is decoded no further, so
+// a small file cannot make the decoder allocate without bound.
+inline bool inflate(const uint8_t* src, size_t n, size_t cap, std::vector<uint8_t>* out, std::string* err) {
   static const uint16_t len_base[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
   static const uint8_t len_extra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
   static const uint16_t dist_base[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
@@ -132,7 +135,7 @@ inline bool inflate(const uint8_t* src, size_t n, std::vector<uint8_t>* out, std
   BitReader b{src + 2, src + n};
   Huffman lit, dist;
   bool last = false;
-  while (!last) {
+  while (!last && out->size() < cap) {
     last = b.get(1) != 0;
     const uint32_t type = b.get(2);
     if (b.fail) { *err = "PNG: truncated deflate stream"; return false; }
@@ -142,7 +145,7 @@ inline bool inflate(const uint8_t* src, size_t n, std::vector<uint8_t>* out, std
       const uint32_t len = b.p[0] | (b.p[1] << 8), nlen = b.p[2] | (b.p[3] << 8);
       b.p += 4;
       if ((len ^ 0xffffu) != nlen || (size_t)(b.end - b.p) < len) { *err = "PNG: corrupt stored block"; return false; }
-      out->insert(out->end(), b.p, b.p + len);
+      out->insert(out->end(), b.p, b.p + std::min<size_t>(len, cap - out->size()));
       b.p += len;
       continue;
     }
@@ -187,6 +190,7 @@ inline bool inflate(const uint8_t* src, size_t n, std::vector<uint8_t>* out, std
     for (;;) {
       const int s = lit.decode(b);
       if (s < 0) { *err = "PNG: bad literal/length code"; return false; }
+      if (out->size() >= cap) return true;  // everything the image needs has been decoded
       if (s < 256) {
         out->push_back((uint8_t)s);
         continue;
@@ -199,7 +203,7 @@ inline bool inflate(const uint8_t* src, size_t n, std::vector<uint8_t>* out, std
       const size_t d = (size_t)dist_base[ds] + b.get(dist_extra[ds]);
       if (b.fail || d > out->size()) { *err = "PNG: distance reaches before the start"; return false; }
       size_t from = out->size() - d;
-      for (int k = 0; k < len; ++k) out->push_back((*out)[from++]);
+      for (int k = 0; k < len && out->size() < cap; ++k) out->push_back((*out)[from++]);
     }
   }
   return true;
@@ -270,7 +274,7 @@ inline bool decode(const uint8_t* data, size_t size, int* w_out, int* h_out, int
   const size_t row_bytes = ((size_t)w * file_ch * depth + 7) / 8;
   const size_t bpp = (size_t)(file_ch * depth + 7) / 8;  // filter distance, at least one byte
   std::vector<uint8_t> raw;
-  if (!inflate(z.data(), z.size(), &raw, err)) return false;
+  if (!inflate(z.data(), z.size(), (row_bytes + 1) * (size_t)h, &raw, err)) return false;
   if (raw.size() < (row_bytes + 1) * (size_t)h) { *err = "PNG: not enough image data"; return false; }
   // ---- undo the scanline filters in place ----
   std::vector<uint8_t> zero(row_bytes, 0);

@@ -259,8 +259,11 @@ static inline v3 fetch_texel(const B2ptTexture* tx, float u, float v) {
   long long last = (long long)tx->width * tx->height - 1;
   if (pixelID < 0) pixelID = 0;
   if (pixelID > last) pixelID = last;
-  const uint8_t* px = tx->texels + pixelID * tx->channels;
-  unsigned int colR = px[0], colG = px[1], colB = px[2];
+  /* Three consecutive bytes, whatever the channel count: with 1 or 2 channels the reference reads into the next
+   * texel(s), and past the end of the image for the last ones (undefined there; read as the last byte here). */
+  const long long end = ((long long)tx->width * tx->height) * tx->channels - 1;
+  const long long at = pixelID * tx->channels;
+  unsigned int colR = tx->texels[at], colG = tx->texels[at + 1 > end ? end : at + 1], colB = tx->texels[at + 2 > end ? end : at + 2];
   return V((float)colR / 255.f, (float)colG / 255.f, (float)colB / 255.f);
 }
 

@@ -38,12 +38,14 @@ CASES = {
     "both_refl_refr_48x20": ("variant:both_refl_refr", 48, 20, []),
     # quadbox with all four texture maps (texquad.mtl, PNG fixtures in texquad/): bump mapping, emission texels, kd / ks
     "texquad_32x32": ("texquad", 32, 32, []),
+    # the same box with a 1-channel kd and a 2-channel ks map: three bytes are read per texel whatever the channel count
+    "greyquad_32x32": ("greyquad", 32, 32, []),
 }
 
 
 def main():
     assert harness.have("ref_cpu"), "build oracle/_ref first: make -C oracle ref"
-    for f in ("quadbox", "hardobj", "texquad"):
+    for f in ("quadbox", "hardobj", "texquad", "greyquad"):
         shutil.copyfile(os.path.join(HERE, f + ".obj"), os.path.join(harness.RUN_MODELS, f + ".obj"))
         shutil.copyfile(os.path.join(HERE, f + ".mtl"), os.path.join(harness.RUN_MODELS, "materials", f + ".mtl"))
     tex_dir = os.path.join(os.path.dirname(harness.RUN_MODELS), "textures")
@@ -55,7 +57,7 @@ def main():
         txt = os.path.join(d, "s.txt")
         if scene.startswith("variant:"):
             shutil.copyfile(os.path.join(HERE, "variants", scene.split(":")[1] + ".txt"), txt)
-        elif scene in ("quadbox", "hardobj", "texquad"):
+        elif scene in ("quadbox", "hardobj", "texquad", "greyquad"):
             with open(txt, "w") as f:
                 f.write(scenes.scene_text("cornellObj", width=w, height=h, obj_path=f"../models/{scene}.obj"))
         else:

@@ -77,7 +77,7 @@ CASES = [
     ("cornell_32x32", {}), ("cornellGlass_32x32", {}), ("cornellGlass_dof_32x24", {"depth_of_field": 1}),
     ("cornellGlass_noaa_24x32", {"antialiasing": 0}), ("sphere_16x16", {}), ("quadbox_32x32", {}),
     ("hardobj_16x16", {}), ("rot_scale_48x20", {}), ("both_refl_refr_48x20", {}),
-    ("texquad_32x32", {}),
+    ("texquad_32x32", {}), ("greyquad_32x32", {}),
 ]
 
 

@@ -20,3 +20,12 @@ def test_textured_mesh_golden_every_stage_bitexact():
     pod = PodScene.load(os.path.join(GOLDEN, "texquad_32x32.b2s"))
     assert [t.shape[2] for t in pod.textures] == [4, 3, 3, 3]
     compare_iteration(pod, {}, what="texquad_32x32")
+
+
+def test_grey_and_grey_alpha_maps_every_stage_bitexact():
+    """tests/golden/greyquad_32x32: a 1-channel kd map and a 2-channel ks map.  The reference reads three bytes per
+    texel whatever the channel count (apps/src/interactions.h:199-212), i.e. into the following texels; the scene and
+    every stage come from the reference's own host build."""
+    pod = PodScene.load(os.path.join(GOLDEN, "greyquad_32x32.b2s"))
+    assert sorted(t.shape[2] for t in pod.textures) == [1, 2, 3, 3]
+    compare_iteration(pod, {}, what="greyquad_32x32")
