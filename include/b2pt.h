@@ -530,6 +530,16 @@ int b2pt_partition_perm(int32_t n, const uint8_t* flags_host, int32_t* perm_host
  * perm_host[k] = source index of sorted slot k.  keys must be in [0, 65535]. */
 int b2pt_sort_desc_perm(int32_t n, const int32_t* keys_host, int32_t* perm_host);
 
+/* The renderer's material sort with its compaction ranks, on host arrays (the kernel behind
+ * thrust::sort_by_key(sortByMaterial) + the live prefix of thrust::stable_partition,
+ * pathtrace.cu:512-516,612,649): material_host[i] < n_materials is the material of path slot i,
+ * live_host[i] != 0 says the path survives the shade.  perm_host[j] = slot of sorted position j
+ * (stable, descending material); rank_host[j] = survivors in front of sorted position j.
+ * general != 0 forces the 256-bin kernel where the few-materials kernel (n_materials <= 8) applies.
+ * Returns the number of survivors or <0. */
+int b2pt_sort_material_ranks(int32_t n, const uint8_t* material_host, const uint8_t* live_host, int32_t n_materials,
+                             int32_t general, int32_t* perm_host, int32_t* rank_host);
+
 /* Stable LSD radix sort of 32-bit keys with 32-bit values (onesweep, 4 passes
  * of 8 bits); the sort behind the LBVH Morton ordering. */
 int b2pt_radix_sort_pairs_u32(int32_t n, uint32_t* keys_host, uint32_t* vals_host);

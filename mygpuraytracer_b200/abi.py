@@ -254,6 +254,7 @@ SYMBOLS = {
     "b2pt_compact_nonzero_i32": (C.c_int, [_i32, _vp, _vp]),
     "b2pt_partition_perm": (C.c_int, [_i32, _vp, _vp]),
     "b2pt_sort_desc_perm": (C.c_int, [_i32, _vp, _vp]),
+    "b2pt_sort_material_ranks": (C.c_int, [_i32, _vp, _vp, _i32, _i32, _vp, _vp]),
     "b2pt_radix_sort_pairs_u32": (C.c_int, [_i32, _vp, _vp]),
     "b2pt_scene_load": (C.c_int, [C.c_char_p, C.POINTER(LoadOverrides), C.POINTER(_vp)]),
     "b2pt_scene_view": (C.POINTER(Scene), [_vp]),

@@ -565,6 +565,16 @@ def sort_desc_perm(keys: np.ndarray) -> np.ndarray:
     return perm
 
 
+def sort_material_ranks(material: np.ndarray, live: np.ndarray, n_materials: int, general: bool = False):
+    """The renderer's material sort: (perm, rank, survivors); see b2pt_sort_material_ranks."""
+    m = np.ascontiguousarray(material, np.uint8)
+    f = np.ascontiguousarray(live, np.uint8)
+    perm, rank = np.empty(len(m), np.int32), np.empty(len(m), np.int32)
+    k = _check(load_library().b2pt_sort_material_ranks(len(m), m.ctypes.data, f.ctypes.data, int(n_materials), int(general),
+                                                       perm.ctypes.data, rank.ctypes.data))
+    return perm, rank, k
+
+
 def radix_sort_pairs(keys: np.ndarray, vals: np.ndarray):
     k = np.ascontiguousarray(keys, np.uint32).copy()
     v = np.ascontiguousarray(vals, np.uint32).copy()

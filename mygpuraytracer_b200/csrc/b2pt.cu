@@ -186,6 +186,7 @@ struct B2ptCtx {
   int long_cap = 0, long_carry = kLongCarry;
   int shade_stride_grid = 0, gen_trace_grid = 0;
   int isect_grid = 0, analytic_grid = 0, sort_grid = 0, shade_grid = 0, gen_grid = 0;
+  bool sort_general = false;  // B2PT_SORT_GENERAL=1: the 256-bin material sort even when the few-materials kernel applies (tests)
   float4* mesh_queue = nullptr;  // [3][P]: the rays that walk a mesh, see IsectParams::queue
   cudaEvent_t ev_loop_a = nullptr, ev_loop_b = nullptr;
   bool loop_timed = false;
@@ -739,7 +740,7 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
   for (int b = 0; b < 2; ++b) {
     if ((rc = c->dalloc(&c->hits[b].h0, P))) return rc;
     if ((rc = c->dalloc(&c->hits[b].h1, P))) return rc;
-    if ((rc = c->dalloc(&c->key[b], P))) return rc;
+    if ((rc = c->dalloc(&c->key[b], P + kSortTile))) return rc;   // k_sort_material_few reads whole 16-byte groups
     if ((rc = c->dalloc(&c->live[b], P + kSortTile))) return rc;  // k_rank_live reads whole 16-byte groups
   }
   if ((rc = c->dalloc(&c->perm, P))) return rc;
@@ -805,6 +806,7 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
   // when several contexts share the GPU (their two phases serialise inside a CTA)
   c->fuse = opt.concurrent_contexts <= 1;
   if (const char* e = getenv("B2PT_FUSE")) c->fuse = atoi(e) != 0;
+  if (const char* e = getenv("B2PT_SORT_GENERAL")) c->sort_general = atoi(e) != 0;
   if (const char* e = getenv("B2PT_LONG_WALK")) c->long_walk = std::max(atoi(e), 1);
   if (const char* e = getenv("B2PT_LONG_CARRY")) c->long_carry = std::max(0, std::min(atoi(e), kLongCarry));  // tests: 0 = always restart at the root
   if (const char* e = getenv("B2PT_LONG_CAP")) c->long_cap = std::max(1, std::min(atoi(e), c->long_cap));      // tests: a full hand-off queue
@@ -1057,7 +1059,9 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
       mp.status_live = c->sort_status_live;
       mp.depth = d;
       if (kt) kt->mark(2);
-      if (c->opt.sort_by_material)
+      if (c->opt.sort_by_material && c->n_materials <= kFewMaterials && !c->sort_general)
+        k_sort_material_few<<<c->sort_grid, kSortThreads, 0, s>>>(mp, c->n_materials);
+      else if (c->opt.sort_by_material)
         k_sort_material<<<c->sort_grid, kSortThreads, 0, s>>>(mp);
       else  // SORT_BY_MATERIAL 0: slot order is kept, only the compaction ranks are needed
         k_rank_live<<<c->sort_grid, kSortThreads, 0, s>>>(mp);
@@ -1689,6 +1693,68 @@ extern "C" int b2pt_sort_desc_perm(int32_t n, const int32_t* keys_host, int32_t*
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(perm_host, dperm, (size_t)n * 4, cudaMemcpyDeviceToHost));
   return 0;
+}
+
+// hist_live for the stand-alone entry below: counts key[i] where live[i] != 0.
+__global__ void k_key_hist_live_u8(const uint8_t* __restrict__ key, const uint8_t* __restrict__ live, int n, unsigned int* hist) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    if (live[i]) atomicAdd(&hist[key[i]], 1u);
+}
+
+extern "C" int b2pt_sort_material_ranks(int32_t n, const uint8_t* material_host, const uint8_t* live_host, int32_t n_materials,
+                                        int32_t general, int32_t* perm_host, int32_t* rank_host) {
+  if (n < 0 || n_materials <= 0 || n_materials > kMaxMaterials) return fail(B2PT_ERR_INVALID, "bad n or n_materials");
+  if (n == 0) return 0;
+  if (!material_host || !live_host || !perm_host || !rank_host) return fail(B2PT_ERR_INVALID, "NULL array");
+  for (int i = 0; i < n; ++i)
+    if (material_host[i] >= n_materials) return fail(B2PT_ERR_RANGE, "material id >= n_materials");
+  Scratch S;
+  uint8_t *dkey = nullptr, *dlive = nullptr;
+  int *dperm = nullptr, *dapos = nullptr;
+  Counters* ctr = nullptr;
+  unsigned long long *status = nullptr, *status_live = nullptr;
+  const int tiles = (n + kSortTile - 1) / kSortTile;
+  const size_t padded = (size_t)tiles * kSortTile;  // the kernels read whole 16-byte groups
+  CK(S.get(&dkey, padded));
+  CK(S.get(&dlive, padded));
+  CK(S.get(&dperm, padded));
+  CK(S.get(&dapos, padded));
+  CK(S.get(&ctr, 1));
+  CK(S.get(&status, (size_t)tiles * 256));
+  CK(S.get(&status_live, (size_t)tiles * 256));
+  CK(cudaMemset(dkey, 0, padded));
+  CK(cudaMemset(dlive, 0, padded));
+  CK(cudaMemcpy(dkey, material_host, (size_t)n, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dlive, live_host, (size_t)n, cudaMemcpyHostToDevice));
+  CK(cudaMemset(ctr, 0, sizeof(Counters)));
+  CK(cudaMemset(status, 0, (size_t)tiles * 256 * 8));
+  CK(cudaMemset(status_live, 0, (size_t)tiles * 256 * 8));
+  CK(cudaMemcpy(&ctr->n_live[0], &n, 4, cudaMemcpyHostToDevice));
+  const unsigned int one = 1;
+  CK(cudaMemcpy(&ctr->serial, &one, 4, cudaMemcpyHostToDevice));
+  const int hg = std::min((n + 255) / 256, 1184);
+  k_key_hist_u8<<<hg, 256>>>(dkey, n, &ctr->hist[0][0]);
+  k_key_hist_live_u8<<<hg, 256>>>(dkey, dlive, n, &ctr->hist_live[0][0]);
+  MatSortParams mp;
+  mp.key = dkey;
+  mp.live = dlive;
+  mp.perm = dperm;
+  mp.apos = dapos;
+  mp.ctr = ctr;
+  mp.status = status;
+  mp.status_live = status_live;
+  mp.depth = 0;
+  if (n_materials <= kFewMaterials && !general)
+    k_sort_material_few<<<tiles, kSortThreads>>>(mp, n_materials);
+  else
+    k_sort_material<<<tiles, kSortThreads>>>(mp);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(perm_host, dperm, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(rank_host, dapos, (size_t)n * 4, cudaMemcpyDeviceToHost));
+  int next = 0;
+  CK(cudaMemcpy(&next, &ctr->n_live[1], 4, cudaMemcpyDeviceToHost));
+  return next;
 }
 
 extern "C" int b2pt_radix_sort_pairs_u32(int32_t n, uint32_t* keys_host, uint32_t* vals_host) {

@@ -131,63 +131,6 @@ __device__ __forceinline__ const DevTexture& obj_tex(const DevScene& sc, const D
   return sc.mat_tex ? sc.mat_tex[4 * material + which] : (&M.kd)[which];
 }
 
-// boxIntersectionTest, apps/src/intersections.h:48-90.  Returns the world-space
-// distance (or -1) and the object-space axis normal of the face that was hit.
-__device__ __forceinline__ float box_exact(const DevGeom& G, V3 o, V3 d, V3* axis_normal) {
-  const V3 qo = xform(G.inv, o, 1.0f);
-  const V3 qd = normalize(xform(G.inv, d, 0.0f));
-  float tmin = -1e38f, tmax = 1e38f;
-  V3 nmin = mk(0, 0, 0), nmax = mk(0, 0, 0);
-  {
-    const float t1 = (-0.5f - qo.x) / qd.x, t2 = (+0.5f - qo.x) / qd.x;
-    const float ta = glm_min(t1, t2), tb = glm_max(t1, t2);
-    const V3 nn = mk(t2 < t1 ? +1.0f : -1.0f, 0, 0);
-    if (ta > 0 && ta > tmin) { tmin = ta; nmin = nn; }
-    if (tb < tmax) { tmax = tb; nmax = nn; }
-  }
-  {
-    const float t1 = (-0.5f - qo.y) / qd.y, t2 = (+0.5f - qo.y) / qd.y;
-    const float ta = glm_min(t1, t2), tb = glm_max(t1, t2);
-    const V3 nn = mk(0, t2 < t1 ? +1.0f : -1.0f, 0);
-    if (ta > 0 && ta > tmin) { tmin = ta; nmin = nn; }
-    if (tb < tmax) { tmax = tb; nmax = nn; }
-  }
-  {
-    const float t1 = (-0.5f - qo.z) / qd.z, t2 = (+0.5f - qo.z) / qd.z;
-    const float ta = glm_min(t1, t2), tb = glm_max(t1, t2);
-    const V3 nn = mk(0, 0, t2 < t1 ? +1.0f : -1.0f);
-    if (ta > 0 && ta > tmin) { tmin = ta; nmin = nn; }
-    if (tb < tmax) { tmax = tb; nmax = nn; }
-  }
-  if (tmax >= tmin && tmax > 0) {
-    if (tmin <= 0) { tmin = tmax; nmin = nmax; }
-    // getPointOnRay (:27-29) normalises the direction again
-    const V3 ip = xform(G.fwd, qo + normalize(qd) * (tmin - .0001f), 1.0f);
-    *axis_normal = nmin;
-    return length(o - ip);
-  }
-  return -1.0f;
-}
-
-// sphereIntersectionTest, apps/src/intersections.h:102-144.  *kind: 2 hit from
-// outside, 3 from inside; *obj: the object-space hit point (normal source).
-__device__ __forceinline__ float sphere_exact(const DevGeom& G, V3 o, V3 d, V3* obj, int* kind) {
-  const V3 ro = xform(G.inv, o, 1.0f);
-  const V3 rd = normalize(xform(G.inv, d, 0.0f));
-  const float vdd = dot(ro, rd);
-  const float radicand = vdd * vdd - (dot(ro, ro) - 0.25f);
-  if (radicand < 0) return -1.0f;
-  const float sq = sqrtf(radicand);
-  const float first = -vdd;
-  const float t1 = first + sq, t2 = first - sq;
-  if (t1 < 0 && t2 < 0) return -1.0f;
-  float ts;
-  if (t1 > 0 && t2 > 0) { ts = fminf(t1, t2); *kind = 2; } else { ts = fmaxf(t1, t2); *kind = 3; }
-  const V3 p = ro + normalize(rd) * (ts - .0001f);
-  *obj = p;
-  return length(o - xform(G.fwd, p, 1.0f));
-}
-
 // 1/x to ~1 ulp (MUFU.RCP) for tests that only prune: the exact tests never see it.
 __device__ __forceinline__ float rcp_fast(float x) {
   float r;
@@ -264,6 +207,72 @@ __device__ __forceinline__ bool will_survive(const DevMaterial* __restrict__ mat
   return !(__ldg(&mats[mat].emittance) > 0.0f) && bounces > 1 && !emissive_texel;
 }
 
+// One exact test of an analytic geom: boxIntersectionTest (apps/src/intersections.h:48-90) or
+// sphereIntersectionTest (:102-144) with the arithmetic the two share written ONCE -- the ray into object space in
+// front, getPointOnRay + the point back into world space + the distance behind -- so that a warp whose lanes hold
+// cubes and spheres runs those parts together and only the middle (the three slabs / the quadratic) per type.
+// Every expression is evaluated as the reference writes it, in glm's order (pt_math.cuh): the bits are the same.
+// Returns the world-space distance or -1; *aux: the box's object-space axis normal / the sphere's object-space hit
+// point; *kind: 1 box, 2 sphere from outside, 3 sphere from inside.
+__device__ __forceinline__ float analytic_exact(const DevGeom& G, V3 o, V3 d, V3* aux, int* kind) {
+  const V3 qo = xform(G.inv, o, 1.0f);
+  const V3 qd = normalize(xform(G.inv, d, 0.0f));
+  float ts = 0.0f;
+  bool hit = false;
+  int k = 1;
+  V3 a = mk(0, 0, 0);
+  if (G.type == 1) {
+    float tmin = -1e38f, tmax = 1e38f;
+    V3 nmin = mk(0, 0, 0), nmax = mk(0, 0, 0);
+    {
+      const float t1 = (-0.5f - qo.x) / qd.x, t2 = (+0.5f - qo.x) / qd.x;
+      const float ta = glm_min(t1, t2), tb = glm_max(t1, t2);
+      const V3 nn = mk(t2 < t1 ? +1.0f : -1.0f, 0, 0);
+      if (ta > 0 && ta > tmin) { tmin = ta; nmin = nn; }
+      if (tb < tmax) { tmax = tb; nmax = nn; }
+    }
+    {
+      const float t1 = (-0.5f - qo.y) / qd.y, t2 = (+0.5f - qo.y) / qd.y;
+      const float ta = glm_min(t1, t2), tb = glm_max(t1, t2);
+      const V3 nn = mk(0, t2 < t1 ? +1.0f : -1.0f, 0);
+      if (ta > 0 && ta > tmin) { tmin = ta; nmin = nn; }
+      if (tb < tmax) { tmax = tb; nmax = nn; }
+    }
+    {
+      const float t1 = (-0.5f - qo.z) / qd.z, t2 = (+0.5f - qo.z) / qd.z;
+      const float ta = glm_min(t1, t2), tb = glm_max(t1, t2);
+      const V3 nn = mk(0, 0, t2 < t1 ? +1.0f : -1.0f);
+      if (ta > 0 && ta > tmin) { tmin = ta; nmin = nn; }
+      if (tb < tmax) { tmax = tb; nmax = nn; }
+    }
+    if (tmax >= tmin && tmax > 0) {
+      if (tmin <= 0) { tmin = tmax; nmin = nmax; }
+      hit = true;
+      ts = tmin;
+      a = nmin;
+    }
+  } else {
+    const float vdd = dot(qo, qd);
+    const float radicand = vdd * vdd - (dot(qo, qo) - 0.25f);
+    if (!(radicand < 0)) {
+      const float sq = sqrtf(radicand);
+      const float first = -vdd;
+      const float t1 = first + sq, t2 = first - sq;
+      if (!(t1 < 0 && t2 < 0)) {
+        hit = true;
+        if (t1 > 0 && t2 > 0) { ts = fminf(t1, t2); k = 2; } else { ts = fmaxf(t1, t2); k = 3; }
+      }
+    }
+  }
+  if (!hit) return -1.0f;
+  // getPointOnRay (:27-29) normalises the direction again
+  const V3 p = qo + normalize(qd) * (ts - .0001f);
+  if (k != 1) a = p;
+  *aux = a;
+  *kind = k;
+  return length(o - xform(G.fwd, p, 1.0f));
+}
+
 // Closest hit in two kernels per depth.
 //
 //  k_intersect_analytic  one thread per ray against the analytic geoms (cubes,
@@ -272,9 +281,7 @@ __device__ __forceinline__ bool will_survive(const DevMaterial* __restrict__ mat
 //     analytic hit (or the miss), the sort key and the material histogram are
 //     written at once.  Rays whose path crosses a mesh's box in front of that
 //     hit are appended to a device queue (one atomic per warp).
-//  k_intersect_mesh      persistent warps drain the queue, 32 rays at a time, all
-//     lanes walking (in the first version only the few lanes of a batch that
-//     touched the mesh were active during the walk: 11 of 32).  Rays the mesh
+//  k_mesh_walk (k_walk.cuh)  persistent warps drain the queue.  Rays the mesh
 //     wins get their record, key and histogram entry rewritten.
 // The closest hit is the lexicographic minimum of (t, geom id) over all geoms,
 // which is what the reference's strict `<` loop in geom order returns.
@@ -291,38 +298,54 @@ __device__ __forceinline__ void analytic_trace(const DevGeom* sgeom, int n_geoms
   float t_min = FLT_MAX;
   int hit = -1, kind = 0;
   V3 aux = mk(0, 0, 0);  // box: axis normal; sphere: object-space point
-  // Pass 1 (warp-coherent, cheap): which geoms does this ray's path cross?  For meshes: the closest box
-  // entry (minus the distance slack) of the rigid ones, and whether a non-rigid one is crossed at all.
+  // Pass 1 (warp-coherent, cheap): which geoms does this ray's path cross, and which of them does it enter
+  // first?  For meshes: the closest box entry (minus the distance slack) of the rigid ones, and whether a
+  // non-rigid one is crossed at all.
   unsigned long long cand = 0ull;
-  float mesh_tn = FLT_MAX;
+  float mesh_tn = FLT_MAX, near_tn = FLT_MAX;
+  int g = -1;
   bool mesh_any = false;
-  for (int g = 0; g < n_geoms; ++g) {
-    const DevGeom& G = sgeom[g];
+  for (int k = 0; k < n_geoms; ++k) {
+    const DevGeom& G = sgeom[k];
     float tn, tf;
     world_slab(G, id, noid, &tn, &tf);
-    if (!(tn <= tf) || tf < 0.0f) continue;
+    if (!(tn <= tf) || tf < 0.0f) continue;  // most geoms end here: the early exit is cheaper than predicating the rest
     if (G.type == 1 || G.type == 0) {
-      cand |= 1ull << g;
+      cand |= 1ull << k;
+      if (tn < near_tn) {
+        near_tn = tn;
+        g = k;
+      }
     } else if (G.type == 3 && G.mesh >= 0) {
       if (G.rigid) mesh_tn = fminf(mesh_tn, tn - G.wmin.w); else mesh_any = true;
     }
   }
-  // Pass 2: each lane runs the exact tests of ITS candidates (typically 1-3 of the 8-9 geoms), in geom
-  // order; the warp iterates max-popcount times instead of once per geom.
-  while (cand) {
-    const int g = __ffsll((long long)cand) - 1;
-    cand &= cand - 1ull;
-    const DevGeom& G = sgeom[g];
-    if (!may_beat(G, id, noid, t_min, true)) continue;
+  // Pass 2: the exact tests, in ROUNDS the lanes of a warp run together.  A lane starts with the candidate it
+  // enters first -- usually the one it hits, after which may_beat drops the others -- and then skips ahead to its
+  // next candidate that can still win BEFORE it joins the next round, so a round is entered with every lane that
+  // has work (0.8 - 1 exact tests per ray, 1.8 - 1.9 rounds per warp of scattered rays on the Cornell scenes:
+  // tools/exp_analytic_model.py).  The result does not depend on the order: the winner is the lexicographic
+  // minimum of (t, geom id), which is what the reference's strict `<` loop in geom order keeps.
+  if (g >= 0) cand &= ~(1ull << g);
+  while (g >= 0) {
     float t;
     V3 taux = mk(0, 0, 0);
     int tkind = 1;
-    if (G.type == 1) t = box_exact(G, o, d, &taux); else t = sphere_exact(G, o, d, &taux, &tkind);
-    if (t > 0.0f && t_min > t) {  // candidates are visited in index order: strict < keeps the lowest id
+    t = analytic_exact(sgeom[g], o, d, &taux, &tkind);
+    if (t > 0.0f && (t < t_min || (t == t_min && g < hit))) {
       t_min = t;
       hit = g;
       kind = tkind;
       aux = taux;
+    }
+    g = -1;
+    while (cand) {
+      const int k = __ffsll((long long)cand) - 1;
+      cand &= cand - 1ull;
+      if (may_beat(sgeom[k], id, noid, t_min, true)) {
+        g = k;
+        break;
+      }
     }
   }
   r->mat = 0;

@@ -356,6 +356,239 @@ __global__ void __launch_bounds__(kSortThreads) k_sort_material(MatSortParams p)
   }
 }
 
+// The same result for scenes with at most kFewMaterials materials (every scene the reference ships), without the
+// chain of 16 match_any rounds and without 256-bin bookkeeping: a thread takes 16 CONSECUTIVE slots (one 16-byte
+// load of keys, one of survival flags), ranks them against its own earlier slots with 4-bit counters packed in a
+// register (two halves of 8 slots, 8 bins x 4 bits each), the per-thread totals are scanned across the CTA as
+// 16-bit pairs (8 words: 4 for all paths, 4 for the survivors), one warp per bin resolves the two tile prefixes
+// in ONE look-back loop, and every slot's position is base[bin] + its rank.  Thread order is slot order, so the
+// permutation is the stable one.  ~1.1 warp instructions per key instead of 4.2, 40 registers instead of 118.
+constexpr int kFewMaterials = 8;
+
+// Two decoupled look-backs (all paths / survivors of one bin) advanced together by a full warp.
+__device__ __forceinline__ void lookback_warp2(unsigned long long* st_a, unsigned long long* st_b, size_t stride, unsigned int tile,
+                                               unsigned int epoch, unsigned int total_a, unsigned int total_b,
+                                               unsigned int* excl_a, unsigned int* excl_b) {
+  const int lane = threadIdx.x & 31;
+  if (lane == 0) {
+    st_volatile_u64(st_a + (size_t)tile * stride, lb_pack(epoch, tile == 0 ? 2u : 1u, total_a));
+    st_volatile_u64(st_b + (size_t)tile * stride, lb_pack(epoch, tile == 0 ? 2u : 1u, total_b));
+  }
+  unsigned int ea = 0, eb = 0;
+  bool done_a = false, done_b = false;  // warp-uniform
+  for (int base = (int)tile - 1; base >= 0 && !(done_a && done_b); base -= 32) {
+    const int t = base - lane;
+    unsigned int fa = 2u, va = 0u, fb = 2u, vb = 0u;  // lanes before tile 0 act as an empty inclusive prefix
+    if (t >= 0) {
+      unsigned long long wa, wb;
+      if (!done_a) {
+        do {
+          wa = ld_volatile_u64(st_a + (size_t)t * stride);
+        } while (lb_epoch(wa) != epoch || lb_flag(wa) == 0u);
+        fa = lb_flag(wa);
+        va = lb_value(wa);
+      }
+      if (!done_b) {
+        do {
+          wb = ld_volatile_u64(st_b + (size_t)t * stride);
+        } while (lb_epoch(wb) != epoch || lb_flag(wb) == 0u);
+        fb = lb_flag(wb);
+        vb = lb_value(wb);
+      }
+    }
+    const unsigned int ia = __ballot_sync(0xffffffffu, fa == 2u), ib = __ballot_sync(0xffffffffu, fb == 2u);
+    const int first_a = ia ? __ffs(ia) - 1 : 32, first_b = ib ? __ffs(ib) - 1 : 32;
+    unsigned int xa = (!done_a && lane <= first_a) ? va : 0u, xb = (!done_b && lane <= first_b) ? vb : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      xa += __shfl_xor_sync(0xffffffffu, xa, o);
+      xb += __shfl_xor_sync(0xffffffffu, xb, o);
+    }
+    ea += xa;
+    eb += xb;
+    done_a = done_a || ia != 0u;
+    done_b = done_b || ib != 0u;
+  }
+  if (tile > 0 && lane == 0) {
+    st_volatile_u64(st_a + (size_t)tile * stride, lb_pack(epoch, 2u, ea + total_a));
+    st_volatile_u64(st_b + (size_t)tile * stride, lb_pack(epoch, 2u, eb + total_b));
+  }
+  *excl_a = ea;
+  *excl_b = eb;
+}
+
+__global__ void __launch_bounds__(kSortThreads, 4) k_sort_material_few(MatSortParams p, int n_mat) {
+  __shared__ unsigned int s_warp[kSortWarps][8];          // warp totals, 16-bit pairs: [0..3] all paths, [4..7] survivors
+  __shared__ unsigned int s_wexcl[kSortWarps][8];         // ... exclusive over the warps of the CTA
+  __shared__ unsigned int s_tot[2][kFewMaterials];        // tile totals per bin: all / survivors
+  __shared__ unsigned int s_base[2][kFewMaterials];       // bin base + tile prefix: all / survivors
+  __shared__ unsigned int s_ex[kFewMaterials][kSortThreads];  // per thread and bin: slots of the tile in front (all | survivors << 16)
+  __shared__ __align__(16) unsigned int s_slot[kSortTile];  // per slot of the tile: bin << 28 | survivors in front << 14 | paths in front
+  __shared__ unsigned int s_tile;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n = p.ctr->n_live[p.depth];
+  if (tid == 0) s_tile = atomicAdd(&p.ctr->sort_ticket[p.depth], 1u);
+  __syncthreads();
+  const unsigned int tile = s_tile;
+  if ((long long)tile * kSortTile >= (long long)n) return;
+  const unsigned int epoch = p.ctr->serial * (unsigned int)(kMaxDepth + 1) + (unsigned int)p.depth + 1u;
+  const int tile_base = (int)tile * kSortTile;
+  const int base = tile_base + tid * 16;
+  unsigned int kw[4] = {0u, 0u, 0u, 0u}, lw[4] = {0u, 0u, 0u, 0u};  // (both arrays are allocated in whole tiles)
+  if (base < n) {
+    const uint4 a = *reinterpret_cast<const uint4*>(p.key + base);
+    const uint4 b = *reinterpret_cast<const uint4*>(p.live + base);
+    kw[0] = a.x; kw[1] = a.y; kw[2] = a.z; kw[3] = a.w;
+    lw[0] = b.x; lw[1] = b.y; lw[2] = b.z; lw[3] = b.w;
+  }
+  // the histograms of the depth (bin totals), wanted after the scan: issue the loads now
+  unsigned int tot = 0, ltot = 0;
+  if (lane < n_mat) {
+    tot = p.ctr->hist[p.depth][n_mat - 1 - lane];
+    ltot = p.ctr->hist_live[p.depth][n_mat - 1 - lane];
+  }
+  // ---- ranks inside the thread: 4-bit counters, bin c = n_mat - 1 - material (ascending bin = descending material) ----
+  unsigned int cnt[2] = {0u, 0u}, lcnt[2] = {0u, 0u};  // per half: 8 bins x 4 bits (a half holds 8 slots: counts <= 8)
+  unsigned int rk[2] = {0u, 0u}, lrk[2] = {0u, 0u};    // per half: 8 slots x 4 bits, rank within the THREAD (<= 15)
+  unsigned int bin_of[2] = {0u, 0u};                   // per half: 8 slots x 4 bits
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    const int h = k >> 3, q = k & 7;
+    const bool valid = base + k < n;
+    const unsigned int mat = (kw[k >> 2] >> (8 * (k & 3))) & 0xffu;
+    const bool alive = valid && ((lw[k >> 2] >> (8 * (k & 3))) & 0xffu) != 0u;
+    const unsigned int c = ((unsigned int)(n_mat - 1) - mat) & 7u;  // (an invalid slot reads material 0: a bin that exists)
+    const unsigned int sh = 4u * c;
+    unsigned int r = (cnt[h] >> sh) & 15u, lr = (lcnt[h] >> sh) & 15u;
+    if (h == 1) {
+      r += (cnt[0] >> sh) & 15u;
+      lr += (lcnt[0] >> sh) & 15u;
+    }
+    rk[h] |= r << (4 * q);
+    lrk[h] |= lr << (4 * q);
+    bin_of[h] |= c << (4 * q);
+    cnt[h] += (valid ? 1u : 0u) << sh;
+    lcnt[h] += (alive ? 1u : 0u) << sh;
+  }
+  // ---- thread totals as 16-bit pairs (bins 2j, 2j+1), inclusive scan over the warp ----
+  unsigned int v[8];
+  {
+    const unsigned int lo = (cnt[0] & 0x0f0f0f0fu) + (cnt[1] & 0x0f0f0f0fu);                // bins 0 2 4 6, one byte each
+    const unsigned int hi = ((cnt[0] >> 4) & 0x0f0f0f0fu) + ((cnt[1] >> 4) & 0x0f0f0f0fu);  // bins 1 3 5 7
+    const unsigned int llo = (lcnt[0] & 0x0f0f0f0fu) + (lcnt[1] & 0x0f0f0f0fu);
+    const unsigned int lhi = ((lcnt[0] >> 4) & 0x0f0f0f0fu) + ((lcnt[1] >> 4) & 0x0f0f0f0fu);
+    v[0] = __byte_perm(lo, hi, 0x0400) & 0x00ff00ffu;
+    v[1] = __byte_perm(lo, hi, 0x0501) & 0x00ff00ffu;
+    v[2] = __byte_perm(lo, hi, 0x0602) & 0x00ff00ffu;
+    v[3] = __byte_perm(lo, hi, 0x0703) & 0x00ff00ffu;
+    v[4] = __byte_perm(llo, lhi, 0x0400) & 0x00ff00ffu;
+    v[5] = __byte_perm(llo, lhi, 0x0501) & 0x00ff00ffu;
+    v[6] = __byte_perm(llo, lhi, 0x0602) & 0x00ff00ffu;
+    v[7] = __byte_perm(llo, lhi, 0x0703) & 0x00ff00ffu;
+  }
+  unsigned int own[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) own[i] = v[i];
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const unsigned int y = __shfl_up_sync(0xffffffffu, v[i], o);
+      if (lane >= o) v[i] += y;  // a warp holds 512 slots: the 16-bit fields cannot carry
+    }
+  }
+  if (lane == 31) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_warp[warp][i] = v[i];
+  }
+  __syncthreads();
+  if (tid < kSortWarps * 8) {  // (warp w, word i): sum of the warps in front; the last warp's inclusive sum is the tile total
+    const int w = tid >> 3, i = tid & 7;
+    unsigned int run = 0;
+    for (int ww = 0; ww < w; ++ww) run += s_warp[ww][i];  // (a tile holds 4096 slots: the 16-bit fields cannot carry)
+    s_wexcl[w][i] = run;
+    if (w == kSortWarps - 1) {
+      const unsigned int last = s_warp[w][i];
+      s_tot[i >> 2][2 * (i & 3)] = (run & 0xffffu) + (last & 0xffffu);
+      s_tot[i >> 2][2 * (i & 3) + 1] = (run >> 16) + (last >> 16);
+    }
+  }
+  __syncthreads();
+  // ---- publish the tile's counts at once (the tiles behind wait for them), resolve the prefixes later ----
+  unsigned int bin_total = 0, bin_ltotal = 0, pre = 0, lpre = 0, lall = 0;
+  if (warp < n_mat) {
+    const int b = warp;
+    pre = lane < b ? tot : 0u;
+    lpre = lane < b ? ltot : 0u;
+    lall = ltot;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {  // n_mat <= 8: lanes 0..7 hold the bins
+      pre += __shfl_xor_sync(0xffffffffu, pre, o);
+      lpre += __shfl_xor_sync(0xffffffffu, lpre, o);
+      lall += __shfl_xor_sync(0xffffffffu, lall, o);
+    }
+    bin_total = __shfl_sync(0xffffffffu, tot, b);
+    bin_ltotal = __shfl_sync(0xffffffffu, ltot, b);
+    if (lane == 0 && tile > 0) {  // (tile 0 publishes its inclusive prefix inside the look-back)
+      if (bin_total != 0u) st_volatile_u64(p.status + (size_t)tile * 256 + b, lb_pack(epoch, 1u, s_tot[0][b]));
+      if (bin_ltotal != 0u) st_volatile_u64(p.status_live + (size_t)tile * 256 + b, lb_pack(epoch, 1u, s_tot[1][b]));
+    }
+  }
+  // ---- every slot's place inside the tile, written in SLOT order to shared memory ----
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const unsigned int ea = v[i] - own[i] + s_wexcl[warp][i];          // paths of the tile in front of this thread, bins 2i, 2i+1
+    const unsigned int el = v[4 + i] - own[4 + i] + s_wexcl[warp][4 + i];  // survivors
+    s_ex[2 * i][tid] = (ea & 0xffffu) | (el << 16);
+    s_ex[2 * i + 1][tid] = (ea >> 16) | (el & 0xffff0000u);
+  }
+  // (a thread reads back only what it wrote itself: no barrier)
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    unsigned int pk[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const unsigned int c = (bin_of[h] >> (4 * q)) & 15u;
+      const unsigned int e = s_ex[c][tid];
+      const unsigned int ra = (e & 0xffffu) + ((rk[h] >> (4 * q)) & 15u);   // < 4096
+      const unsigned int rl = (e >> 16) + ((lrk[h] >> (4 * q)) & 15u);      // < 4096
+      pk[q] = (c << 28) | (rl << 14) | ra;
+    }
+    uint4* dst = reinterpret_cast<uint4*>(s_slot + tid * 16 + 8 * h);
+    dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+  }
+  // ---- per bin (one warp each): base of the bin from the histograms, tile prefixes by look-back ----
+  if (warp < n_mat) {
+    const int b = warp;
+    unsigned int e = 0, el = 0;
+    if (bin_total != 0u) {  // warp-uniform; bins nobody holds are never read
+      if (bin_ltotal != 0u) lookback_warp2(p.status + b, p.status_live + b, 256, tile, epoch, s_tot[0][b], s_tot[1][b], &e, &el);
+      else e = lookback_warp(p.status + b, 256, tile, epoch, s_tot[0][b]);
+    }
+    if (lane == 0) {
+      s_base[0][b] = pre + e;
+      s_base[1][b] = lpre + el;
+      // the number of survivors is the live count of the next depth
+      if (tile == 0 && b == 0) p.ctr->n_live[p.depth + 1] = (int)lall;
+    }
+  }
+  __syncthreads();
+  // ---- scatter, consecutive threads on consecutive slots: runs of one material become coalesced stores ----
+#pragma unroll 4
+  for (int r = 0; r < 16; ++r) {
+    const int s = r * kSortThreads + tid;
+    const int idx = tile_base + s;
+    if (idx < n) {
+      const unsigned int w = s_slot[s];
+      const unsigned int c = w >> 28;
+      const unsigned int j = s_base[0][c] + (w & 0x3fffu);
+      p.perm[j] = idx;
+      p.apos[j] = (int)(s_base[1][c] + ((w >> 14) & 0x3fffu));
+    }
+  }
+}
+
 // Compaction ranks WITHOUT a sort (SORT_BY_MATERIAL 0, apps/src/pathtrace.cu:38,611-613): paths are shaded in slot
 // order, so all the shade kernel needs is apos[j] = survivors in front of slot j (the live prefix of
 // thrust::stable_partition, :649) and the live count of the next depth.  One pass over the 1-byte survival flags:

@@ -48,6 +48,24 @@ def test_sort_desc_perm_equals_stable_sort(n, nmat):
 
 
 @pytest.mark.parametrize("n", SIZES)
+@pytest.mark.parametrize("nmat,general", [(1, False), (3, False), (6, False), (8, False), (6, True), (9, False), (200, False)])
+def test_material_sort_with_compaction_ranks(n, nmat, general):
+    """The kernels the renderer launches per depth (k_sort_material_few for <= 8 materials, k_sort_material
+    otherwise): thrust::sort_by_key(sortByMaterial) + the live prefix of stable_partition(isTerminate)."""
+    rng = np.random.default_rng(n * 31 + nmat)
+    m = rng.integers(0, nmat, n).astype(np.uint8)
+    if n > 100:
+        m[n // 4: n // 2] = nmat - 1  # a long run of one material crossing tiles
+    live = (rng.random(n) < 0.6).astype(np.uint8)
+    perm, rank, kept = api.sort_material_ranks(m, live, nmat, general)
+    want = np.argsort(-m.astype(np.int64), kind="stable").astype(np.int32)
+    assert np.array_equal(perm, want)
+    ls = live[want].astype(np.int64)
+    assert np.array_equal(rank, (np.cumsum(ls) - ls).astype(np.int32))
+    assert kept == int(live.sum())
+
+
+@pytest.mark.parametrize("n", SIZES)
 def test_radix_sort_pairs(n):
     rng = np.random.default_rng(n + 3)
     k = rng.integers(0, 1 << 30, n, dtype=np.int64).astype(np.uint32)

@@ -1,4 +1,4 @@
 cd "${GRAFT_REPO_ROOT:-.}"
 O=gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q > $O/t8.log 2>&1; tail -8 $O/t8.log
-timeout 300 python tools/exp_walk.py head 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_gpu_prims.py tests/test_gpu_parity.py -m gpu -x -q > $O/t11.log 2>&1; tail -n 4 $O/t11.log
+timeout 300 python tools/exp_walk.py v6 2>&1 | tail -n 3
