@@ -40,9 +40,16 @@
 namespace b2pt {
 
 constexpr int kWalkThreads = 256;
-constexpr int kWalkMinBlocks = 3;  // resident CTAs per SM the register budget is set for
-constexpr int kWalkShort = 8;      // (node, tn) entries per lane in shared memory
-constexpr int kWalkSpill = 88;     // spill entries per lane: 96 in all = 3 per level of a 32-level wide tree
+#ifndef B2PT_WALK_MINBLOCKS
+#define B2PT_WALK_MINBLOCKS 3
+#endif
+constexpr int kWalkMinBlocks = B2PT_WALK_MINBLOCKS;  // resident CTAs per SM the register budget is set for
+#ifndef B2PT_WALK_SHORT
+#define B2PT_WALK_SHORT 16
+#endif
+constexpr int kWalkShort = B2PT_WALK_SHORT;   // (node, tn) entries per lane in shared memory: deep enough that the
+                                              // spill below is the exception (its code stays off the fast path)
+constexpr int kWalkSpill = 96 - kWalkShort;   // spill entries per lane: 96 in all = 3 per level of a 32-level wide tree
 #ifndef B2PT_REFILL_MIN
 #define B2PT_REFILL_MIN 8
 #endif
@@ -230,13 +237,16 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkMinBlocks) k_mesh_walk(Isec
     else if (sp < kWalkShort + kWalkSpill) spill[sp - kWalkShort] = e;                  \
     ++sp;                                                                               \
   }
-// Next thing to do: entries that fell behind the closest hit are dropped without touching memory.
+// Next thing to do: entries that fell behind the closest hit are dropped without touching memory.  The common
+// case -- the stack lies in shared memory -- is one LDS and one compare per entry; the spill is a rare side path.
 #define B2PT_WALK_POP_NEXT()                                                            \
   {                                                                                     \
     node = kWalkDone;                                                                   \
     while (sp > 0) {                                                                    \
       --sp;                                                                             \
-      const int2 e = sp < kWalkShort ? sst[sp * kWalkThreads] : spill[min(sp - kWalkShort, kWalkSpill - 1)]; \
+      int2 e;                                                                           \
+      if (sp < kWalkShort) e = sst[sp * kWalkThreads];                                  \
+      else e = spill[min(sp - kWalkShort, kWalkSpill - 1)];                             \
       if (__int_as_float(e.y) <= R.lim) {                                               \
         node = e.x;                                                                     \
         break;                                                                          \
@@ -370,10 +380,22 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkMinBlocks) k_mesh_walk(Isec
         B2PT_CSWAP(0, 1) B2PT_CSWAP(2, 3) B2PT_CSWAP(0, 2) B2PT_CSWAP(1, 3) B2PT_CSWAP(1, 2)
 #undef B2PT_CSWAP
         if (ch[0] != kEmptyChild) {
-          // nearest first; the others go on the stack farthest first
-          if (ch[3] != kEmptyChild) B2PT_WALK_PUSH(ch[3], tn[3])
-          if (ch[2] != kEmptyChild) B2PT_WALK_PUSH(ch[2], tn[2])
-          if (ch[1] != kEmptyChild) B2PT_WALK_PUSH(ch[1], tn[1])
+          // nearest first; the others go on the stack farthest first.  With room for all three in shared memory
+          // (the rule) the pushes are three predicated stores; the spill path keeps the general form.
+          if (sp + 3 <= kWalkShort) {
+            const bool p3 = ch[3] != kEmptyChild, p2 = ch[2] != kEmptyChild, p1 = ch[1] != kEmptyChild;
+            int2* top = sst + sp * kWalkThreads;
+            if (p3) top[0] = make_int2(ch[3], __float_as_int(tn[3]));
+            top += p3 ? kWalkThreads : 0;
+            if (p2) top[0] = make_int2(ch[2], __float_as_int(tn[2]));
+            top += p2 ? kWalkThreads : 0;
+            if (p1) top[0] = make_int2(ch[1], __float_as_int(tn[1]));
+            sp += (p3 ? 1 : 0) + (p2 ? 1 : 0) + (p1 ? 1 : 0);
+          } else {
+            if (ch[3] != kEmptyChild) B2PT_WALK_PUSH(ch[3], tn[3])
+            if (ch[2] != kEmptyChild) B2PT_WALK_PUSH(ch[2], tn[2])
+            if (ch[1] != kEmptyChild) B2PT_WALK_PUSH(ch[1], tn[1])
+          }
           node = ch[0];
         } else {
           B2PT_WALK_POP_NEXT()
