@@ -807,7 +807,6 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
   c->fuse = opt.concurrent_contexts <= 1;
   if (const char* e = getenv("B2PT_FUSE")) c->fuse = atoi(e) != 0;
   if (const char* e = getenv("B2PT_SORT_GENERAL")) c->sort_general = atoi(e) != 0;
-  if (const char* e = getenv("B2PT_LONG_WALK")) c->long_walk = std::max(atoi(e), 1);
   if (const char* e = getenv("B2PT_LONG_CARRY")) c->long_carry = std::max(0, std::min(atoi(e), kLongCarry));  // tests: 0 = always restart at the root
   if (const char* e = getenv("B2PT_LONG_CAP")) c->long_cap = std::max(1, std::min(atoi(e), c->long_cap));      // tests: a full hand-off queue
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_intersect_analytic, 256, 0));
@@ -817,11 +816,13 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
     // and fill each other's tails (measured: 4 contexts, 1.18 -> 1.03 ms per iteration in aggregate)
     c->analytic_grid = std::min(c->analytic_grid, c->sm_count * 2);
     c->walk_grid = c->sm_count;
+    c->long_walk = 32;  // with the SMs shared, throughput counts, not the length of the launch: 24 -> 32 steps is -1.4 % per iteration
     c->long_grid = c->sm_count * 2;
     c->finish_grid = c->sm_count * 2;
     c->shade_stride_grid = c->sm_count * 4;
   }
   // experiment knobs: resident CTAs per SM of the persistent / grid-stride kernels
+  if (const char* e = getenv("B2PT_LONG_WALK")) c->long_walk = std::max(atoi(e), 1);
   if (const char* e = getenv("B2PT_WALK_CTAS")) c->walk_grid = c->sm_count * std::max(1, std::min(atoi(e), walk_occ));
   if (const char* e = getenv("B2PT_LONG_CTAS")) c->long_grid = c->sm_count * std::max(1, atoi(e));
   if (const char* e = getenv("B2PT_ANALYTIC_CTAS")) c->analytic_grid = c->sm_count * std::max(1, atoi(e));

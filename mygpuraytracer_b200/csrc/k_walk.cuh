@@ -51,7 +51,7 @@ constexpr int kWalkShort = B2PT_WALK_SHORT;   // (node, tn) entries per lane in 
                                               // spill below is the exception (its code stays off the fast path)
 constexpr int kWalkSpill = 96 - kWalkShort;   // spill entries per lane: 96 in all = 3 per level of a 32-level wide tree
 #ifndef B2PT_REFILL_MIN
-#define B2PT_REFILL_MIN 8
+#define B2PT_REFILL_MIN 12
 #endif
 constexpr int kRefillMin = B2PT_REFILL_MIN;  // waiting lanes that trigger a refill pass
 constexpr int kWalkMeshes = 4;     // meshes whose geom is staged in shared memory

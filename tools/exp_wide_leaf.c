@@ -194,6 +194,7 @@ static void per_walk(const char* name) {
          reach_nodes, reach_nodes * (W <= 4 ? 128.0 : 256.0) / 1e6, W <= 4 ? 128 : 256);
 }
 
+static int refill_min = 8;  // idle lanes that trigger a refill (EXP_REFILL_MIN)
 // The warp-synchronous schedule of k_mesh_walk.  rays_per_lane = 1: every warp gets 32 rays and never refills.
 static void per_warp(const char* name, int rays_per_lane, int fused) {
   const int nwarps = (nrays + 32 * rays_per_lane - 1) / (32 * rays_per_lane);
@@ -215,7 +216,7 @@ static void per_warp(const char* name, int rays_per_lane, int fused) {
     while (1) {
       int nn_ = 0, nl_ = 0, idle = 0;
       for (int l = 0; l < 32; ++l) { if (!active[l]) { ++idle; continue; } if (w[l].node >= 0) ++nn_; else ++nl_; }
-      if (nn_ + nl_ == 0 || (idle >= 8 && qhead < nrays && rays_per_lane > 1)) {
+      if (nn_ + nl_ == 0 || (idle >= refill_min && qhead < nrays && rays_per_lane > 1)) {
         int got = 0;
         for (int l = 0; l < 32 && qhead < nrays && rays_per_lane > 1; ++l)
           if (!active[l]) { walk_begin(&w[l], rays + 8 * (size_t)qhead++); steps[l] = 0; active[l] = w[l].node != EMPTY; ++got; }
@@ -258,6 +259,7 @@ int main(int argc, char** argv) {
   if (fread(rays, 1, sz, f) != (size_t)sz) return 1;
   fclose(f);
   if (argc > 3) handoff = atoi(argv[3]);
+  if (getenv("EXP_REFILL_MIN")) refill_min = atoi(getenv("EXP_REFILL_MIN"));
   leafbox = malloc(sizeof(Box) * n); key = malloc(8 * (size_t)n); order = malloc(4 * (size_t)n);
   kids = malloc(sizeof(Kids) * n); nbox = malloc(sizeof(Box) * n); wide = malloc(sizeof(Wide) * (size_t)n);
   ncount = malloc(4 * (size_t)n); nfirst = malloc(4 * (size_t)n); reach = malloc(n);
@@ -291,8 +293,9 @@ int main(int argc, char** argv) {
   refit(root);
   printf("%d triangles, %d rays, hand-off after %d steps\n", n, nrays, handoff);
   const int Ws[] = {4, 6, 8}, Ls[] = {1, 2, 4, 8};
-  for (int a = 0; a < 3; ++a)
-    for (int b = 0; b < 4; ++b) {
+  const int only = getenv("EXP_ONLY") != NULL;  // EXP_ONLY=1: the shipped shape (W = 4, L = 2) only
+  for (int a = 0; a < (only ? 1 : 3); ++a)
+    for (int b = (only ? 1 : 0); b < (only ? 2 : 4); ++b) {
       W = Ws[a]; L = Ls[b];
       emit_wide();
       char nm[64];
@@ -303,6 +306,7 @@ int main(int argc, char** argv) {
       per_warp("one wave, fused step", 1, 1);
       per_warp("3 rays/lane, alternating", 3, 0);
       per_warp("3 rays/lane, fused", 3, 1);
+      per_warp("12 rays/lane, alternating", 12, 0);
     }
   return 0;
 }
