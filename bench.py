@@ -46,13 +46,16 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of each kernel, from the committed `ncu --set full`
-# capture of this workload (profiles/, cold caches: an upper bound on the warm traffic); see TRAFFIC_SOURCE
-TRAFFIC_SOURCE = "profiles/r01_final_ncu_depth01.md, r01_final_ncu_unfused_depth1.md (depth-1 launches)"
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of each kernel, from the committed `ncu --set full`
+# capture of this workload (cold caches: an upper bound on the warm traffic).  The capture is the DEPTH-1 launch
+# (951 052 rays) of a lane context of the timed region; `roofline.traffic_vs_algorithmic` compares it with the
+# algorithmic bytes of that same launch, not with the average launch.
+TRAFFIC_SOURCE = "profiles/r02_ncu_depth1_shared.md (depth-1 launches, shared-SM grids); fused kernels: profiles/r01_final_ncu_depth01.md"
 TRAFFIC = {
-    "k_intersect_analytic": 31.24e6, "k_mesh_walk": 71.61e6, "k_mesh_walk_long": 20.69e6, "k_mesh_finish": 50.24e6,
-    "k_sort_material": 1.99e6, "k_shade_compact": 169.64e6, "k_shade_trace": 197.83e6, "k_generate_trace": 123.39e6,
+    "k_intersect_analytic": 32.63e6, "k_mesh_walk": 31.10e6, "k_mesh_walk_long": 8.67e6, "k_mesh_finish": 53.14e6,
+    "k_sort_material": 1.99e6, "k_shade_compact": 169.11e6, "k_shade_trace": 197.83e6, "k_generate_trace": 123.39e6,
 }
+TRAFFIC_DEPTH = 1
 
 METRIC = "Mpaths/s"
 # BASELINE.json "configs", in order.  4 is the configuration the metric is quoted on (the default).
@@ -540,6 +543,7 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 "k_mesh_walk_long": ("walk_long", 57.0 * n_long),
                 "k_mesh_finish": ("finish", 57.0 * n_walks),             # queue 4 + partial record 20 read, record 32 + flag 1 written
                 "k_sort_material": ("sort", 10.0 * segments),            # key 1 + flag 1 read, permutation 4 + rank 4 written
+                                                                         # (k_sort_material_few when the scene has <= 8 materials)
                 "k_shade_compact": ("shade", 132.0 * segments),          # permutation 4 + hit 32 + state 48 read, state 48 written
                 "k_generate": ("generate", 44.0 * P),
             }
@@ -552,9 +556,15 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             dom = max((k for k in kern if k != "k_generate"), key=lambda k: prof.get(kern[k][0], 0.0))
             dom_ms, dom_bytes = prof[kern[dom][0]], kern[dom][1]
             dom_gbs = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+            # algorithmic bytes of the launch the ncu capture holds (depth TRAFFIC_DEPTH), for traffic_vs_algorithmic
+            per_unit = dom_bytes / max(1, {"k_mesh_walk": n_walks, "k_mesh_finish": n_walks, "k_mesh_walk_long": n_long}.get(dom, segments))
+            units_d = {"k_mesh_walk": int(extras["walks"][TRAFFIC_DEPTH]), "k_mesh_finish": int(extras["walks"][TRAFFIC_DEPTH]),
+                       "k_mesh_walk_long": int(extras["long_walks"][TRAFFIC_DEPTH])}.get(dom, int(live[TRAFFIC_DEPTH]))
             line["roofline"] = {
                 "kernel": dom, "bound": "hbm", "achieved": dom_gbs, "peak": peak, "unit": "GB/s", "frac": dom_gbs / peak,
                 "traffic": TRAFFIC.get(dom), "traffic_source": TRAFFIC_SOURCE, "peak_source": peak_src,
+                "traffic_launch": f"depth {TRAFFIC_DEPTH}", "algorithmic_bytes_traffic_launch": per_unit * units_d,
+                "traffic_vs_algorithmic": (TRAFFIC.get(dom, 0.0) / (per_unit * units_d)) if units_d else None,
                 "regime": "a lane context of the timed region (grids sized to a share of the SMs, unfused kernels) rendering one "
                           "iteration ALONE, CUDA events around every launch: the regime ncu's serialised launch list of this "
                           "command measures",

@@ -427,10 +427,12 @@ __global__ void __launch_bounds__(kSortThreads, 4) k_sort_material_few(MatSortPa
   __shared__ unsigned int s_tile;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n = p.ctr->n_live[p.depth];
+  // the grid is sized for a full frame: CTAs beyond the live paths leave before they queue up for a ticket
+  // (exactly ceil(n / tile) CTAs stay, so the tickets they draw are still 0 .. tiles-1)
+  if ((long long)blockIdx.x * kSortTile >= (long long)n) return;
   if (tid == 0) s_tile = atomicAdd(&p.ctr->sort_ticket[p.depth], 1u);
   __syncthreads();
   const unsigned int tile = s_tile;
-  if ((long long)tile * kSortTile >= (long long)n) return;
   const unsigned int epoch = p.ctr->serial * (unsigned int)(kMaxDepth + 1) + (unsigned int)p.depth + 1u;
   const int tile_base = (int)tile * kSortTile;
   const int base = tile_base + tid * 16;
