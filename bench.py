@@ -24,6 +24,9 @@ Keys beyond the base contract:
                   a lane context of the timed region, run alone): algorithmic bytes / average launch time against
                   the measured HBM copy bandwidth (MEASURED_PEAKS.json); `regime` says which grids were timed
   roofline_iter   Bytes_iter = 84*P + 280*S over the step
+  roofline_kernels  every kernel: algorithmic bytes over its live launch time against measured HBM, and (default
+                  workload) `issue`: its warp instructions (committed ncu pass) over the same time against the issue
+                  capacity -- the bound that matters for the intersection kernels; issue_iter is the same for a step
   cpu_baseline    the reference's own intersections.h / interactions.h compiled for the host
                   (oracle/_ref/ref_cpu, kind "reference") or the C oracle (kind "port") on a bounded sample
   cpu_baseline_config1  BASELINE.md's B-CPU line: scenes/cornell.txt 800x800 depth 8, iteration 1, in full
@@ -56,6 +59,16 @@ TRAFFIC = {
     "k_sort_material": 1.99e6, "k_shade_compact": 169.11e6, "k_shade_trace": 197.83e6, "k_generate_trace": 123.39e6,
 }
 TRAFFIC_DEPTH = 1
+# Warp instructions of ONE iteration per kernel (ncu smsp__inst_executed.sum summed over the 8 depths, lanes per
+# instruction beside it) for the DEFAULT workload only (config 4, 250 500 triangles): profiles/r02_inst_per_kernel.md.
+# Against them `roofline_kernels[...]["issue"]` states what the HBM fraction cannot say for the kernels that are
+# bound by instruction issue and latency: warp instructions per second of the live launch times against the issue
+# capacity of the GPU (SMs x 4 schedulers x SM clock).
+INST_SOURCE = "profiles/r02_inst_per_kernel.md (end of round 2)"
+INST_PER_STEP = {  # kernel: (million warp instructions, active lanes per instruction)
+    "k_intersect_analytic": (183.06, 20.7), "k_mesh_walk": (166.54, 14.1), "k_mesh_walk_long": (26.71, 17.3),
+    "k_mesh_finish": (20.78, 12.6), "k_sort_material": (17.62, 30.7), "k_shade_compact": (50.60, 30.3), "k_generate": (9.06, 32.0),
+}
 
 METRIC = "Mpaths/s"
 # BASELINE.json "configs", in order.  4 is the configuration the metric is quoted on (the default).
@@ -525,6 +538,13 @@ def run_ours(args, rank: int, world: int, local_rank: int):
             "live_paths_per_depth": [int(x) for x in live[: args.depth + 1]],
             "scene_load_s": round(load_s, 2), "image_checksum": checksum,
         }
+        if args.config == 4 and args.triangles == 250_000 and clocks and clocks.get("sm_mhz"):
+            # the whole step against the issue capacity: what four lanes together reach
+            tot = sum(v[0] for v in INST_PER_STEP.values()) * 1e6
+            cap = torch.cuda.get_device_properties(local_rank).multi_processor_count * 4 * clocks["sm_mhz"] * 1e6
+            line["issue_iter"] = {"warp_inst_per_iteration": tot, "achieved": tot / (dev_ms / K * 1e-3) / 1e9, "peak": cap / 1e9,
+                                  "unit": "G warp inst/s", "frac": tot / (dev_ms / K * 1e-3) / cap, "source": INST_SOURCE,
+                                  "note": "per GPU; instruction counts of one iteration from the committed ncu pass, time from this run"}
         iter_bytes = 84.0 * P + 280.0 * segments
         iter_gbs = iter_bytes * world / (dev_ms / K * 1e-3) / 1e9
         line["roofline_iter"] = {"bytes_per_step": iter_bytes * world, "achieved": iter_gbs, "peak": peak * world, "unit": "GB/s",
@@ -553,6 +573,12 @@ def run_ours(args, rank: int, world: int, local_rank: int):
                 gbs = nbytes / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
                 roofline_kernels[name] = {"ms_per_step": kms, "algorithmic_bytes_per_step": nbytes, "achieved": gbs,
                                           "unit": "GB/s", "frac": gbs / peak}
+                if args.config == 4 and args.triangles == 250_000 and name in INST_PER_STEP and kms > 0 and clocks and clocks.get("sm_mhz"):
+                    minst, lanes = INST_PER_STEP[name]
+                    cap = torch.cuda.get_device_properties(local_rank).multi_processor_count * 4 * clocks["sm_mhz"] * 1e6
+                    roofline_kernels[name]["issue"] = {
+                        "warp_inst_per_step": minst * 1e6, "lanes_per_inst": lanes, "achieved": minst * 1e6 / (kms * 1e-3) / 1e9,
+                        "peak": cap / 1e9, "unit": "G warp inst/s", "frac": minst * 1e6 / (kms * 1e-3) / cap, "source": INST_SOURCE}
             dom = max((k for k in kern if k != "k_generate"), key=lambda k: prof.get(kern[k][0], 0.0))
             dom_ms, dom_bytes = prof[kern[dom][0]], kern[dom][1]
             dom_gbs = dom_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
@@ -682,7 +708,8 @@ def main():
     ap.add_argument("--height", type=int, default=0)
     ap.add_argument("--depth", type=int, default=0)
     ap.add_argument("--triangles", type=int, default=250_000)
-    ap.add_argument("--streams", type=int, default=4, help="lanes (contexts rendering ahead) per GPU")
+    ap.add_argument("--streams", type=int, default=6,
+                    help="lanes (contexts rendering ahead) per GPU; 4 / 5 / 6 lanes: 2559 / 2604 / 2610 Mpaths/s on one B200")
     ap.add_argument("--reduce", default="p2p", choices=["p2p", "nccl"],
                     help="how a frame is combined across ranks: k_frame_reduce over NVLink peer memory, or one NCCL reduce")
     ap.add_argument("--spp", type=int, default=0, help="render this many samples per pixel from scratch instead of timing windows")
