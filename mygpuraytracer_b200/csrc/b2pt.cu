@@ -417,9 +417,15 @@ static int build_mesh(B2ptCtx* c, const float* pos_host, const float* uv_host, i
   RadixTemps& rtemps = rguard.t;
   if ((rc = radix_temps_alloc(&rtemps, n))) return rc;
 
-  EventPair ev;
+  // build_ms is DEVICE time: the build has two small read-backs (tree depth, node count) and one allocation of
+  // the final size in the middle, so it is timed as three segments between them and the segments are added
+  EventPair ev, ev2, ev3;
   CK(cudaEventCreate(&ev.a));
   CK(cudaEventCreate(&ev.b));
+  CK(cudaEventCreate(&ev2.a));
+  CK(cudaEventCreate(&ev2.b));
+  CK(cudaEventCreate(&ev3.a));
+  CK(cudaEventCreate(&ev3.b));
   CK(cudaEventRecord(ev.a, s));
   const int blocks = (n + 255) / 256;
   k_bounds_init<<<1, 32, 0, s>>>(bounds);
@@ -447,8 +453,10 @@ static int build_mesh(B2ptCtx* c, const float* pos_host, const float* uv_host, i
     CK(cudaMemsetAsync(wdepth, 0, (size_t)(n - 1) * sizeof(int), s));
     const int one = 1;
     CK(cudaMemcpyAsync(wdepth, &one, sizeof(int), cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(ev.b, s));
     CK(cudaMemcpyAsync(&hb, bounds, sizeof hb, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    CK(cudaEventRecord(ev2.a, s));
     const int levels = std::max(1, std::min(hb.max_depth, 64));
     for (int level = 1; level <= levels; ++level) k_wide_levels<<<iblocks, 256, 0, s>>>(n, nodes_tmp, wdepth, level, bounds);
     c->launches += levels;
@@ -458,6 +466,7 @@ static int build_mesh(B2ptCtx* c, const float* pos_host, const float* uv_host, i
     CK(cudaMemsetAsync(scan_status, 0, (size_t)scan_tiles * sizeof(unsigned long long), s));
     k_scan_family<0><<<scan_tiles, kScanThreads, 0, s>>>(flag, nullptr, n - 1, slot, nullptr, scan_ticket, scan_status, 1u, nullptr);
     c->launches += 2;
+    CK(cudaEventRecord(ev2.b, s));
     int last[2] = {0, 0};
     CK(cudaMemcpyAsync(&last[0], slot + (n - 2), sizeof(int), cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(&last[1], flag + (n - 2), sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -471,6 +480,8 @@ static int build_mesh(B2ptCtx* c, const float* pos_host, const float* uv_host, i
   out->tris = out->nodes + node_f4;
   out->bvh_bytes = (node_f4 + tri_f4) * sizeof(float4);
   out->info.n_nodes = n_nodes;
+  if (!tree) CK(cudaEventRecord(ev.b, s));
+  CK(cudaEventRecord(ev3.a, s));
   if (tree) {
     k_compact_nodes<<<(n - 1 + 255) / 256, 256, 0, s>>>(n, nodes_tmp, wdepth, slot, out->nodes);
     c->launches += 1;
@@ -478,10 +489,16 @@ static int build_mesh(B2ptCtx* c, const float* pos_host, const float* uv_host, i
     CK(cudaMemsetAsync(out->nodes, 0, node_f4 * sizeof(float4), s));
   }
   CK(cudaMemcpyAsync(out->tris, tris_tmp, tri_f4 * sizeof(float4), cudaMemcpyDeviceToDevice, s));
-  CK(cudaEventRecord(ev.b, s));
+  CK(cudaEventRecord(ev3.b, s));
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(s));
-  CK(cudaEventElapsedTime(&out->info.build_ms, ev.a, ev.b));
+  {
+    float m1 = 0.0f, m2 = 0.0f, m3 = 0.0f;
+    CK(cudaEventElapsedTime(&m1, ev.a, ev.b));
+    if (tree) CK(cudaEventElapsedTime(&m2, ev2.a, ev2.b));
+    CK(cudaEventElapsedTime(&m3, ev3.a, ev3.b));
+    out->info.build_ms = m1 + m2 + m3;
+  }
   CK(cudaMemcpy(&hb, bounds, sizeof hb, cudaMemcpyDeviceToHost));
   out->info.max_depth = tree ? hb.max_depth : 1;
   out->wide_depth = tree ? hb.wide_depth : 0;
