@@ -103,6 +103,17 @@ def test_mesh_scenes_bvh_bitexact(tmp_path, name, tris):
     assert (pod.geoms["type"][np.maximum(d0.geom, 0)][d0.t > 0] == abi.OBJ).sum() > 20, "mesh must be visible"
 
 
+@pytest.mark.parametrize("env", [{"B2PT_SORT_GENERAL": "1"}, {"B2PT_SORT_GENERAL": "0"}])
+def test_both_material_sorts_in_the_renderer(tmp_path, monkeypatch, env):
+    """Scenes with at most 8 materials sort with k_sort_material_few, the others with the 256-bin k_sort_material:
+    the same mesh scene through both (the switch only exists for this test and for A/B timing), every stage --
+    the sort permutation and the compaction ranks behind partition_pixel included -- identical to the oracle."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    pod = _mesh_scene(tmp_path, "cornellSpaceship", 173, 99, 5000)  # 17 127 paths: five sort tiles, the last one ragged
+    compare_iteration(pod, {}, what=f"cornellSpaceship/sort {env}")
+
+
 @pytest.mark.parametrize("tris,env", [(1000, {}), (20000, {}), (20000, {"B2PT_LONG_WALK": "2"})])
 def test_two_meshes_one_scaled_bitexact(tmp_path, monkeypatch, tris, env):
     """Two OBJ geoms, the second scaled by 1.5 (not rigid: its object-space
