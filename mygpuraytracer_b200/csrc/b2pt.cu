@@ -10,7 +10,8 @@
 //     k_intersect_analytic             memset + computeIntersections (cubes, spheres) + sort key + histograms
 //     k_mesh_walk, k_mesh_walk_long,   computeIntersections (OBJ geoms): LBVH walk, long walks, record completion
 //     k_mesh_finish
-//     k_sort_material                  thrust::sort_by_key  -> 4-byte permutation + compaction ranks
+//     k_sort_material_few / k_sort_material   thrust::sort_by_key  -> 4-byte permutation + compaction ranks
+//                                        (<= 8 materials: the packed-counter kernel; else the 256-bin one)
 //     k_shade_compact                  shadeFakeMaterial + stable_partition + finalGather
 //
 // Every kernel reads its element count from device memory, so the sequence is

@@ -18,6 +18,11 @@
 // device ticket so a tile's predecessors are always resident or finished.
 // Bin bases come from a histogram computed beforehand (by k_intersect for the
 // material sort, by k_radix_hist for the LSD sort).
+//
+// Kernels: k_onesweep_pass<Policy> (the LSD passes, and the stand-alone b2pt_sort_desc_perm), k_sort_material (the
+// renderer's material sort with compaction ranks, any number of materials), k_sort_material_few (the same result for
+// scenes with at most 8 materials: packed counters instead of match_any rounds, what every shipped scene uses),
+// k_rank_live (SORT_BY_MATERIAL 0 and the pixel-keyed RNG: compaction ranks only).
 #pragma once
 
 #include "k_prims.cuh"
