@@ -1,4 +1,5 @@
+# scratch: the command of the last ad-hoc gpurun call of the session (kept so that the calls in profiles/r02_notes.md can be repeated)
 cd "${GRAFT_REPO_ROOT:-.}"
-for v in base sh5 sh6 an5 fi5 all5 an1 fi1 sh1; do
-  B2PT_LIB=build/variants/libb2pt_$v.so timeout 300 python tools/exp_walk.py $v 2>&1 | tail -n 3 | cut -c1-215
-done
+O=gpurun_out
+timeout 900 python -m pytest tests -m gpu -x -q > $O/tests.log 2>&1; tail -n 4 $O/tests.log
+timeout 300 python tools/exp_walk.py head 2>&1 | tail -n 3
