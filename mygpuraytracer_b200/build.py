@@ -60,5 +60,23 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+# The same library with 8-wide BVH nodes (two 128-byte lines per node, -DB2PT_WIDE=8): built and kept beside the
+# product so that tests/test_gpu_wide8.py can run the parity cases through it.  It is NOT what the renderer loads:
+# measured on the B200 it is slower than the 4-wide walk (walk 0.497 -> 0.644 ms per iteration for 26 % fewer
+# steps and a third fewer hand-offs: profiles/r02_notes.md).
+LIB_WIDE8 = os.path.join(HERE, "libb2pt_wide8.so")
+
+
+def build_wide8(force: bool = False) -> str:
+    if not force and os.path.exists(LIB_WIDE8) and all(os.path.getmtime(p) <= os.path.getmtime(LIB_WIDE8) for p in _deps()):
+        return LIB_WIDE8
+    r = subprocess.run(["nvcc"] + NVCC_FLAGS + ["-DB2PT_WIDE=8"] + sources() + ["-o", LIB_WIDE8], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed (wide8):\n" + r.stdout + r.stderr)
+    return LIB_WIDE8
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--wide8" in sys.argv:
+        print(build_wide8(force="--force" in sys.argv))

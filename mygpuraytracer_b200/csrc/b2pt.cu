@@ -405,7 +405,7 @@ static int build_mesh(B2ptCtx* c, const float* pos_host, const float* uv_host, i
   CK(tmp.get(&leaf_box, (size_t)n * 2));
   CK(tmp.get(&node_box, (size_t)inner * 2));
   CK(tmp.get(&tris_tmp, (size_t)n * 3));
-  CK(tmp.get(&nodes_tmp, (size_t)inner * 8));
+  CK(tmp.get(&nodes_tmp, (size_t)inner * kNodeF4));
   CK(tmp.get(&children, (size_t)inner));
   CK(tmp.get(&range, (size_t)inner));
   CK(tmp.get(&parent, (size_t)(2 * n)));
@@ -476,7 +476,7 @@ static int build_mesh(B2ptCtx* c, const float* pos_host, const float* uv_host, i
   }
   // ... and keep only those: nodes and triangles share one allocation so that a single L2 access-policy window
   // can keep the whole acceleration structure resident
-  const size_t node_f4 = (size_t)std::max(n_nodes, 1) * 8, tri_f4 = (size_t)n * 3;
+  const size_t node_f4 = (size_t)std::max(n_nodes, 1) * kNodeF4, tri_f4 = (size_t)n * 3;
   if ((rc = c->dalloc(&out->nodes, node_f4 + tri_f4))) return rc;
   out->tris = out->nodes + node_f4;
   out->bvh_bytes = (node_f4 + tri_f4) * sizeof(float4);
@@ -505,11 +505,11 @@ static int build_mesh(B2ptCtx* c, const float* pos_host, const float* uv_host, i
   out->wide_depth = tree ? hb.wide_depth : 0;
   out->root = tree ? 0 : leaf_code(0, n);
   if (getenv("B2PT_TRAVERSAL_STATS"))
-    fprintf(stderr, "[b2pt bvh] %d triangles: binary depth %d, %d wide nodes (%.1f MB), 4-wide depth %d, leaves of <= %d triangles\n", n,
-            out->info.max_depth, n_nodes, n_nodes * 128.0 / 1e6, out->wide_depth, kLeafTris);
+    fprintf(stderr, "[b2pt bvh] %d triangles: binary depth %d, %d wide nodes (%.1f MB), wide depth %d, leaves of <= %d triangles\n", n,
+            out->info.max_depth, n_nodes, n_nodes * 16.0 * kNodeF4 / 1e6, out->wide_depth, kLeafTris);
   // a walk's stack holds at most three entries per inner wide node on its path (nearest child first, the other
   // hits pushed); k_mesh_walk_long's depth-first fallback relies on the same bound
-  if (out->info.max_depth > 64 || 3 * out->wide_depth > kWalkShort + kWalkSpill)
+  if (out->info.max_depth > 64 || (kWide - 1) * out->wide_depth > kWalkShort + kWalkSpill)
     return fail(B2PT_ERR_RANGE, "LBVH deeper than the traversal stack");
   return 0;
 }

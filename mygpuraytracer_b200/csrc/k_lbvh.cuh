@@ -233,6 +233,14 @@ __global__ void __launch_bounds__(256) k_tree_depth(int n, const int* __restrict
 // (both planes of an axis sit in one aligned 32-byte half-sector: the walk picks the plane a ray enters
 // through with a 16-byte address offset).  An unused slot has min = +FLT_MAX, max = -FLT_MAX.
 constexpr int kEmptyChild = 0x40000000;
+#ifndef B2PT_WIDE
+#define B2PT_WIDE 4
+#endif
+// Children per traversal node: 4, or 8 as TWO of the 128-byte lines above side by side (slots 0..3 in the first line,
+// 4..7 in the second: the walk runs the same four-slot box test on each).  kNodeF4 float4s per node.
+constexpr int kWide = B2PT_WIDE;
+static_assert(kWide == 4 || kWide == 8, "4- or 8-wide nodes");
+constexpr int kNodeF4 = 2 * kWide;
 #ifndef B2PT_LEAF_TRIS
 #define B2PT_LEAF_TRIS 2
 #endif
@@ -257,14 +265,15 @@ __global__ void __launch_bounds__(256) k_emit_wide4(int n, const int2* __restric
   if (i >= n - 1) return;
   // a child can be opened if it is an inner node with more triangles than a leaf may hold
   auto openable = [&](int c) { return c >= 0 && range[c].y - range[c].x + 1 > kLeafTris; };
-  int id[4] = {kEmptyChild, kEmptyChild, kEmptyChild, kEmptyChild};
+  int id[kWide];
+  for (int q = 0; q < kWide; ++q) id[q] = kEmptyChild;
   int k = 2;
   {
     const int2 c = children[i];
     id[0] = c.x;
     id[1] = c.y;
   }
-  for (int round = 0; round < 2; ++round) {
+  for (int round = 0; round < kWide - 2; ++round) {
     int pick = -1;
     float best_area = -1.0f;
     for (int q = 0; q < k; ++q) {
@@ -280,9 +289,9 @@ __global__ void __launch_bounds__(256) k_emit_wide4(int n, const int2* __restric
     id[pick] = g.x;
     id[k++] = g.y;
   }
-  float lo[3][4], hi[3][4];
-  int code[4];
-  for (int q = 0; q < 4; ++q) {
+  float lo[3][kWide], hi[3][kWide];
+  int code[kWide];
+  for (int q = 0; q < kWide; ++q) {
     float4 b0 = make_float4(FLT_MAX, FLT_MAX, FLT_MAX, 0.0f), b1 = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, 0.0f);
     code[q] = kEmptyChild;
     if (id[q] != kEmptyChild) {
@@ -296,13 +305,16 @@ __global__ void __launch_bounds__(256) k_emit_wide4(int n, const int2* __restric
     lo[0][q] = b0.x; lo[1][q] = b0.y; lo[2][q] = b0.z;
     hi[0][q] = b1.x; hi[1][q] = b1.y; hi[2][q] = b1.z;
   }
-  float4* o = nodes + 8 * (size_t)i;
-  for (int a = 0; a < 3; ++a) {
-    o[2 * a] = make_float4(lo[a][0], lo[a][1], lo[a][2], lo[a][3]);
-    o[2 * a + 1] = make_float4(hi[a][0], hi[a][1], hi[a][2], hi[a][3]);
+  for (int h = 0; h < kWide / 4; ++h) {  // one 128-byte line per four slots
+    float4* o = nodes + kNodeF4 * (size_t)i + 8 * h;
+    const int q = 4 * h;
+    for (int a = 0; a < 3; ++a) {
+      o[2 * a] = make_float4(lo[a][q], lo[a][q + 1], lo[a][q + 2], lo[a][q + 3]);
+      o[2 * a + 1] = make_float4(hi[a][q], hi[a][q + 1], hi[a][q + 2], hi[a][q + 3]);
+    }
+    o[6] = make_float4(__int_as_float(code[q]), __int_as_float(code[q + 1]), __int_as_float(code[q + 2]), __int_as_float(code[q + 3]));
+    o[7] = make_float4(__int_as_float(k), 0.0f, 0.0f, 0.0f);  // children of the whole node (not read by the walk)
   }
-  o[6] = make_float4(__int_as_float(code[0]), __int_as_float(code[1]), __int_as_float(code[2]), __int_as_float(code[3]));
-  o[7] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 }
 
 // Reachability and depth of the wide tree, one level per launch: the nodes reached at `level` mark their
@@ -313,10 +325,12 @@ __global__ void __launch_bounds__(256) k_wide_levels(int n, const float4* __rest
                                                      TriBounds* info) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1 || wdepth[i] != level) return;
-  const float4 cf = nodes[8 * (size_t)i + 6];
-  const int ch[4] = {__float_as_int(cf.x), __float_as_int(cf.y), __float_as_int(cf.z), __float_as_int(cf.w)};
-  for (int k = 0; k < 4; ++k)
-    if (ch[k] >= 0 && ch[k] != kEmptyChild) wdepth[ch[k]] = level + 1;
+  for (int h = 0; h < kWide / 4; ++h) {
+    const float4 cf = nodes[kNodeF4 * (size_t)i + 8 * h + 6];
+    const int ch[4] = {__float_as_int(cf.x), __float_as_int(cf.y), __float_as_int(cf.z), __float_as_int(cf.w)};
+    for (int k = 0; k < 4; ++k)
+      if (ch[k] >= 0 && ch[k] != kEmptyChild) wdepth[ch[k]] = level + 1;
+  }
   atomicMax(&info->wide_depth, level);
 }
 
@@ -331,15 +345,17 @@ __global__ void __launch_bounds__(256) k_compact_nodes(int n, const float4* __re
                                                        const int* __restrict__ slot, float4* dst) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n - 1 || wdepth[i] == 0) return;
-  const float4* s = src + 8 * (size_t)i;
-  float4* d = dst + 8 * (size_t)slot[i];
-  for (int k = 0; k < 6; ++k) d[k] = s[k];
-  const float4 cf = s[6];
-  int ch[4] = {__float_as_int(cf.x), __float_as_int(cf.y), __float_as_int(cf.z), __float_as_int(cf.w)};
-  for (int k = 0; k < 4; ++k)
-    if (ch[k] >= 0 && ch[k] != kEmptyChild) ch[k] = slot[ch[k]];
-  d[6] = make_float4(__int_as_float(ch[0]), __int_as_float(ch[1]), __int_as_float(ch[2]), __int_as_float(ch[3]));
-  d[7] = s[7];
+  for (int h = 0; h < kWide / 4; ++h) {
+    const float4* s = src + kNodeF4 * (size_t)i + 8 * h;
+    float4* d = dst + kNodeF4 * (size_t)slot[i] + 8 * h;
+    for (int k = 0; k < 6; ++k) d[k] = s[k];
+    const float4 cf = s[6];
+    int ch[4] = {__float_as_int(cf.x), __float_as_int(cf.y), __float_as_int(cf.z), __float_as_int(cf.w)};
+    for (int k = 0; k < 4; ++k)
+      if (ch[k] >= 0 && ch[k] != kEmptyChild) ch[k] = slot[ch[k]];
+    d[6] = make_float4(__int_as_float(ch[0]), __int_as_float(ch[1]), __int_as_float(ch[2]), __int_as_float(ch[3]));
+    d[7] = s[7];
+  }
 }
 
 }  // namespace b2pt

@@ -44,12 +44,16 @@ constexpr int kWalkThreads = 256;
 #define B2PT_WALK_MINBLOCKS 3
 #endif
 constexpr int kWalkMinBlocks = B2PT_WALK_MINBLOCKS;  // resident CTAs per SM the register budget is set for
+#ifndef B2PT_WALK_SORT
+#define B2PT_WALK_SORT 5  // comparators of the child sort in a node step (5: full order; 3 / 4: experiments)
+#endif
 #ifndef B2PT_WALK_SHORT
-#define B2PT_WALK_SHORT 16
+#define B2PT_WALK_SHORT (B2PT_WIDE == 8 ? 20 : 16)
 #endif
 constexpr int kWalkShort = B2PT_WALK_SHORT;   // (node, tn) entries per lane in shared memory: deep enough that the
                                               // spill below is the exception (its code stays off the fast path)
-constexpr int kWalkSpill = 96 - kWalkShort;   // spill entries per lane: 96 in all = 3 per level of a 32-level wide tree
+constexpr int kWalkStackTotal = kWide == 8 ? 160 : 96;  // (kWide - 1) entries per level of the wide tree: 32 / 22 levels (checked at build time)
+constexpr int kWalkSpill = kWalkStackTotal - kWalkShort;   // spill entries per lane in local memory
 #ifndef B2PT_REFILL_MIN
 #define B2PT_REFILL_MIN 12
 #endif
@@ -363,38 +367,59 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkMinBlocks) k_mesh_walk(Isec
     if (node_step) {
       if (can_node) {
         if (STATS) ++s_nodes;
-        WideHit wh;
-        float4 cf;
-        wide_slab_fma(nodes + 8 * (size_t)node, offx, offy, offz, R.id, R.noid, R.lim, &wh, &cf);
-        float tn[4] = {wh.tn[0], wh.tn[1], wh.tn[2], wh.tn[3]};
-        int ch[4] = {wh.ok[0] ? __float_as_int(cf.x) : kEmptyChild, wh.ok[1] ? __float_as_int(cf.y) : kEmptyChild,
-                     wh.ok[2] ? __float_as_int(cf.z) : kEmptyChild, wh.ok[3] ? __float_as_int(cf.w) : kEmptyChild};
+        float tn[kWide];
+        int ch[kWide];
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (ch[k] == kEmptyChild) tn[k] = FLT_MAX;
+        for (int h = 0; h < kWide / 4; ++h) {  // the same four-slot box test on each 128-byte line of the node
+          WideHit wh;
+          float4 cf;
+          wide_slab_fma(nodes + kNodeF4 * (size_t)node + 8 * h, offx, offy, offz, R.id, R.noid, R.lim, &wh, &cf);
+          ch[4 * h + 0] = wh.ok[0] ? __float_as_int(cf.x) : kEmptyChild;
+          ch[4 * h + 1] = wh.ok[1] ? __float_as_int(cf.y) : kEmptyChild;
+          ch[4 * h + 2] = wh.ok[2] ? __float_as_int(cf.z) : kEmptyChild;
+          ch[4 * h + 3] = wh.ok[3] ? __float_as_int(cf.w) : kEmptyChild;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) tn[4 * h + k] = wh.ok[k] ? wh.tn[k] : FLT_MAX;
+        }
 #define B2PT_CSWAP(a, b)                                   \
   if (tn[b] < tn[a]) {                                     \
     const float tt = tn[a]; tn[a] = tn[b]; tn[b] = tt;     \
     const int cc = ch[a]; ch[a] = ch[b]; ch[b] = cc;       \
   }
-        B2PT_CSWAP(0, 1) B2PT_CSWAP(2, 3) B2PT_CSWAP(0, 2) B2PT_CSWAP(1, 3) B2PT_CSWAP(1, 2)
+        if (kWide == 4) {
+#if B2PT_WALK_SORT == 3   // nearest child only: the other hits go on the stack as they come
+          B2PT_CSWAP(0, 1) B2PT_CSWAP(2, 3) B2PT_CSWAP(0, 2)
+#elif B2PT_WALK_SORT == 4  // the two nearest in order
+          B2PT_CSWAP(0, 1) B2PT_CSWAP(2, 3) B2PT_CSWAP(0, 2) B2PT_CSWAP(1, 2)
+#else
+          B2PT_CSWAP(0, 1) B2PT_CSWAP(2, 3) B2PT_CSWAP(0, 2) B2PT_CSWAP(1, 3) B2PT_CSWAP(1, 2)
+#endif
+        } else {
+          // eight children: the nearest comes to slot 0 (seven comparators), the others keep their slot order -- a
+          // full sort is 19 comparators, and the model of the walk on the renderer's rays prices the missing
+          // order at +5 % steps (tools/exp_wide_leaf.c, EXP_UNSORTED)
+          B2PT_CSWAP(0, 1) B2PT_CSWAP(2, 3) B2PT_CSWAP(4 % kWide, 5 % kWide) B2PT_CSWAP(6 % kWide, 7 % kWide)
+          B2PT_CSWAP(0, 2) B2PT_CSWAP(4 % kWide, 6 % kWide) B2PT_CSWAP(0, 4 % kWide)
+        }
 #undef B2PT_CSWAP
         if (ch[0] != kEmptyChild) {
-          // nearest first; the others go on the stack farthest first.  With room for all three in shared memory
-          // (the rule) the pushes are three predicated stores; the spill path keeps the general form.
-          if (sp + 3 <= kWalkShort) {
-            const bool p3 = ch[3] != kEmptyChild, p2 = ch[2] != kEmptyChild, p1 = ch[1] != kEmptyChild;
+          // nearest first; the others go on the stack (farthest first when they are sorted).  With room for all of
+          // them in shared memory (the rule) the pushes are predicated stores; the spill path keeps the general form.
+          if (sp + (kWide - 1) <= kWalkShort) {
             int2* top = sst + sp * kWalkThreads;
-            if (p3) top[0] = make_int2(ch[3], __float_as_int(tn[3]));
-            top += p3 ? kWalkThreads : 0;
-            if (p2) top[0] = make_int2(ch[2], __float_as_int(tn[2]));
-            top += p2 ? kWalkThreads : 0;
-            if (p1) top[0] = make_int2(ch[1], __float_as_int(tn[1]));
-            sp += (p3 ? 1 : 0) + (p2 ? 1 : 0) + (p1 ? 1 : 0);
+            int pushed = 0;
+#pragma unroll
+            for (int k = kWide - 1; k >= 1; --k) {
+              const bool pk = ch[k] != kEmptyChild;
+              if (pk) top[0] = make_int2(ch[k], __float_as_int(tn[k]));
+              top += pk ? kWalkThreads : 0;
+              pushed += pk ? 1 : 0;
+            }
+            sp += pushed;
           } else {
-            if (ch[3] != kEmptyChild) B2PT_WALK_PUSH(ch[3], tn[3])
-            if (ch[2] != kEmptyChild) B2PT_WALK_PUSH(ch[2], tn[2])
-            if (ch[1] != kEmptyChild) B2PT_WALK_PUSH(ch[1], tn[1])
+#pragma unroll
+            for (int k = kWide - 1; k >= 1; --k)
+              if (ch[k] != kEmptyChild) B2PT_WALK_PUSH(ch[k], tn[k])
           }
           node = ch[0];
         } else {
@@ -489,7 +514,7 @@ constexpr int kCoopThreads = 128;
 #endif
 constexpr int kCoopGroup = B2PT_COOP_GROUP;
 constexpr int kCoopCap = 32 * kCoopGroup;                        // stack entries per group (32 KB per CTA in all)
-constexpr int kCoopDfs = kCoopCap - 96 - 3 * kCoopGroup;         // above this only one entry per round is taken
+constexpr int kCoopDfs = kCoopCap - kWalkStackTotal - (kWide - 1) * kCoopGroup;  // above this only one entry per round is taken
 constexpr unsigned int kCoopMask = kCoopGroup == 32 ? 0xffffffffu : ((1u << (kCoopGroup & 31)) - 1u);
 
 __global__ void __launch_bounds__(kCoopThreads) k_mesh_walk_long(IsectParams p) {
@@ -616,19 +641,27 @@ __global__ void __launch_bounds__(kCoopThreads) k_mesh_walk_long(IsectParams p) 
     }
     sp -= take;
     __syncwarp();
-    int ch[4] = {kEmptyChild, kEmptyChild, kEmptyChild, kEmptyChild};
-    float tn[4] = {FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX};
+    int ch[kWide];
+    float tn[kWide];
+#pragma unroll
+    for (int k = 0; k < kWide; ++k) {
+      ch[k] = kEmptyChild;
+      tn[k] = FLT_MAX;
+    }
     float t = -1.0f, u = 0.0f, v = 0.0f;
     int fid = 0x7fffffff;
     if (walk_is_inner(node)) {
-      WideHit wh;
-      float4 cf;
-      wide_slab_fma(nodes + 8 * (size_t)node, offx, offy, offz, R.id, R.noid, R.lim, &wh, &cf);
-      tn[0] = wh.tn[0]; tn[1] = wh.tn[1]; tn[2] = wh.tn[2]; tn[3] = wh.tn[3];
-      ch[0] = wh.ok[0] ? __float_as_int(cf.x) : kEmptyChild;
-      ch[1] = wh.ok[1] ? __float_as_int(cf.y) : kEmptyChild;
-      ch[2] = wh.ok[2] ? __float_as_int(cf.z) : kEmptyChild;
-      ch[3] = wh.ok[3] ? __float_as_int(cf.w) : kEmptyChild;
+#pragma unroll
+      for (int h = 0; h < kWide / 4; ++h) {
+        WideHit wh;
+        float4 cf;
+        wide_slab_fma(nodes + kNodeF4 * (size_t)node + 8 * h, offx, offy, offz, R.id, R.noid, R.lim, &wh, &cf);
+        tn[4 * h + 0] = wh.tn[0]; tn[4 * h + 1] = wh.tn[1]; tn[4 * h + 2] = wh.tn[2]; tn[4 * h + 3] = wh.tn[3];
+        ch[4 * h + 0] = wh.ok[0] ? __float_as_int(cf.x) : kEmptyChild;
+        ch[4 * h + 1] = wh.ok[1] ? __float_as_int(cf.y) : kEmptyChild;
+        ch[4 * h + 2] = wh.ok[2] ? __float_as_int(cf.z) : kEmptyChild;
+        ch[4 * h + 3] = wh.ok[3] ? __float_as_int(cf.w) : kEmptyChild;
+      }
     } else if (node < 0) {
       t = leaf_exact(tris, node, R.qo, R.qd, &u, &v, &fid);
     }
@@ -660,7 +693,7 @@ __global__ void __launch_bounds__(kCoopThreads) k_mesh_walk_long(IsectParams p) 
     // append the children that are still in front of the closest hit (segmented scan over the group)
     int cnt = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < kWide; ++k) {
       if (ch[k] != kEmptyChild && !(tn[k] <= R.lim)) ch[k] = kEmptyChild;
       cnt += ch[k] != kEmptyChild;
     }
@@ -673,7 +706,7 @@ __global__ void __launch_bounds__(kCoopThreads) k_mesh_walk_long(IsectParams p) 
     const int all = __shfl_sync(0xffffffffu, incl, kCoopGroup - 1, kCoopGroup);
     int w = sp + incl - cnt;
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
+    for (int k = 0; k < kWide; ++k)
       if (ch[k] != kEmptyChild) st[w++] = make_int2(ch[k], __float_as_int(tn[k]));
     sp += all;
     __syncwarp();

@@ -300,7 +300,7 @@ int main(int argc, char** argv) {
       emit_wide();
       char nm[64];
       snprintf(nm, sizeof nm, "W=%d L=%d", W, L);
-      sorted_order = 1;
+      sorted_order = getenv("EXP_UNSORTED") ? 0 : 1;  // EXP_UNSORTED=1: nearest child first, the other hits pushed in slot order
       per_walk(nm);
       per_warp("one wave, alternating", 1, 0);
       per_warp("one wave, fused step", 1, 1);
