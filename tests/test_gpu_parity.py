@@ -87,6 +87,23 @@ def test_larger_frames_bitexact(tmp_path, name, w, h):
     compare_iteration(pod, {}, iters=(1, 2, 7), what=f"{name} {w}x{h}")
 
 
+@pytest.mark.parametrize("name,optkw", [("cornell", {}), ("cornellGlass", {"depth_of_field": 1, "antialiasing": 1})])
+def test_baseline_configs_1_and_2_at_full_size(tmp_path, name, optkw):
+    """BASELINE.json configs[0] and configs[1] at their own size (800x800, depth 8; cornellGlass with DOF and
+    stochastic AA): image, albedo and live paths per depth after three iterations, bit for bit against the oracle's
+    whole-iteration path (640 000 paths per iteration: 313 sort tiles, the analytic rounds with every geom type)."""
+    pod = api.Scene(scenes.write_scene(name, str(tmp_path / "s.txt"), width=800, height=800)).pod
+    opt = abi.default_options(trig_mode=abi.TRIG_PORTABLE, **optkw)
+    with api.Renderer(pod, opt) as r:
+        r.render(1, 3, 1)
+        img, alb = r.read()
+        live = r.live_counts()
+    ref_img, ref_alb, ref_live, _seg = oracle.render(pod, opt, 1, 3, 1)
+    assert_same_bits(img, ref_img, f"{name} 800x800 image after 3 iterations")
+    assert_same_bits(alb, ref_alb, f"{name} 800x800 albedo")
+    assert list(live[: len(ref_live)]) == list(ref_live[: len(live)])
+
+
 def _mesh_scene(tmp_path, name, w, h, tris):
     root = assets.prepare(str(tmp_path / "run"), triangles=tris, procedural_size=256)
     return api.Scene(assets.scene_file(name, w, h, root=root)).pod
