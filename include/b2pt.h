@@ -566,6 +566,10 @@ typedef struct B2ptLoadOverrides {
 int b2pt_scene_load(const char* path, const B2ptLoadOverrides* ov, B2ptLoadedScene** out);
 const B2ptScene* b2pt_scene_view(const B2ptLoadedScene* s);
 const char* b2pt_scene_image_name(const B2ptLoadedScene* s); /* FILE line */
+/* What the loader tolerated the way the reference does instead of failing, one line each ("" if nothing): today the
+ * texture files an MTL names that are missing or cannot be decoded -- the reference prints "Failed to load ... texture
+ * file" and renders without the map (scene.cpp:150-154), and so does this library. */
+const char* b2pt_scene_warnings(const B2ptLoadedScene* s);
 void b2pt_scene_free(B2ptLoadedScene* s);
 
 /* ---- misc ------------------------------------------------------------------------- */

@@ -259,6 +259,7 @@ SYMBOLS = {
     "b2pt_scene_load": (C.c_int, [C.c_char_p, C.POINTER(LoadOverrides), C.POINTER(_vp)]),
     "b2pt_scene_view": (C.POINTER(Scene), [_vp]),
     "b2pt_scene_image_name": (C.c_char_p, [_vp]),
+    "b2pt_scene_warnings": (C.c_char_p, [_vp]),
     "b2pt_scene_free": (None, [_vp]),
     "b2pt_last_error": (C.c_char_p, []),
     "b2pt_abi_version": (C.c_int, []),

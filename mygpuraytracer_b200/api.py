@@ -112,10 +112,12 @@ class Scene:
             try:
                 pod = PodScene.from_ctypes(lib.b2pt_scene_view(h).contents)
                 name = lib.b2pt_scene_image_name(h).decode("utf-8", "replace")
+                warnings = [w for w in lib.b2pt_scene_warnings(h).decode("utf-8", "replace").splitlines() if w]
             finally:
                 lib.b2pt_scene_free(h)
         else:
-            name = "pod"
+            name, warnings = "pod", []
+        self.warnings = warnings  # what the loader tolerated like the reference does (missing / undecodable textures)
         self.pod = pod
         self.state = RenderState(pod, name)
 

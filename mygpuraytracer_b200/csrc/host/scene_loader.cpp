@@ -54,6 +54,7 @@ struct B2ptLoadedScene {
   B2ptScene view{};
   std::string image_name;
   std::string scene_dir;
+  std::string warnings;  // one line per thing the loader tolerated the way the reference does (b2pt_scene_warnings)
 };
 
 extern "C" const char* b2pt_last_error(void);
@@ -428,7 +429,11 @@ int load_obj(B2ptLoadedScene* S, const std::string& obj_path, const std::vector<
     std::string tp = find_file(name, tex_dirs);
     LoadedTexture t;
     if (tp.empty() || !decode_image_file(tp, /*flip_vertically=*/true, &t.w, &t.h, &t.c, &t.texels)) {
-      // "Failed to load ... texture file": the reference pushes an empty Texture (scene.cpp:150-154)
+      // "Failed to load ... texture file": the reference pushes an empty Texture (scene.cpp:150-154) and prints
+      // the name; here the slot stays empty and the name goes to b2pt_scene_warnings()
+      S->warnings += "texture '" + name + "' " + (tp.empty() ? "not found" : "could not be decoded (" + tp + ")") +
+                     ": the map is left empty, as in the reference\n";
+      tex_cache[name] = -1;
       return -1;
     }
     S->tex_store.push_back(std::move(t));
@@ -682,4 +687,5 @@ extern "C" int b2pt_scene_load(const char* path, const B2ptLoadOverrides* ov, B2
 
 extern "C" const B2ptScene* b2pt_scene_view(const B2ptLoadedScene* s) { return s ? &s->view : nullptr; }
 extern "C" const char* b2pt_scene_image_name(const B2ptLoadedScene* s) { return s ? s->image_name.c_str() : ""; }
+extern "C" const char* b2pt_scene_warnings(const B2ptLoadedScene* s) { return s ? s->warnings.c_str() : ""; }
 extern "C" void b2pt_scene_free(B2ptLoadedScene* s) { delete s; }

@@ -305,12 +305,20 @@ def test_png_decoder_rejects_damaged_files(tmp_path):
         cases.append(bytes(b))
     for blob in cases:
         (tmp_path / "textures" / "bad.png").write_bytes(blob)
-        pod = api.Scene(path).pod
+        sc = api.Scene(path)
+        pod = sc.pod
         # a texture that does not load leaves the geom without one, like the reference ("Failed to load Kd
         # texture file", scene.cpp:150-154); a flipped bit in the pixel data may still decode: then the shape holds
         assert len(pod.textures) == 0 or pod.textures[0].shape == (71, 93, 3)
         if len(pod.textures) == 0:
             assert int(pod.geoms["tex_kd"][6]) == -1
+            # ... and the loader says so (b2pt_scene_warnings), as the reference prints the name
+            assert len(sc.warnings) == 1 and "bad.png" in sc.warnings[0] and "could not be decoded" in sc.warnings[0]
+        else:
+            assert sc.warnings == []
+    os.remove(tmp_path / "textures" / "bad.png")
+    sc = api.Scene(path)
+    assert len(sc.pod.textures) == 0 and len(sc.warnings) == 1 and "not found" in sc.warnings[0]
 
 
 def test_jpeg_decoder_matches_reference_texels():
