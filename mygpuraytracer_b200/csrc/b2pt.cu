@@ -180,6 +180,7 @@ struct B2ptCtx {
   uint8_t *fb_key = nullptr, *fb_live = nullptr;
   unsigned int* fb_hist = nullptr;  // [2][kMaxMaterials]: hist[0], hist_live[0] of the cached depth
   int walk_grid = 0, finish_grid = 0, long_grid = 0, long_walk = 24;
+  int long_lanes = 32;  // lanes per long walk: 32 alone, 16 when contexts share the SMs (B2PT_LONG_LANES)
   int2* long_queue = nullptr;
   float4* long_best = nullptr;
   int2* long_stack = nullptr;
@@ -818,7 +819,7 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
   c->finish_grid = c->sm_count * 8;
   c->shade_stride_grid = c->sm_count * 12;
   c->gen_trace_grid = (int)std::min<size_t>((P + 255) / 256, (size_t)c->sm_count * 8);
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mesh_walk_long, kCoopThreads, 0));
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mesh_walk_long<32>, kCoopThreads, 0));
   c->long_grid = c->sm_count * std::max(occ, 1);
   // the fused kernels shorten the chain of one context (1.435 -> 1.39 ms) but cost 2 % of aggregate throughput
   // when several contexts share the GPU (their two phases serialise inside a CTA)
@@ -834,6 +835,7 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
     // and fill each other's tails (measured: 4 contexts, 1.18 -> 1.03 ms per iteration in aggregate)
     c->analytic_grid = std::min(c->analytic_grid, c->sm_count * 2);
     c->walk_grid = c->sm_count;
+    c->long_lanes = 16;
     c->long_walk = 32;  // with the SMs shared, throughput counts, not the length of the launch: 24 -> 32 steps is -1.4 % per iteration
     c->long_grid = c->sm_count * 2;
     c->finish_grid = c->sm_count * 2;
@@ -841,6 +843,7 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
   }
   // experiment knobs: resident CTAs per SM of the persistent / grid-stride kernels
   if (const char* e = getenv("B2PT_LONG_WALK")) c->long_walk = std::max(atoi(e), 1);
+  if (const char* e = getenv("B2PT_LONG_LANES")) c->long_lanes = atoi(e) == 16 ? 16 : 32;
   if (const char* e = getenv("B2PT_WALK_CTAS")) c->walk_grid = c->sm_count * std::max(1, std::min(atoi(e), walk_occ));
   if (const char* e = getenv("B2PT_LONG_CTAS")) c->long_grid = c->sm_count * std::max(1, atoi(e));
   if (const char* e = getenv("B2PT_ANALYTIC_CTAS")) c->analytic_grid = c->sm_count * std::max(1, atoi(e));
@@ -1053,7 +1056,10 @@ static int enqueue_iteration(B2ptCtx* c, bool record, bool time_loop, bool captu
           else
             k_mesh_walk<false><<<c->walk_grid, kWalkThreads, 0, s>>>(ip);
           if (kt) kt->mark(5);
-          k_mesh_walk_long<<<c->long_grid, kCoopThreads, 0, s>>>(ip);
+          if (c->long_lanes == 32)
+            k_mesh_walk_long<32><<<c->long_grid, kCoopThreads, 0, s>>>(ip);
+          else
+            k_mesh_walk_long<16><<<c->long_grid, kCoopThreads, 0, s>>>(ip);
           if (kt) kt->mark(6);
           k_mesh_finish<<<c->finish_grid, 256, 0, s>>>(ip);
           c->launches += 3;

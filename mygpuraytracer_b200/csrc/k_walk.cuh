@@ -509,15 +509,15 @@ __global__ void __launch_bounds__(kWalkThreads, kWalkMinBlocks) k_mesh_walk(Isec
 // warp-uniform: the groups of a warp run their rounds in lockstep and refill independently.  When the mesh a ray
 // came with is done, the group folds the result and walks the ray's remaining meshes from their roots.
 constexpr int kCoopThreads = 128;
-#ifndef B2PT_COOP_GROUP
-#define B2PT_COOP_GROUP 16
-#endif
-constexpr int kCoopGroup = B2PT_COOP_GROUP;
-constexpr int kCoopCap = 32 * kCoopGroup;                        // stack entries per group (32 KB per CTA in all)
-constexpr int kCoopDfs = kCoopCap - kWalkStackTotal - (kWide - 1) * kCoopGroup;  // above this only one entry per round is taken
-constexpr unsigned int kCoopMask = kCoopGroup == 32 ? 0xffffffffu : ((1u << (kCoopGroup & 31)) - 1u);
-
+// Lanes per long walk: 16 when several contexts share the SMs (two rays per warp), 32 when a context has the GPU to
+// itself -- there a launch ends with its longest walk, and a whole warp per ray shortens it (long walks 0.277 ->
+// 0.250 ms per iteration full-width; with four contexts 32 lanes cost 1 % of the aggregate).  kCoopGroup is the
+// template argument of the kernel; the constants below depend on it.
+template <int kCoopGroup>
 __global__ void __launch_bounds__(kCoopThreads) k_mesh_walk_long(IsectParams p) {
+  constexpr int kCoopCap = 32 * kCoopGroup;                                           // stack entries per group (32 KB per CTA in all)
+  constexpr int kCoopDfs = kCoopCap - kWalkStackTotal - (kWide - 1) * kCoopGroup;     // above this only one entry per round is taken
+  constexpr unsigned int kCoopMask = kCoopGroup == 32 ? 0xffffffffu : ((1u << (kCoopGroup & 31)) - 1u);
   __shared__ int2 cstack[(kCoopThreads / kCoopGroup) * kCoopCap];
   const int lane = threadIdx.x & 31;
   const int gl = lane & (kCoopGroup - 1);           // lane within the group

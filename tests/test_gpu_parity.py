@@ -250,8 +250,10 @@ def test_first_bounce_cache_changes_nothing(tmp_path, scene_kind):
 
 
 @pytest.mark.parametrize("env", [
-    {"B2PT_LONG_WALK": "1"},                              # every walk finishes in the cooperative kernel
+    {"B2PT_LONG_WALK": "1"},                              # every walk finishes in the cooperative kernel (32 lanes per ray)
+    {"B2PT_LONG_WALK": "1", "B2PT_LONG_LANES": "16"},     # ... in its 16-lane form (what contexts that share the SMs run)
     {"B2PT_LONG_WALK": "3", "B2PT_LONG_CARRY": "0"},      # ... restarting at the root, pruned by the carried hit
+    {"B2PT_LONG_WALK": "3", "B2PT_LONG_CARRY": "0", "B2PT_LONG_LANES": "16"},
     {"B2PT_LONG_WALK": "2", "B2PT_LONG_CAP": "64"},       # hand-off queue full: lanes keep walking
     {"B2PT_LONG_WALK": "1000000"},                        # no hand-off at all
 ])
