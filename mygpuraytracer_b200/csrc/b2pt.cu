@@ -106,6 +106,7 @@ struct MeshBuild {
   int wide_depth = 0;  // inner wide nodes on the longest root-to-leaf path
   float* face_pos = nullptr;
   float* face_uv = nullptr;
+  float4* face_rec = nullptr;
   size_t bvh_bytes = 0;
   B2ptBvhInfo info{};
 };
@@ -374,6 +375,9 @@ static int build_mesh(B2ptCtx* c, const float* pos_host, const float* uv_host, i
   if ((rc = c->dalloc(&out->face_uv, (size_t)n * 6))) return rc;
   CK(cudaMemcpyAsync(out->face_pos, pos_host, (size_t)n * 36, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(out->face_uv, uv_host, (size_t)n * 24, cudaMemcpyHostToDevice, s));
+  if ((rc = c->dalloc(&out->face_rec, (size_t)n * 4))) return rc;
+  k_face_records<<<(n + 255) / 256, 256, 0, s>>>(out->face_pos, out->face_uv, n, out->face_rec);
+  c->launches += 1;
   out->info.n_faces = n;
 
   // pad: a few 1e-6 of the mesh extent (host pass over the positions)
@@ -690,6 +694,7 @@ static int create_impl(const B2ptScene* sc, const B2ptOptions* opt_in, B2ptCtx* 
       M.tris = mb.tris;
       M.face_pos = mb.face_pos;
       M.face_uv = mb.face_uv;
+      M.face_rec = mb.face_rec;
       M.n_faces = G.face_count;
       M.root = mb.root;
       M.geom = g;

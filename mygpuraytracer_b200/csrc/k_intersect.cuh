@@ -167,13 +167,13 @@ __device__ __forceinline__ bool may_beat(const DevGeom& G, V3 id, V3 noid, float
 // (apps/src/intersections.h:226,235-279).
 __device__ __forceinline__ void mesh_record(const DevGeom& G, const DevMesh& M, const DevTexture& bump, int face, float bu,
                                             float bv, V3* nrm_out, float* tu_out, float* tv_out) {
-  const float* fp = M.face_pos + 9 * (size_t)face;
-  const float* fu = M.face_uv + 6 * (size_t)face;
-  const V3 v0 = mk(__ldg(fp), __ldg(fp + 1), __ldg(fp + 2));
-  const V3 v1 = mk(__ldg(fp + 3), __ldg(fp + 4), __ldg(fp + 5));
-  const V3 v2 = mk(__ldg(fp + 6), __ldg(fp + 7), __ldg(fp + 8));
-  const float u0x = __ldg(fu), u0y = __ldg(fu + 1), u1x = __ldg(fu + 2), u1y = __ldg(fu + 3);
-  const float u2x = __ldg(fu + 4), u2y = __ldg(fu + 5);
+  const float4* fr = M.face_rec + 4 * (size_t)face;
+  const float4 r0 = __ldg(fr), r1 = __ldg(fr + 1), r2 = __ldg(fr + 2), r3 = __ldg(fr + 3);
+  const V3 v0 = mk(r0.x, r0.y, r0.z);
+  const V3 v1 = mk(r0.w, r1.x, r1.y);
+  const V3 v2 = mk(r1.z, r1.w, r2.x);
+  const float u0x = r2.y, u0y = r2.z, u1x = r2.w, u1y = r3.x;
+  const float u2x = r3.y, u2y = r3.z;
   const float w = 1 - bu - bv;
   const float tu = (w * u0x + bu * u1x) + bv * u2x;
   const float tv = (w * u0y + bu * u1y) + bv * u2y;

@@ -223,6 +223,19 @@ __global__ void __launch_bounds__(256) k_tree_depth(int n, const int* __restrict
   atomicMax(&info->max_depth, depth);
 }
 
+// The 15 floats of a face (positions, texture coordinates) as one aligned 64-byte record (DevMesh::face_rec).
+__global__ void __launch_bounds__(256) k_face_records(const float* __restrict__ face_pos, const float* __restrict__ face_uv, int n,
+                                                      float4* rec) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = face_pos + 9 * (size_t)i;
+  const float* u = face_uv + 6 * (size_t)i;
+  rec[4 * (size_t)i + 0] = make_float4(p[0], p[1], p[2], p[3]);
+  rec[4 * (size_t)i + 1] = make_float4(p[4], p[5], p[6], p[7]);
+  rec[4 * (size_t)i + 2] = make_float4(p[8], u[0], u[1], u[2]);
+  rec[4 * (size_t)i + 3] = make_float4(u[3], u[4], u[5], 0.0f);
+}
+
 // ---- 4-wide traversal nodes with fat leaves -----------------------------------------------------------
 // child ids:  >= 0 (and < kEmptyChild)  inner node index
 //             kEmptyChild               unused slot

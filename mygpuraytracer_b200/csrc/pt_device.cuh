@@ -60,8 +60,11 @@ struct DevGeom {
 struct DevMesh {
   const float4* nodes;    // 8 x float4 (one 128-byte line) per 4-wide BVH node, child-major (see k_lbvh.cuh)
   const float4* tris;     // 3 x float4 per triangle in BVH leaf (Morton) order: (v0,face) (v1,-) (v2,-)
-  const float* face_pos;  // 9 floats per face, original order
+  const float* face_pos;  // 9 floats per face, original order (the LBVH build and the brute-force validation kernel)
   const float* face_uv;   // 6 floats per face, original order
+  const float4* face_rec; // the same 15 floats per face in ONE aligned 64-byte record (v0 v1 v2 | uv0 uv1 uv2 | pad): what
+                          // the winner of a walk gathers -- two sectors and four 128-bit loads instead of 15 scalar loads
+                          // over up to five sectors
   int n_faces;
   int root;  // 0: the root node; < 0: a leaf code (a mesh of at most kLeafTris triangles has no nodes)
   int geom;  // the geom this mesh belongs to (meshes are numbered in geom order)
