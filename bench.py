@@ -55,8 +55,8 @@ if ROOT not in sys.path:
 # algorithmic bytes of that same launch, not with the average launch.
 TRAFFIC_SOURCE = "profiles/r02_ncu_depth1_shared.md (depth-1 launches, shared-SM grids); fused kernels: profiles/r01_final_ncu_depth01.md"
 TRAFFIC = {
-    "k_intersect_analytic": 32.63e6, "k_mesh_walk": 31.10e6, "k_mesh_walk_long": 8.67e6, "k_mesh_finish": 53.14e6,
-    "k_sort_material": 1.99e6, "k_shade_compact": 169.11e6, "k_shade_trace": 197.83e6, "k_generate_trace": 123.39e6,
+    "k_intersect_analytic": 32.02e6, "k_mesh_walk": 30.58e6, "k_mesh_walk_long": 8.67e6, "k_mesh_finish": 49.18e6,
+    "k_sort_material": 1.99e6, "k_shade_compact": 170.02e6, "k_shade_trace": 197.83e6, "k_generate_trace": 123.39e6,
 }
 TRAFFIC_DEPTH = 1
 # Warp instructions of ONE iteration per kernel (ncu smsp__inst_executed.sum summed over the 8 depths, lanes per
@@ -66,8 +66,8 @@ TRAFFIC_DEPTH = 1
 # capacity of the GPU (SMs x 4 schedulers x SM clock).
 INST_SOURCE = "profiles/r02_inst_per_kernel.md (end of round 2)"
 INST_PER_STEP = {  # kernel: (million warp instructions, active lanes per instruction)
-    "k_intersect_analytic": (183.06, 20.7), "k_mesh_walk": (166.54, 14.1), "k_mesh_walk_long": (26.71, 17.3),
-    "k_mesh_finish": (20.78, 12.6), "k_sort_material": (17.62, 30.7), "k_shade_compact": (50.60, 30.3), "k_generate": (9.06, 32.0),
+    "k_intersect_analytic": (183.06, 20.7), "k_mesh_walk": (164.00, 14.1), "k_mesh_walk_long": (26.32, 17.8),
+    "k_mesh_finish": (20.43, 12.5), "k_sort_material": (17.58, 30.7), "k_shade_compact": (50.60, 30.3), "k_generate": (9.06, 32.0),
 }
 
 METRIC = "Mpaths/s"
